@@ -1,0 +1,143 @@
+"""ctypes binding of the CPU oracle (TEST INFRASTRUCTURE -- never imported by rrtmg_lw_b200).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  Arrays are numpy float64 in the reference's Fortran layout seen from C
+(``(nlay, ncol)`` row-major == Fortran ``(ncol, nlay)``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "liborc.so")
+_STATIC = os.path.join(os.path.dirname(_HERE), "rrtmg_lw_b200", "data", "lw_static_tables.bin")
+
+_lib = None
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+def build(force: bool = False):
+    if force or not os.path.exists(_LIB):
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB)
+        _lib.orc_get_table.restype = C.c_long
+    return _lib
+
+
+def _p(a):
+    if a is None:
+        return None
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"], (a.dtype, a.flags)
+    return a.ctypes.data_as(_dp)
+
+
+def ini(kdata_blob: np.ndarray, cpdair: float = 1004.0, default_real_kind: int = 4):
+    st = np.fromfile(_STATIC, dtype="<f8")
+    rc = lib().orc_ini(C.c_double(cpdair), _p(st), _p(np.ascontiguousarray(kdata_blob)), C.c_int(default_real_kind))
+    assert rc == 0, rc
+
+
+def _np(t):
+    if t is None:
+        return None
+    if hasattr(t, "detach"):
+        t = t.detach().cpu().numpy()
+    return np.ascontiguousarray(t, dtype=np.float64)
+
+
+def rrtmg_lw(b, icld=0, idrv=0, inflglw=0, iceflglw=0, liqflglw=0, mc=None, nthreads=1):
+    """Run the oracle on a synth.Batch.  mc = dict(cldfmcl, taucmcl, ciwpmcl, clwpmcl, reicmcl, relqmcl)
+    with the (nlay, ncol, 140) / (nlay, ncol) layouts.  Returns dict of outputs + rc + icld."""
+    ncol, nlay = b.ncol, b.nlay
+    z3 = np.zeros((nlay, ncol, 140)) if (mc is None and icld > 0) else None
+    z2 = np.zeros((nlay, ncol)) if (mc is None and icld > 0) else None
+    m = mc or dict(cldfmcl=z3, taucmcl=z3, ciwpmcl=z3, clwpmcl=z3, reicmcl=z2, relqmcl=z2)
+    if icld == 0 and mc is None:
+        dummy3 = np.zeros((1,)); dummy2 = np.zeros((1,))
+        m = dict(cldfmcl=dummy3, taucmcl=dummy3, ciwpmcl=dummy3, clwpmcl=dummy3, reicmcl=dummy2, relqmcl=dummy2)
+    out = {k: np.zeros((nlay + 1, ncol)) for k in ("uflx", "dflx", "uflxc", "dflxc", "duflx_dt", "duflxc_dt")}
+    out["hr"] = np.zeros((nlay, ncol)); out["hrc"] = np.zeros((nlay, ncol))
+    ic = C.c_int(icld)
+    keep = [_np(x) for x in (b.play, b.plev, b.tlay, b.tlev, b.tsfc, b.h2ovmr, b.o3vmr, b.co2vmr, b.ch4vmr, b.n2ovmr,
+                             b.o2vmr, b.cfc11vmr, b.cfc12vmr, b.cfc22vmr, b.ccl4vmr, b.emis)]
+    mk = [_np(m[k]) for k in ("cldfmcl", "taucmcl", "ciwpmcl", "clwpmcl", "reicmcl", "relqmcl")]
+    ta = _np(b.tauaer)
+    rc = lib().orc_rrtmg_lw(ncol, ncol, nlay, C.byref(ic), idrv, *[_p(x) for x in keep], inflglw, iceflglw, liqflglw,
+                            *[_p(x) for x in mk], _p(ta), _p(out["uflx"]), _p(out["dflx"]), _p(out["hr"]),
+                            _p(out["uflxc"]), _p(out["dflxc"]), _p(out["hrc"]), _p(out["duflx_dt"]),
+                            _p(out["duflxc_dt"]), nthreads)
+    out["rc"] = rc
+    out["icld"] = ic.value
+    return out
+
+
+def column_stages(b, icol, icld=0, idrv=0, inflglw=0, iceflglw=0, liqflglw=0, mc=None):
+    ncol, nlay = b.ncol, b.nlay
+    d = np.zeros((1,))
+    m = mc or dict(cldfmcl=d, taucmcl=d, ciwpmcl=d, clwpmcl=d, reicmcl=d, relqmcl=d)
+    keep = [_np(x) for x in (b.play, b.plev, b.tlay, b.tlev, b.tsfc, b.h2ovmr, b.o3vmr, b.co2vmr, b.ch4vmr, b.n2ovmr,
+                             b.o2vmr, b.cfc11vmr, b.cfc12vmr, b.cfc22vmr, b.ccl4vmr, b.emis)]
+    mk = [_np(m[k]) for k in ("cldfmcl", "taucmcl", "ciwpmcl", "clwpmcl", "reicmcl", "relqmcl")]
+    ta = _np(b.tauaer)
+    ints6 = np.zeros((nlay, 6), dtype=np.int32)
+    facs = np.zeros((nlay, 4))
+    taug = np.zeros((140, nlay)); fracs = np.zeros((140, nlay))
+    itr = np.zeros((140, nlay, 2), dtype=np.int32)
+    scal = np.zeros(2)
+    rc = lib().orc_column_stages(icol, ncol, ncol, nlay, icld, idrv, *[_p(x) for x in keep], inflglw, iceflglw,
+                                 liqflglw, *[_p(x) for x in mk], _p(ta), ints6.ctypes.data_as(_ip), _p(facs),
+                                 _p(taug), _p(fracs), itr.ctypes.data_as(_ip), _p(scal))
+    return dict(rc=rc, ints6=ints6, facs=facs, taug=taug, fracs=fracs, itr=itr, laytrop=int(scal[0]), pwvcm=scal[1])
+
+
+def mcica_subcol_lw(b, icld, permuteseed=1, irng=0, alpha=None):
+    """Oracle sub-column generator on a synth.Batch; returns the McICA dict for rrtmg_lw()."""
+    ncol, nlay = b.ncol, b.nlay
+    o3 = {k: np.zeros((nlay, ncol, 140)) for k in ("cldfmcl", "ciwpmcl", "clwpmcl", "taucmcl")}
+    o2 = {k: np.zeros((nlay, ncol)) for k in ("reicmcl", "relqmcl")}
+    ir = C.c_int(irng)
+    al = _np(alpha) if alpha is not None else np.zeros((nlay, ncol))
+    args = [_np(x) for x in (b.play, b.cldfrac, b.ciwp, b.clwp, b.rei, b.rel, b.tauc)]
+    rc = lib().orc_mcica_subcol_lw(ncol, ncol, nlay, icld, permuteseed, C.byref(ir), *[_p(x) for x in args], _p(al),
+                                   _p(o3["cldfmcl"]), _p(o3["ciwpmcl"]), _p(o3["clwpmcl"]), _p(o2["reicmcl"]),
+                                   _p(o2["relqmcl"]), _p(o3["taucmcl"]))
+    d = dict(o3); d.update(o2); d["rc"] = rc; d["irng"] = ir.value
+    return d
+
+
+def get_alpha(b, icld, idcor=0, decorr_con=2500.0, juldat=1):
+    alpha = np.zeros((b.nlay, b.ncol))
+    rc = lib().orc_get_alpha(b.ncol, b.ncol, b.nlay, icld, idcor, C.c_double(decorr_con), _p(_np(b.dz)),
+                             _p(_np(b.lat)), juldat, _p(_np(b.cldfrac)), _p(alpha))
+    assert rc == 0
+    return alpha
+
+
+def mt_stream(seed, n):
+    ints = np.zeros(n, dtype=np.uint32); reals = np.zeros(n)
+    lib().orc_mt_stream(seed, n, ints.ctypes.data_as(C.POINTER(C.c_uint)), _p(reals))
+    return ints, reals
+
+
+def kiss_stream(seeds, n):
+    reals = np.zeros(n); st = np.zeros(4, dtype=np.int32)
+    lib().orc_kiss_stream(*[int(s) for s in seeds], n, _p(reals), st.ctypes.data_as(_ip))
+    return reals, st
+
+
+def get_table(name):
+    n = lib().orc_get_table(name.encode(), None, 0)
+    out = np.zeros(n)
+    lib().orc_get_table(name.encode(), _p(out), n)
+    return out

@@ -1,0 +1,143 @@
+// orc_common.h -- shared state of the CPU ORACLE (test infrastructure only).
+//
+// The oracle is a plain C++ restatement of the reference's Fortran algorithm for the
+// rrtmg_lw hot path.  It exists to CHECK the CUDA product; nothing under
+// rrtmg_lw_b200/ may include, link or call it.  Only tests/, __graft_entry__.smoke()
+// and bench.py's cpu_baseline / --impl reference legs use it.
+//
+// PARITY STATUS: the reference's own Fortran cannot be built here (no Fortran
+// compiler in the image) and its k-distribution data (src/rrtmg_lw_k_g.f90,
+// data/rrtmg_lw.nc) are missing from the mount, so this oracle is pinned only by
+// the data-independent known answers of the reference (Planck surface fluxes of
+// the 4 standard atmospheres in run_examples_std_atm/output_rrtm_*, the MT19937
+// test vector, structural sums of the g-point reduction maps, closed-form lookup
+// tables).  For every k-dependent quantity: "parity unpinned" -- see DESIGN.md.
+//
+// Module-level state mirrors modules/rrlw_*.f90 of the reference.
+#ifndef ORC_COMMON_H
+#define ORC_COMMON_H
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace orc {
+
+constexpr int NBND = 16;    // nbndlw  modules/parrrtm.f90:35
+constexpr int NGPT = 140;   // ngptlw  modules/parrrtm.f90:36
+constexpr int MG = 16;      // mg      modules/parrrtm.f90:34
+constexpr int NTBL = 10000; // ntbl    modules/rrlw_tbl.f90:34
+
+// one spectral band's REDUCED tables (modules/rrlw_kgNN.f90, the non-"o" arrays)
+struct Band {
+    int ng = 0;  // ngc(band)
+    std::map<std::string, std::vector<double>> arr;  // reduced arrays by reference name
+    std::map<std::string, int> lead;                 // leading extent of each
+    const double* a(const char* n) const {
+        auto it = arr.find(n);
+        return it == arr.end() ? nullptr : it->second.data();
+    }
+};
+
+struct State {
+    bool inited = false;
+    int drk = 4;  // default real kind of the Fortran build being restated (4: plain gfortran, 8: -r8)
+    // rrlw_con
+    double grav, planck, boltz, clight, avogad, alosmt, gascon, radcn1, radcn2, sbcnst, secdy;
+    double heatfac, fluxfac, oneminus, pi;
+    // rrlw_wvn
+    double delwave[NBND];
+    int ng[NBND], nspa[NBND], nspb[NBND];
+    int ngc[NBND], ngs[NBND], ngn[NGPT], ngb[NGPT], ngm[NBND * MG];
+    double wt[MG], rwgt[NBND * MG];
+    // rrlw_ref  (1-based access through helpers below)
+    double pref[59], preflog[59], tref[59], chi_mls[7 * 59];
+    // Planck tables
+    double totplnk[181 * 16], totplk16[181], totplnkderiv[181 * 16], totplk16deriv[181];
+    // rrlw_cld
+    double abscld1, absice0[2], absice1[2 * 5], absice2[43 * 16], absice3[46 * 16], absliq0, absliq1[58 * 16];
+    // rrlw_tbl
+    double tau_tbl[NTBL + 1], exp_tbl[NTBL + 1], tfn_tbl[NTBL + 1], bpade;
+    Band band[NBND];
+
+    double chi(int sp, int lev) const { return chi_mls[(sp - 1) + 7 * (lev - 1)]; }
+    double tp(int it, int ib) const { return totplnk[(it - 1) + 181 * (ib - 1)]; }
+    double tpd(int it, int ib) const { return totplnkderiv[(it - 1) + 181 * (ib - 1)]; }
+};
+
+extern State G;
+
+// A default-kind REAL literal of the Fortran source: float32-rounded when the
+// build being restated is plain gfortran (drk == 4), exact under -r8.  SURVEY T1.
+inline double lit(double x) { return G.drk == 4 ? (double)(float)x : x; }
+
+// per-column work arrays (the locals of rrtmg_lw, src/rrtmg_lw_rad.f90:349-446); 1-based layers
+struct Column {
+    int nlayers = 0;
+    std::vector<double> pavel, tavel, pz, tz, coldry, wbrodl;
+    std::vector<double> wkl;  // (7, nlayers)  only the 7 used species
+    std::vector<double> wx;   // (4, nlayers)
+    double tbound = 0, pwvcm = 0;
+    double semiss[NBND];
+    std::vector<double> taua;  // (nlayers, 16)
+    int inflag = 0, iceflag = 0, liqflag = 0;
+    std::vector<double> cldfmc, taucmc, ciwpmc, clwpmc;  // (140, nlayers)
+    std::vector<double> reicmc, relqmc;
+    // setcoef outputs
+    int laytrop = 0;
+    std::vector<int> jp, jt, jt1, indself, indfor, indminor;
+    std::vector<double> planklay, planklev;  // (nlayers,16), (0:nlayers,16)
+    double plankbnd[NBND], dplankbnd_dt[NBND];
+    std::vector<double> colh2o, colco2, colo3, coln2o, colco, colch4, colo2, colbrd;
+    std::vector<double> fac00, fac01, fac10, fac11;
+    std::vector<double> rat_h2oco2, rat_h2oco2_1, rat_h2oo3, rat_h2oo3_1, rat_h2on2o, rat_h2on2o_1,
+        rat_h2och4, rat_h2och4_1, rat_n2oco2, rat_n2oco2_1, rat_o3co2, rat_o3co2_1;
+    std::vector<double> selffac, selffrac, forfac, forfrac, minorfrac, scaleminor, scaleminorn2;
+    // taumol outputs
+    std::vector<double> fracs, taug, taut;  // (nlayers, 140)
+    int ncbands = 0;
+    // rtrnmc outputs (0:nlayers)
+    std::vector<double> totuflux, totdflux, fnet, htr, totuclfl, totdclfl, fnetc, htrc, dtotuflux_dt, dtotuclfl_dt;
+    std::vector<int> itr_dump;  // optional: table indices (nlayers,140,2) for bit-exact checks
+
+    void resize(int nl);
+    // accessors, 1-based
+    double& WKL(int m, int l) { return wkl[(m - 1) + 7 * (l - 1)]; }
+    double& WX(int m, int l) { return wx[(m - 1) + 4 * (l - 1)]; }
+    double& TAUA(int l, int b) { return taua[(l - 1) + nlayers * (b - 1)]; }
+    double& CLD(std::vector<double>& v, int ig, int l) { return v[(ig - 1) + NGPT * (l - 1)]; }
+    double& PLAY(int l, int b) { return planklay[(l - 1) + nlayers * (b - 1)]; }
+    double& PLEV(int l, int b) { return planklev[l + (nlayers + 1) * (b - 1)]; }
+    double& LG(std::vector<double>& v, int l, int ig) { return v[(l - 1) + nlayers * (ig - 1)]; }
+};
+
+// status codes shared by oracle entry points (mirror the reference's STOP sites)
+enum {
+    ORC_OK = 0,
+    ORC_ERR_FLAG = 1,
+    ORC_ERR_ICE_RADIUS = 2,
+    ORC_ERR_LIQ_RADIUS = 3,
+    ORC_ERR_KISS_PRESSURE = 4,
+    ORC_ERR_NOT_INIT = 6
+};
+
+void setcoef(Column& c, int istart, int idrv);
+void taumol(Column& c);
+int cldprmc(Column& c);
+void rtrnmc(Column& c, int istart, int iend, int iout, int idrv, bool dump_itr);
+
+// Mersenne Twister (src/mcica_random_numbers.f90)
+struct MT {
+    int32_t state[624];
+    int cur;
+    void seed(int32_t s);
+    int32_t next_int();
+    double next_real();
+};
+void kiss(int32_t& s1, int32_t& s2, int32_t& s3, int32_t& s4, double& r);
+
+}  // namespace orc
+#endif
