@@ -1,0 +1,142 @@
+/* rrtmg_lw_b200.h -- C ABI of the B200-native RRTMG_LW longwave hot path.
+ *
+ * These are the entry points a thin ISO_C_BINDING shim binds behind the reference's
+ * UNCHANGED Fortran GCM interface (fortran/rrtmg_lw_b200_shim.f90):
+ *
+ *   reference interface (file:line under the reference tree)          C entry point
+ *   ---------------------------------------------------------------  ------------------------------
+ *   rrtmg_lw_ini(cpdair)            src/rrtmg_lw_init.f90:47          rrtmg_lw_b200_ini
+ *   rrtmg_lw(ncol,nlay,icld,...)    src/rrtmg_lw_rad.f90:99-108       rrtmg_lw_b200_rrtmg_lw
+ *   mcica_subcol_lw(iplon,ncol,...) src/mcica_subcol_gen_lw.f90:183   rrtmg_lw_b200_mcica_subcol_lw
+ *   get_alpha(iplon,ncol,...)       src/mcica_subcol_gen_lw.f90:68    rrtmg_lw_b200_get_alpha
+ *   [mcica_subcol_lw -> rrtmg_lw fused, sub-columns never materialised] rrtmg_lw_b200_rrtmg_lw_mcica
+ *
+ * Conventions
+ *   - Every array keeps the reference's Fortran layout, passed as a plain pointer:
+ *       (ncol,nlay) arrays:     element (i,k) at  i + ld*k            (column index fastest)
+ *       emis(ncol,16):          element (i,b) at  i + ld*b
+ *       tauaer(ncol,nlay,16):   element (i,k,b) at i + ld*(k + nlay*b)
+ *       McICA (140,ncol,nlay):  element (g,i,k) at g + 140*(i + ld*k)
+ *       tauc(16,ncol,nlay):     element (b,i,k) at b + 16*(i + ld*k)
+ *     `ld` is the extent of the column dimension of the caller's arrays (size(x,1) in the
+ *     shim; >= ncol).  Layer 1 is the surface layer (src/rrtmg_lw_rad.f90:785-787).
+ *   - memspace RRTMG_LW_HOST: pointers are host memory, the call copies in/out and is
+ *     synchronous.  RRTMG_LW_DEVICE: pointers are device memory on the current CUDA device,
+ *     work is enqueued on `stream` (a cudaStream_t passed as void*, NULL = default stream);
+ *     the status word is checked on the next HOST-mode call or rrtmg_lw_b200_sync().
+ *   - Return value: 0 on success, otherwise an RRTMG_LW_ERR_* code.  The reference STOPs at
+ *     these sites (src/rrtmg_lw_cldprmc.f90:191,204,208,217,231,253;
+ *     src/mcica_subcol_gen_lw.f90:259,465); the shim turns a non-zero code into
+ *     `error stop` with the reference's message (rrtmg_lw_b200_strerror).
+ *   - No CPU fallback exists: without a CUDA device every compute entry returns
+ *     RRTMG_LW_ERR_CUDA.
+ */
+#ifndef RRTMG_LW_B200_H
+#define RRTMG_LW_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    RRTMG_LW_OK = 0,
+    RRTMG_LW_ERR_FLAG = 1,          /* invalid icld / inflag=1 with McICA */
+    RRTMG_LW_ERR_ICE_RADIUS = 2,    /* 'ICE RADIUS OUT OF BOUNDS' etc. */
+    RRTMG_LW_ERR_LIQ_RADIUS = 3,    /* 'LIQUID EFFECTIVE RADIUS OUT OF BOUNDS' */
+    RRTMG_LW_ERR_KISS_PRESSURE = 4, /* 'KISSVEC SEED GENERATOR REQUIRES PMID FROM BOTTOM FOUR LAYERS' */
+    RRTMG_LW_ERR_CUDA = 5,          /* CUDA runtime failure / no device */
+    RRTMG_LW_ERR_NOT_INIT = 6,      /* rrtmg_lw_b200_ini not called */
+    RRTMG_LW_ERR_ARG = 7            /* bad argument (NULL pointer, ld < ncol, nlay out of range, ...) */
+};
+
+enum { RRTMG_LW_HOST = 0, RRTMG_LW_DEVICE = 1 };
+
+/* Replaces rrtmg_lw_ini (src/rrtmg_lw_init.f90:47-194): constants, g-point reduction maps,
+ * tau/exp/tfn lookup tables, reduction of the 16-g k-data to 140 g-points, upload to the
+ * current CUDA device.
+ *   kdata           : unreduced k-distribution blob, include/rrtmg_lw_kdata_layout.h
+ *                     (the reference compiles these data in via rrtmg_lw_k_g.f90)
+ *   nkdata          : number of doubles in kdata (must equal RRTMG_LW_KDATA_DOUBLES)
+ *   default_real_kind: 4 = semantics of a plain `gfortran -O3` build of the reference,
+ *                     8 = of the shipped `-r8` makefiles (affects default-kind literals only) */
+int rrtmg_lw_b200_ini(double cpdair, const double* kdata, long nkdata, int default_real_kind);
+
+/* Replaces rrtmg_lw (src/rrtmg_lw_rad.f90:99-595), argument for argument.
+ * icld is inout (clamped to 2 when outside [0,3], :470).  duflx_dt/duflxc_dt may be NULL
+ * when idrv == 0.  The McICA arrays are read only when *icld >= 1. */
+int rrtmg_lw_b200_rrtmg_lw(int ncol, int ld, int nlay, int* icld, int idrv,
+                           const double* play, const double* plev, const double* tlay, const double* tlev,
+                           const double* tsfc, const double* h2ovmr, const double* o3vmr, const double* co2vmr,
+                           const double* ch4vmr, const double* n2ovmr, const double* o2vmr,
+                           const double* cfc11vmr, const double* cfc12vmr, const double* cfc22vmr,
+                           const double* ccl4vmr, const double* emis, int inflglw, int iceflglw, int liqflglw,
+                           const double* cldfmcl, const double* taucmcl, const double* ciwpmcl,
+                           const double* clwpmcl, const double* reicmcl, const double* relqmcl,
+                           const double* tauaer, double* uflx, double* dflx, double* hr, double* uflxc,
+                           double* dflxc, double* hrc, double* duflx_dt, double* duflxc_dt,
+                           int memspace, void* stream);
+
+/* Replaces mcica_subcol_lw (src/mcica_subcol_gen_lw.f90:183-291); irng is inout (:442).
+ * iplon is accepted and ignored, as in the reference.  icld in [0,5]; alpha read for icld 4/5. */
+int rrtmg_lw_b200_mcica_subcol_lw(int iplon, int ncol, int ld, int nlay, int icld, int permuteseed, int* irng,
+                                  const double* play, const double* cldfrac, const double* ciwp,
+                                  const double* clwp, const double* rei, const double* rel, const double* tauc,
+                                  const double* alpha, double* cldfmcl, double* ciwpmcl, double* clwpmcl,
+                                  double* reicmcl, double* relqmcl, double* taucmcl, int memspace, void* stream);
+
+/* Replaces get_alpha (src/mcica_subcol_gen_lw.f90:68-180). */
+int rrtmg_lw_b200_get_alpha(int iplon, int ncol, int ld, int nlayers, int icld, int idcor, double decorr_con,
+                            const double* dz, const double* lat, int juldat, const double* cldfrac,
+                            double* alpha, int memspace, void* stream);
+
+/* mcica_subcol_lw followed by rrtmg_lw in ONE device pass: the (140,ncol,nlay) sub-column
+ * arrays are never materialised (140 mask bits per (column,layer) instead of 4x140 doubles).
+ * Results are identical to calling the two entry points above in sequence.
+ * icld_overlap in [0,5] selects the generator's overlap (the value rrtmg_lw itself would see
+ * is min(icld,3)->2 clamp per :470, which does not change its arithmetic). */
+int rrtmg_lw_b200_rrtmg_lw_mcica(int ncol, int ld, int nlay, int icld_overlap, int idrv, int permuteseed, int irng,
+                                 const double* play, const double* plev, const double* tlay, const double* tlev,
+                                 const double* tsfc, const double* h2ovmr, const double* o3vmr,
+                                 const double* co2vmr, const double* ch4vmr, const double* n2ovmr,
+                                 const double* o2vmr, const double* cfc11vmr, const double* cfc12vmr,
+                                 const double* cfc22vmr, const double* ccl4vmr, const double* emis, int inflglw,
+                                 int iceflglw, int liqflglw, const double* cldfrac, const double* ciwp,
+                                 const double* clwp, const double* rei, const double* rel, const double* tauc,
+                                 const double* alpha, const double* tauaer, double* uflx, double* dflx, double* hr,
+                                 double* uflxc, double* dflxc, double* hrc, double* duflx_dt, double* duflxc_dt,
+                                 int memspace, void* stream);
+
+/* Wait for all enqueued work and return the sticky device status (first error wins);
+ * col/lay (1-based, may be NULL) receive the first offending column and layer. */
+int rrtmg_lw_b200_sync(int* col, int* lay);
+
+/* Stage dump of ONE column (0-based icol) of the most recent rrtmg_lw/rrtmg_lw_mcica call made
+ * with debug capture enabled (rrtmg_lw_b200_debug_capture(1)); host pointers, any may be NULL:
+ *   ints6 (6,nlay) jp,jt,jt1,indself,indfor,indminor ; facs (4,nlay) fac00,fac01,fac10,fac11
+ *   taug,fracs (nlay,140) ; itr (2,nlay,140) ; scal = {laytrop, pwvcm} ; mask (nlay,140) 0/1 bytes */
+int rrtmg_lw_b200_debug_capture(int enable);
+int rrtmg_lw_b200_debug_stages(int icol, int* ints6, double* facs, double* taug, double* fracs, int* itr,
+                               double* scal, unsigned char* mask);
+
+/* Readback of an init-time table for parity tests: "tau_tbl","exp_tbl","tfn_tbl","rwgt" or
+ * "<band>:<reduced array name>" (e.g. "3:absa", reference element order).  Returns the element
+ * count (0 = unknown name); copies min(count, cap) doubles when out != NULL. */
+long rrtmg_lw_b200_get_table(const char* name, double* out, long cap);
+
+/* Upper bound of columns processed per internal pass (scratch is sized to it). */
+int rrtmg_lw_b200_set_chunk(int max_columns);
+/* Number of kernels launched by this library since the last call with reset != 0. */
+long rrtmg_lw_b200_launch_count(int reset);
+/* CUDA-event time (ms) spent in the band kernels / all kernels of the last HOST- or DEVICE-mode
+ * call when timing capture is enabled with rrtmg_lw_b200_set_timing(1). */
+int rrtmg_lw_b200_set_timing(int enable);
+int rrtmg_lw_b200_last_timing(float* ms_band_kernels, float* ms_all_kernels);
+
+const char* rrtmg_lw_b200_strerror(int code);
+const char* rrtmg_lw_b200_version(void);
+void rrtmg_lw_b200_finalize(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

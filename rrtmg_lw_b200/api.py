@@ -1,0 +1,214 @@
+"""Host-side mirror of the reference's GCM interface over the C ABI (ctypes).
+
+Same names and argument meaning as the Fortran entry points the library replaces:
+
+* ``rrtmg_lw_ini(cpdair)``                 -- ``src/rrtmg_lw_init.f90:47``
+* ``rrtmg_lw(ncol, nlay, icld, idrv, ...)``  -- ``src/rrtmg_lw_rad.f90:99-108``
+* ``mcica_subcol_lw(iplon, ncol, nlay, ...)`` -- ``src/mcica_subcol_gen_lw.f90:183-185``
+* ``get_alpha(iplon, ncol, nlayers, ...)``   -- ``src/mcica_subcol_gen_lw.f90:68-69``
+
+plus ``rrtmg_lw_mcica`` (generator + radiation in one device pass).  Arrays are either numpy
+float64 (host pointers; the call stages them through the GPU) or CUDA ``torch`` float64 tensors
+(device pointers; nothing is copied).  Layout is the reference's Fortran layout seen from C:
+``(nlay, ncol)`` row-major == Fortran ``(ncol, nlay)``; McICA arrays ``(nlay, ncol, 140)``;
+``emis (16, ncol)``; ``tauaer (16, nlay, ncol)``; ``tauc (nlay, ncol, 16)``.
+
+There is no CPU path: if ``librrtmg_lw_b200.so`` is missing or no CUDA device is present the
+calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "librrtmg_lw_b200.so")
+
+HOST, DEVICE = 0, 1
+_dp = C.POINTER(C.c_double)
+_lib = None
+
+
+class RrtmgLwError(RuntimeError):
+    def __init__(self, code, where=""):
+        self.code = code
+        msg = lib().rrtmg_lw_b200_strerror(code).decode()
+        super().__init__("rrtmg_lw_b200 error %d%s: %s" % (code, (" in " + where) if where else "", msg))
+
+
+def lib():
+    """Load the CUDA library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("librrtmg_lw_b200.so not built -- run `python -c 'import __graft_entry__ as g; "
+                               "g.build()'` (there is no CPU fallback)")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.rrtmg_lw_b200_strerror.restype = C.c_char_p
+        _lib.rrtmg_lw_b200_version.restype = C.c_char_p
+        _lib.rrtmg_lw_b200_get_table.restype = C.c_long
+        _lib.rrtmg_lw_b200_launch_count.restype = C.c_long
+        _lib.rrtmg_lw_b200_ini.argtypes = [C.c_double, _dp, C.c_long, C.c_int]
+    return _lib
+
+
+def _is_torch(a):
+    return a is not None and hasattr(a, "data_ptr")
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if _is_torch(a):
+        assert a.dtype.is_floating_point and a.element_size() == 8 and a.is_contiguous(), "float64 contiguous tensor"
+        return C.cast(C.c_void_p(a.data_ptr()), _dp)
+    assert isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags["C_CONTIGUOUS"], "float64 C-contiguous array"
+    return a.ctypes.data_as(_dp)
+
+
+def _space(arrs):
+    dev = [a for a in arrs if _is_torch(a) and a.is_cuda]
+    if dev:
+        assert all((a is None) or (_is_torch(a) and a.is_cuda) for a in arrs), "mixing host and device arrays"
+        return DEVICE
+    assert all((a is None) or isinstance(a, np.ndarray) for a in arrs), "host arrays must be numpy"
+    return HOST
+
+
+def _stream(space):
+    if space == DEVICE:
+        import torch
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return None
+
+
+def rrtmg_lw_ini(cpdair: float, kdata: np.ndarray, default_real_kind: int = 4):
+    """Replaces ``rrtmg_lw_ini(cpdair)``.  ``kdata`` = unreduced k-distribution blob
+    (``rrtmg_lw_b200.kdata``; the reference compiles these numbers in)."""
+    k = np.ascontiguousarray(kdata, dtype=np.float64)
+    rc = lib().rrtmg_lw_b200_ini(float(cpdair), _ptr(k), k.size, int(default_real_kind))
+    if rc:
+        raise RrtmgLwError(rc, "rrtmg_lw_ini")
+
+
+def rrtmg_lw(ncol, nlay, icld, idrv, play, plev, tlay, tlev, tsfc, h2ovmr, o3vmr, co2vmr, ch4vmr, n2ovmr, o2vmr,
+             cfc11vmr, cfc12vmr, cfc22vmr, ccl4vmr, emis, inflglw, iceflglw, liqflglw, cldfmcl, taucmcl, ciwpmcl,
+             clwpmcl, reicmcl, relqmcl, tauaer, uflx, dflx, hr, uflxc, dflxc, hrc, duflx_dt=None, duflxc_dt=None,
+             ld=None):
+    """Replaces ``rrtmg_lw``; outputs are written in place.  Returns the (possibly clamped) icld."""
+    arrs = [play, plev, tlay, tlev, tsfc, h2ovmr, o3vmr, co2vmr, ch4vmr, n2ovmr, o2vmr, cfc11vmr, cfc12vmr, cfc22vmr,
+            ccl4vmr, emis, cldfmcl, taucmcl, ciwpmcl, clwpmcl, reicmcl, relqmcl, tauaer, uflx, dflx, hr, uflxc, dflxc,
+            hrc, duflx_dt, duflxc_dt]
+    space = _space(arrs)
+    ic = C.c_int(int(icld))
+    p = [_ptr(a) for a in arrs]
+    rc = lib().rrtmg_lw_b200_rrtmg_lw(int(ncol), int(ld or ncol), int(nlay), C.byref(ic), int(idrv), *p[:16],
+                                      int(inflglw), int(iceflglw), int(liqflglw), *p[16:], space, _stream(space))
+    if rc:
+        raise RrtmgLwError(rc, "rrtmg_lw")
+    return ic.value
+
+
+def rrtmg_lw_mcica(ncol, nlay, icld, idrv, permuteseed, irng, play, plev, tlay, tlev, tsfc, h2ovmr, o3vmr, co2vmr,
+                   ch4vmr, n2ovmr, o2vmr, cfc11vmr, cfc12vmr, cfc22vmr, ccl4vmr, emis, inflglw, iceflglw, liqflglw,
+                   cldfrac, ciwp, clwp, rei, rel, tauc, alpha, tauaer, uflx, dflx, hr, uflxc, dflxc, hrc,
+                   duflx_dt=None, duflxc_dt=None, ld=None):
+    """``mcica_subcol_lw`` + ``rrtmg_lw`` fused on the device (sub-columns never materialised)."""
+    a1 = [play, plev, tlay, tlev, tsfc, h2ovmr, o3vmr, co2vmr, ch4vmr, n2ovmr, o2vmr, cfc11vmr, cfc12vmr, cfc22vmr,
+          ccl4vmr, emis]
+    a2 = [cldfrac, ciwp, clwp, rei, rel, tauc, alpha, tauaer, uflx, dflx, hr, uflxc, dflxc, hrc, duflx_dt, duflxc_dt]
+    space = _space(a1 + a2)
+    rc = lib().rrtmg_lw_b200_rrtmg_lw_mcica(int(ncol), int(ld or ncol), int(nlay), int(icld), int(idrv),
+                                            int(permuteseed), int(irng), *[_ptr(a) for a in a1], int(inflglw),
+                                            int(iceflglw), int(liqflglw), *[_ptr(a) for a in a2], space, _stream(space))
+    if rc:
+        raise RrtmgLwError(rc, "rrtmg_lw_mcica")
+
+
+def mcica_subcol_lw(iplon, ncol, nlay, icld, permuteseed, irng, play, cldfrac, ciwp, clwp, rei, rel, tauc, alpha,
+                    cldfmcl, ciwpmcl, clwpmcl, reicmcl, relqmcl, taucmcl, ld=None):
+    """Replaces ``mcica_subcol_lw``; returns the (possibly normalised) irng."""
+    arrs = [play, cldfrac, ciwp, clwp, rei, rel, tauc, alpha, cldfmcl, ciwpmcl, clwpmcl, reicmcl, relqmcl, taucmcl]
+    space = _space(arrs)
+    ir = C.c_int(int(irng))
+    rc = lib().rrtmg_lw_b200_mcica_subcol_lw(int(iplon), int(ncol), int(ld or ncol), int(nlay), int(icld),
+                                             int(permuteseed), C.byref(ir), *[_ptr(a) for a in arrs], space,
+                                             _stream(space))
+    if rc:
+        raise RrtmgLwError(rc, "mcica_subcol_lw")
+    return ir.value
+
+
+def get_alpha(iplon, ncol, nlayers, icld, idcor, decorr_con, dz, lat, juldat, cldfrac, alpha, ld=None):
+    """Replaces ``get_alpha``."""
+    arrs = [dz, lat, cldfrac, alpha]
+    space = _space(arrs)
+    rc = lib().rrtmg_lw_b200_get_alpha(int(iplon), int(ncol), int(ld or ncol), int(nlayers), int(icld), int(idcor),
+                                       C.c_double(decorr_con), _ptr(dz), _ptr(lat), int(juldat), _ptr(cldfrac),
+                                       _ptr(alpha), space, _stream(space))
+    if rc:
+        raise RrtmgLwError(rc, "get_alpha")
+
+
+def sync():
+    col, lay = C.c_int(0), C.c_int(0)
+    rc = lib().rrtmg_lw_b200_sync(C.byref(col), C.byref(lay))
+    if rc:
+        e = RrtmgLwError(rc, "device status (column %d, layer %d)" % (col.value, lay.value))
+        e.col, e.lay = col.value, lay.value
+        raise e
+
+
+def set_chunk(n):
+    rc = lib().rrtmg_lw_b200_set_chunk(int(n))
+    if rc:
+        raise RrtmgLwError(rc, "set_chunk")
+
+
+def launch_count(reset=False):
+    return int(lib().rrtmg_lw_b200_launch_count(1 if reset else 0))
+
+
+def set_timing(on):
+    lib().rrtmg_lw_b200_set_timing(1 if on else 0)
+
+
+def last_timing():
+    a, b = C.c_float(0), C.c_float(0)
+    lib().rrtmg_lw_b200_last_timing(C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+def debug_capture(col):
+    """Capture the stage dump of global column ``col`` (0-based) on the next call; None disables."""
+    lib().rrtmg_lw_b200_debug_capture(0 if col is None else int(col) + 1)
+
+
+def debug_stages(col, nlay, want_mask=False):
+    ints6 = np.zeros((nlay, 6), dtype=np.int32)
+    facs = np.zeros((nlay, 4))
+    taug = np.zeros((140, nlay)); fracs = np.zeros((140, nlay))
+    itr = np.zeros((140, nlay, 2), dtype=np.int32)
+    scal = np.zeros(2)
+    mask = np.zeros((140, nlay), dtype=np.uint8) if want_mask else None
+    ip = C.POINTER(C.c_int)
+    rc = lib().rrtmg_lw_b200_debug_stages(int(col), ints6.ctypes.data_as(ip), _ptr(facs), _ptr(taug), _ptr(fracs),
+                                          itr.ctypes.data_as(ip), _ptr(scal),
+                                          mask.ctypes.data_as(C.POINTER(C.c_ubyte)) if want_mask else None)
+    if rc:
+        raise RrtmgLwError(rc, "debug_stages")
+    return dict(ints6=ints6, facs=facs, taug=taug, fracs=fracs, itr=itr, laytrop=int(scal[0]), pwvcm=scal[1], mask=mask)
+
+
+def get_table(name):
+    n = lib().rrtmg_lw_b200_get_table(name.encode(), None, 0)
+    out = np.zeros(n)
+    if n:
+        lib().rrtmg_lw_b200_get_table(name.encode(), _ptr(out), n)
+    return out
+
+
+def finalize():
+    lib().rrtmg_lw_b200_finalize()

@@ -1,0 +1,697 @@
+// lw_api.cu -- the C ABI of include/rrtmg_lw_b200.h: table upload, scratch management, chunked
+// execution of the kernel pipeline, host<->device staging for host-pointer calls.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/rrtmg_lw_b200.h"
+#include "../../include/rrtmg_lw_kdata_layout.h"
+#include "lw_band.cuh"
+#include "lw_launch.h"
+
+// numeric blob of tools/extract_static_tables.py, embedded at build time
+static const double kStaticTables[] = {
+#include "_generated/lw_static_tables.inc"
+};
+
+namespace lw {
+namespace {
+
+struct Ctx {
+    bool inited = false;
+    HostTables H;
+    double* d_arena = nullptr;
+    GTab* d_gtab = nullptr;
+    double *d_totplnk = nullptr, *d_totplnkderiv = nullptr, *d_exptfn = nullptr, *d_tau = nullptr;
+    double *d_absice2 = nullptr, *d_absice3 = nullptr, *d_absliq1 = nullptr;
+    // scratch, sized for (cap_cols, cap_lay)
+    Scratch S{};
+    long cap_cols = 0;
+    int cap_lay = 0;
+    std::vector<void*> scratch_allocs;
+    // host-mode staging arena
+    double* stage = nullptr;
+    size_t stage_doubles = 0;
+    int chunk = 32768;
+    long launches = 0;
+    bool dbg = false;
+    long dbg_col = -1;  // requested by debug_capture: always column given at debug_stages time? (we capture col 0..)
+    int dbg_nlay = 0;
+    bool timing = false;
+    float ms_band = 0.f, ms_all = 0.f;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::mutex mu;
+};
+Ctx G;
+
+#define CK(x)                                                                            \
+    do {                                                                                 \
+        cudaError_t e__ = (x);                                                           \
+        if (e__ != cudaSuccess) {                                                        \
+            std::fprintf(stderr, "rrtmg_lw_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return RRTMG_LW_ERR_CUDA;                                                    \
+        }                                                                                \
+    } while (0)
+
+template <typename T>
+int dalloc(T** p, size_t n) {
+    CK(cudaMalloc((void**)p, n * sizeof(T)));
+    return 0;
+}
+
+void free_scratch() {
+    for (void* p : G.scratch_allocs) cudaFree(p);
+    G.scratch_allocs.clear();
+    G.cap_cols = 0;
+    G.cap_lay = 0;
+}
+
+int ensure_scratch(long cols, int nlay) {
+    if (cols <= G.cap_cols && nlay <= G.cap_lay) return 0;
+    const unsigned long long* old_status = G.S.status;
+    (void)old_status;
+    free_scratch();
+    const long P = ((cols + 31) / 32) * 32;
+    Scratch& S = G.S;
+    S = Scratch{};
+    S.pitch = P;
+    auto A = [&](auto** p, size_t n) -> int {
+        int rc = dalloc(p, n);
+        if (rc == 0) G.scratch_allocs.push_back((void*)*p);
+        return rc;
+    };
+    const size_t plane = (size_t)nlay * P;
+    if (A(&S.fld, (size_t)NFIELD * plane)) return RRTMG_LW_ERR_CUDA;
+    if (A(&S.ipack, plane)) return RRTMG_LW_ERR_CUDA;
+    if (A(&S.pwvcm, (size_t)P)) return RRTMG_LW_ERR_CUDA;
+    if (A(&S.laytrop, (size_t)P)) return RRTMG_LW_ERR_CUDA;
+    if (A(&S.mask, 5 * plane)) return RRTMG_LW_ERR_CUDA;
+    if (A(&S.ctop, (size_t)P)) return RRTMG_LW_ERR_CUDA;
+    if (A(&S.state, (size_t)5 * 16 * plane)) return RRTMG_LW_ERR_CUDA;
+    if (A(&S.abscld, plane)) return RRTMG_LW_ERR_CUDA;
+    if (A(&S.status, (size_t)1)) return RRTMG_LW_ERR_CUDA;
+    CK(cudaMemset(S.status, 0, sizeof(unsigned long long)));
+    if (A(&S.dbg_taug, (size_t)NGPT * nlay)) return RRTMG_LW_ERR_CUDA;
+    if (A(&S.dbg_fracs, (size_t)NGPT * nlay)) return RRTMG_LW_ERR_CUDA;
+    if (A(&S.dbg_itr, (size_t)2 * NGPT * nlay)) return RRTMG_LW_ERR_CUDA;
+    if (A(&S.dbg_ints, (size_t)6 * nlay)) return RRTMG_LW_ERR_CUDA;
+    if (A(&S.dbg_facs, (size_t)4 * nlay)) return RRTMG_LW_ERR_CUDA;
+    if (A(&S.dbg_scal, (size_t)2)) return RRTMG_LW_ERR_CUDA;
+    S.dbg_col = -1;
+    G.cap_cols = P;
+    G.cap_lay = nlay;
+    return 0;
+}
+
+int ensure_stage(size_t doubles) {
+    if (doubles <= G.stage_doubles) return 0;
+    if (G.stage) cudaFree(G.stage);
+    G.stage = nullptr;
+    G.stage_doubles = 0;
+    CK(cudaMalloc((void**)&G.stage, doubles * sizeof(double)));
+    G.stage_doubles = doubles;
+    return 0;
+}
+
+int decode_status(int* col, int* lay) {
+    unsigned long long v = 0;
+    if (!G.S.status) return RRTMG_LW_OK;
+    CK(cudaMemcpy(&v, G.S.status, sizeof(v), cudaMemcpyDeviceToHost));
+    if (v == 0) return RRTMG_LW_OK;
+    CK(cudaMemset(G.S.status, 0, sizeof(v)));
+    if (col) *col = (int)((v >> 24) & 0xffffffffull);
+    if (lay) *lay = (int)(v & 0xffffff);
+    return (int)(v >> 56);
+}
+
+bool launch_band(int band, int cld, int idrv, const ColIn& in, const ColOut& out, const Scratch& s, const RunCfg& r,
+                 cudaStream_t st) {
+    return launch_band_tu0(band, cld, idrv, in, out, s, r, st) || launch_band_tu1(band, cld, idrv, in, out, s, r, st) ||
+           launch_band_tu2(band, cld, idrv, in, out, s, r, st) || launch_band_tu3(band, cld, idrv, in, out, s, r, st) ||
+           launch_band_tu4(band, cld, idrv, in, out, s, r, st) || launch_band_tu5(band, cld, idrv, in, out, s, r, st);
+}
+
+enum Mode { MODE_STRICT = 0, MODE_FUSED = 1 };
+
+// Device-resident pipeline over column chunks.  `in`/`out` hold device pointers with their ld.
+int run_device(Mode mode, int ncol, int nlay, int icld, int idrv, int inflag, int iceflag, int liqflag, int permuteseed,
+               int irng, ColIn in, ColOut out, cudaStream_t st) {
+    if (nlay < 4 && mode == MODE_FUSED && icld > 0 && irng == 0) return RRTMG_LW_ERR_ARG;  // KISS seeds need 4 layers
+    if (nlay < 1 || nlay > LW_MAXLAY) return RRTMG_LW_ERR_ARG;
+    if (mode == MODE_FUSED && icld > 0 && irng != 0) return RRTMG_LW_ERR_ARG;  // MT stream: see mcica_subcol_lw
+    const int chunk = G.chunk;
+    int rc = ensure_scratch(ncol < chunk ? ncol : chunk, nlay);
+    if (rc) return rc;
+    const int cld = icld == 0 ? CLD_NONE : (mode == MODE_FUSED ? CLD_MASK : CLD_ARRAYS);
+    if (G.timing) {
+        for (auto& e : G.ev)
+            if (!e) CK(cudaEventCreate(&e));
+        G.ms_band = 0.f;
+        G.ms_all = 0.f;
+    }
+    for (long c0 = 0; c0 < ncol; c0 += chunk) {
+        RunCfg r{};
+        r.ncol = (int)((ncol - c0) < chunk ? (ncol - c0) : chunk);
+        r.c0 = c0;
+        r.nlay = nlay;
+        r.idrv = idrv;
+        r.inflag = inflag; r.iceflag = iceflag; r.liqflag = liqflag;
+        r.icld = icld; r.irng = irng; r.permuteseed = permuteseed;
+        Scratch S = G.S;
+        S.dbg_col = (G.dbg && G.dbg_col >= c0 && G.dbg_col < c0 + r.ncol) ? (int)(G.dbg_col - c0) : -1;
+        if (S.dbg_col >= 0) G.dbg_nlay = nlay;
+        if (G.timing) CK(cudaEventRecord(G.ev[0], st));
+        launch_prep(in, S, r, st); G.launches++;
+        if (cld == CLD_MASK) { launch_mcica_kiss(in, S, r, st); G.launches++; }
+        if (cld == CLD_ARRAYS) { launch_cldflags(in, S, r, st); G.launches += 2; }
+        if (G.timing) CK(cudaEventRecord(G.ev[1], st));
+        for (int b = 1; b <= NBND; ++b) {
+            if (!launch_band(b, cld, idrv, in, out, S, r, st)) return RRTMG_LW_ERR_ARG;
+            G.launches++;
+        }
+        if (G.timing) CK(cudaEventRecord(G.ev[2], st));
+        launch_finalize(in, out, S, r, cld != CLD_NONE, st); G.launches++;
+        if (G.timing) {
+            CK(cudaEventRecord(G.ev[3], st));
+            CK(cudaEventSynchronize(G.ev[3]));
+            float a = 0.f, b = 0.f;
+            CK(cudaEventElapsedTime(&a, G.ev[1], G.ev[2]));
+            CK(cudaEventElapsedTime(&b, G.ev[0], G.ev[3]));
+            G.ms_band += a;
+            G.ms_all += b;
+        }
+        CK(cudaGetLastError());
+    }
+    return RRTMG_LW_OK;
+}
+
+// staging helper: carve nrows x (w * P) doubles from the arena, copy the chunk's columns in
+struct Stager {
+    double* base;
+    size_t used = 0;
+    long P;
+    cudaStream_t st;
+    double* carve(size_t n) { double* p = base + used; used += n; return p; }
+    // src element (e, i, k) at e + w*(i + ld*k); copies columns [c0, c0+nc)
+    int in(const double* src, double** dst, int w, long ld, long c0, int nc, long nrows) {
+        double* d = carve((size_t)w * P * nrows);
+        *dst = d;
+        CK(cudaMemcpy2DAsync(d, (size_t)w * P * sizeof(double), src + (size_t)w * c0, (size_t)w * ld * sizeof(double),
+                             (size_t)w * nc * sizeof(double), nrows, cudaMemcpyHostToDevice, st));
+        return 0;
+    }
+    int out(double* dsthost, const double* d, int w, long ld, long c0, int nc, long nrows) {
+        CK(cudaMemcpy2DAsync(dsthost + (size_t)w * c0, (size_t)w * ld * sizeof(double), d, (size_t)w * P * sizeof(double),
+                             (size_t)w * nc * sizeof(double), nrows, cudaMemcpyDeviceToHost, st));
+        return 0;
+    }
+};
+
+bool check_common(int ncol, int ld, int nlay) { return ncol >= 1 && ld >= ncol && nlay >= 1 && nlay <= LW_MAXLAY; }
+
+}  // namespace
+}  // namespace lw
+
+using namespace lw;
+
+extern "C" int rrtmg_lw_b200_ini(double cpdair, const double* kdata, long nkdata, int default_real_kind) {
+    std::lock_guard<std::mutex> lk(G.mu);
+    if (!kdata || nkdata != RRTMG_LW_KDATA_DOUBLES) return RRTMG_LW_ERR_ARG;
+    if (default_real_kind != 4 && default_real_kind != 8) return RRTMG_LW_ERR_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        std::fprintf(stderr, "rrtmg_lw_b200: no CUDA device; this library has no CPU path\n");
+        return RRTMG_LW_ERR_CUDA;
+    }
+    static_assert(sizeof(kStaticTables) / sizeof(double) == 9110, "static table blob size");
+    build_host_tables(cpdair, kStaticTables, kdata, default_real_kind, G.H);
+    HostTables& H = G.H;
+    auto up = [&](double** d, const std::vector<double>& h) -> int {
+        if (*d) cudaFree(*d);
+        *d = nullptr;
+        CK(cudaMalloc((void**)d, h.size() * sizeof(double)));
+        CK(cudaMemcpy(*d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+        return 0;
+    };
+    if (up(&G.d_arena, H.arena)) return RRTMG_LW_ERR_CUDA;
+    if (up(&G.d_totplnk, H.totplnk)) return RRTMG_LW_ERR_CUDA;
+    if (up(&G.d_totplnkderiv, H.totplnkderiv)) return RRTMG_LW_ERR_CUDA;
+    if (up(&G.d_tau, H.tau_tbl)) return RRTMG_LW_ERR_CUDA;
+    if (up(&G.d_absice2, H.absice2)) return RRTMG_LW_ERR_CUDA;
+    if (up(&G.d_absice3, H.absice3)) return RRTMG_LW_ERR_CUDA;
+    if (up(&G.d_absliq1, H.absliq1)) return RRTMG_LW_ERR_CUDA;
+    std::vector<double> et(2 * (NTBL + 1));
+    for (int i = 0; i <= NTBL; ++i) { et[2 * i] = H.exp_tbl[i]; et[2 * i + 1] = H.tfn_tbl[i]; }
+    if (up(&G.d_exptfn, et)) return RRTMG_LW_ERR_CUDA;
+
+    // jp-indexed tables + chi ratios (setcoef.f90:338-351, 392-396: chi_mls(a,jp)/chi_mls(b,jp))
+    GTab gt;
+    std::memcpy(gt.preflog, H.ct.preflog, sizeof(gt.preflog));
+    std::memcpy(gt.tref, H.ct.tref, sizeof(gt.tref));
+    std::memcpy(gt.chi, H.ct.chi_mls, sizeof(gt.chi));
+    auto chi = [&](int sp, int lev) { return H.ct.chi_mls[(sp - 1) + 7 * (lev - 1)]; };
+    const int num[6] = {1, 1, 1, 1, 4, 3}, den[6] = {2, 3, 4, 6, 2, 2};
+    for (int k = 0; k < 6; ++k)
+        for (int jp = 1; jp <= 59; ++jp) gt.rat[k][jp - 1] = chi(num[k], jp) / chi(den[k], jp);
+    if (!G.d_gtab) CK(cudaMalloc((void**)&G.d_gtab, sizeof(GTab)));
+    CK(cudaMemcpy(G.d_gtab, &gt, sizeof(GTab), cudaMemcpyHostToDevice));
+
+    // refrat_* constants of taumol (taumol.f90:504-513, 812-815, 1080-1086, 1442-1445, 1839-1842, 2242,
+    // 2454-2460, 2770-2773, 2991)
+    double rr[NBND][5];
+    std::memset(rr, 0, sizeof(rr));
+    rr[2][0] = chi(1, 9) / chi(2, 9);   rr[2][1] = chi(1, 13) / chi(2, 13); rr[2][2] = chi(1, 3) / chi(2, 3); rr[2][3] = chi(1, 13) / chi(2, 13);
+    rr[3][0] = chi(1, 11) / chi(2, 11); rr[3][1] = chi(3, 13) / chi(2, 13);
+    rr[4][0] = chi(1, 5) / chi(2, 5);   rr[4][1] = chi(3, 43) / chi(2, 43); rr[4][2] = chi(1, 7) / chi(2, 7);
+    rr[6][0] = chi(1, 3) / chi(3, 3);   rr[6][2] = chi(1, 3) / chi(3, 3);
+    rr[8][0] = chi(1, 9) / chi(6, 9);   rr[8][2] = chi(1, 3) / chi(6, 3);
+    rr[11][0] = chi(1, 10) / chi(2, 10);
+    rr[12][0] = chi(1, 5) / chi(4, 5);  rr[12][2] = chi(1, 1) / chi(4, 1);  rr[12][4] = chi(1, 3) / chi(4, 3);
+    rr[14][0] = chi(4, 1) / chi(2, 1);  rr[14][2] = chi(4, 1) / chi(2, 1);
+    rr[15][0] = chi(1, 6) / chi(6, 6);
+
+    // band pointers into the device arena
+    for (int b = 0; b < NBND; ++b) {
+        auto P = [&](int slot) -> const double* {
+            return H.off[b][slot] == (size_t)-1 ? nullptr : G.d_arena + H.off[b][slot];
+        };
+        BandTab& T = H.ct.band[b];
+        T.ka = P(0); T.kb = P(1); T.selfref = P(2); T.forref = P(3); T.fracrefa = P(4); T.fracrefb = P(5);
+        for (int m = 0; m < 5; ++m) T.m[m] = P(6 + m);
+        T.v[0] = P(11); T.v[1] = P(12);
+    }
+    DevPtrs dp;
+    dp.g = G.d_gtab; dp.totplnk = G.d_totplnk; dp.totplnkderiv = G.d_totplnkderiv;
+    dp.exptfn = reinterpret_cast<const double2*>(G.d_exptfn); dp.tau_tbl = G.d_tau;
+    dp.absice2 = G.d_absice2; dp.absice3 = G.d_absice3; dp.absliq1 = G.d_absliq1;
+    CK(upload_constants_kernels(H.ct, dp, rr));
+    CK(upload_constants_tu0(H.ct, dp, rr));
+    CK(upload_constants_tu1(H.ct, dp, rr));
+    CK(upload_constants_tu2(H.ct, dp, rr));
+    CK(upload_constants_tu3(H.ct, dp, rr));
+    CK(upload_constants_tu4(H.ct, dp, rr));
+    CK(upload_constants_tu5(H.ct, dp, rr));
+    CK(cudaDeviceSynchronize());
+    G.inited = true;
+    return RRTMG_LW_OK;
+}
+
+extern "C" int rrtmg_lw_b200_rrtmg_lw(int ncol, int ld, int nlay, int* icld, int idrv, const double* play,
+                                      const double* plev, const double* tlay, const double* tlev, const double* tsfc,
+                                      const double* h2ovmr, const double* o3vmr, const double* co2vmr,
+                                      const double* ch4vmr, const double* n2ovmr, const double* o2vmr,
+                                      const double* cfc11vmr, const double* cfc12vmr, const double* cfc22vmr,
+                                      const double* ccl4vmr, const double* emis, int inflglw, int iceflglw, int liqflglw,
+                                      const double* cldfmcl, const double* taucmcl, const double* ciwpmcl,
+                                      const double* clwpmcl, const double* reicmcl, const double* relqmcl,
+                                      const double* tauaer, double* uflx, double* dflx, double* hr, double* uflxc,
+                                      double* dflxc, double* hrc, double* duflx_dt, double* duflxc_dt, int memspace,
+                                      void* stream) {
+    std::lock_guard<std::mutex> lk(G.mu);
+    if (!G.inited) return RRTMG_LW_ERR_NOT_INIT;
+    if (!icld || !check_common(ncol, ld, nlay)) return RRTMG_LW_ERR_ARG;
+    if (*icld < 0 || *icld > 3) *icld = 2;  // rad.f90:470
+    if (idrv != 0 && idrv != 1) return RRTMG_LW_ERR_ARG;
+    if (idrv == 1 && (!duflx_dt || !duflxc_dt)) return RRTMG_LW_ERR_ARG;
+    const bool cloudy = *icld >= 1;
+    if (!play || !plev || !tlay || !tlev || !tsfc || !h2ovmr || !o3vmr || !co2vmr || !ch4vmr || !n2ovmr || !o2vmr ||
+        !cfc11vmr || !cfc12vmr || !cfc22vmr || !ccl4vmr || !emis || !tauaer || !uflx || !dflx || !hr || !uflxc ||
+        !dflxc || !hrc)
+        return RRTMG_LW_ERR_ARG;
+    if (cloudy && (!cldfmcl || !taucmcl || !ciwpmcl || !clwpmcl || !reicmcl || !relqmcl)) return RRTMG_LW_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (memspace == RRTMG_LW_DEVICE) {
+        ColIn in{};
+        in.play = play; in.plev = plev; in.tlay = tlay; in.tlev = tlev; in.tsfc = tsfc; in.h2o = h2ovmr; in.o3 = o3vmr;
+        in.co2 = co2vmr; in.ch4 = ch4vmr; in.n2o = n2ovmr; in.o2 = o2vmr; in.cfc11 = cfc11vmr; in.cfc12 = cfc12vmr;
+        in.cfc22 = cfc22vmr; in.ccl4 = ccl4vmr; in.emis = emis; in.tauaer = tauaer;
+        in.cldfmcl = cldfmcl; in.taucmcl = taucmcl; in.ciwpmcl = ciwpmcl; in.clwpmcl = clwpmcl;
+        in.reicmcl = reicmcl; in.relqmcl = relqmcl;
+        in.ld = ld; in.nlay = nlay;
+        ColOut out{uflx, dflx, hr, uflxc, dflxc, hrc, duflx_dt, duflxc_dt, ld};
+        return run_device(MODE_STRICT, ncol, nlay, *icld, idrv, inflglw, iceflglw, liqflglw, 0, 0, in, out, st);
+    }
+    // host pointers: stage chunk by chunk
+    const int chunk = G.chunk < ncol ? G.chunk : ncol;
+    const long P = ((chunk + 31) / 32) * 32;
+    const size_t per_col = (size_t)12 * nlay + 2 * (nlay + 1) + 1 + 16 + 16 * (size_t)nlay +
+                           (cloudy ? (size_t)4 * 140 * nlay + 2 * nlay : 0) + 6 * (size_t)(nlay + 1) + 2 * (size_t)nlay;
+    int rc = ensure_stage(per_col * P + 64);
+    if (rc) return rc;
+    const int saved_chunk = G.chunk;
+    for (long c0 = 0; c0 < ncol; c0 += chunk) {
+        const int nc = (int)((ncol - c0) < chunk ? (ncol - c0) : chunk);
+        Stager sg{G.stage, 0, P, st};
+        ColIn in{};
+        double* d;
+#define IN2(field, src, rows) if (sg.in(src, &d, 1, ld, c0, nc, rows)) return RRTMG_LW_ERR_CUDA; in.field = d;
+        IN2(play, play, nlay) IN2(plev, plev, nlay + 1) IN2(tlay, tlay, nlay) IN2(tlev, tlev, nlay + 1) IN2(tsfc, tsfc, 1)
+        IN2(h2o, h2ovmr, nlay) IN2(o3, o3vmr, nlay) IN2(co2, co2vmr, nlay) IN2(ch4, ch4vmr, nlay) IN2(n2o, n2ovmr, nlay)
+        IN2(o2, o2vmr, nlay) IN2(cfc11, cfc11vmr, nlay) IN2(cfc12, cfc12vmr, nlay) IN2(cfc22, cfc22vmr, nlay)
+        IN2(ccl4, ccl4vmr, nlay) IN2(emis, emis, 16) IN2(tauaer, tauaer, (long)16 * nlay)
+        if (cloudy) {
+#define IN3(field, src) if (sg.in(src, &d, 140, ld, c0, nc, nlay)) return RRTMG_LW_ERR_CUDA; in.field = d;
+            IN3(cldfmcl, cldfmcl) IN3(taucmcl, taucmcl) IN3(ciwpmcl, ciwpmcl) IN3(clwpmcl, clwpmcl)
+#undef IN3
+            IN2(reicmcl, reicmcl, nlay) IN2(relqmcl, relqmcl, nlay)
+        }
+#undef IN2
+        in.ld = P; in.nlay = nlay;
+        ColOut out{};
+        out.ld = P;
+        out.uflx = sg.carve((size_t)P * (nlay + 1)); out.dflx = sg.carve((size_t)P * (nlay + 1));
+        out.uflxc = sg.carve((size_t)P * (nlay + 1)); out.dflxc = sg.carve((size_t)P * (nlay + 1));
+        out.duflx_dt = sg.carve((size_t)P * (nlay + 1)); out.duflxc_dt = sg.carve((size_t)P * (nlay + 1));
+        out.hr = sg.carve((size_t)P * nlay); out.hrc = sg.carve((size_t)P * nlay);
+        const long dbg_save = G.dbg_col;
+        if (G.dbg) G.dbg_col = dbg_save - c0;  // chunk-relative for the staged call
+        G.chunk = chunk;
+        rc = run_device(MODE_STRICT, nc, nlay, *icld, idrv, inflglw, iceflglw, liqflglw, 0, 0, in, out, st);
+        G.chunk = saved_chunk;
+        G.dbg_col = dbg_save;
+        if (rc) return rc;
+        if (sg.out(uflx, out.uflx, 1, ld, c0, nc, nlay + 1) || sg.out(dflx, out.dflx, 1, ld, c0, nc, nlay + 1) ||
+            sg.out(uflxc, out.uflxc, 1, ld, c0, nc, nlay + 1) || sg.out(dflxc, out.dflxc, 1, ld, c0, nc, nlay + 1) ||
+            sg.out(hr, out.hr, 1, ld, c0, nc, nlay) || sg.out(hrc, out.hrc, 1, ld, c0, nc, nlay))
+            return RRTMG_LW_ERR_CUDA;
+        if (idrv == 1 && (sg.out(duflx_dt, out.duflx_dt, 1, ld, c0, nc, nlay + 1) ||
+                          sg.out(duflxc_dt, out.duflxc_dt, 1, ld, c0, nc, nlay + 1)))
+            return RRTMG_LW_ERR_CUDA;
+        CK(cudaStreamSynchronize(st));
+    }
+    return decode_status(nullptr, nullptr);
+}
+
+extern "C" int rrtmg_lw_b200_rrtmg_lw_mcica(int ncol, int ld, int nlay, int icld_overlap, int idrv, int permuteseed,
+                                            int irng, const double* play, const double* plev, const double* tlay,
+                                            const double* tlev, const double* tsfc, const double* h2ovmr,
+                                            const double* o3vmr, const double* co2vmr, const double* ch4vmr,
+                                            const double* n2ovmr, const double* o2vmr, const double* cfc11vmr,
+                                            const double* cfc12vmr, const double* cfc22vmr, const double* ccl4vmr,
+                                            const double* emis, int inflglw, int iceflglw, int liqflglw,
+                                            const double* cldfrac, const double* ciwp, const double* clwp,
+                                            const double* rei, const double* rel, const double* tauc,
+                                            const double* alpha, const double* tauaer, double* uflx, double* dflx,
+                                            double* hr, double* uflxc, double* dflxc, double* hrc, double* duflx_dt,
+                                            double* duflxc_dt, int memspace, void* stream) {
+    std::lock_guard<std::mutex> lk(G.mu);
+    if (!G.inited) return RRTMG_LW_ERR_NOT_INIT;
+    if (!check_common(ncol, ld, nlay)) return RRTMG_LW_ERR_ARG;
+    if (icld_overlap < 0 || icld_overlap > 5) return RRTMG_LW_ERR_FLAG;  // 'MCICA_SUBCOL_LW: INVALID ICLD'
+    if (idrv != 0 && idrv != 1) return RRTMG_LW_ERR_ARG;
+    if (idrv == 1 && (!duflx_dt || !duflxc_dt)) return RRTMG_LW_ERR_ARG;
+    const bool cloudy = icld_overlap >= 1;
+    if (!play || !plev || !tlay || !tlev || !tsfc || !h2ovmr || !o3vmr || !co2vmr || !ch4vmr || !n2ovmr || !o2vmr ||
+        !cfc11vmr || !cfc12vmr || !cfc22vmr || !ccl4vmr || !emis || !tauaer || !uflx || !dflx || !hr || !uflxc ||
+        !dflxc || !hrc)
+        return RRTMG_LW_ERR_ARG;
+    if (cloudy && (!cldfrac || !ciwp || !clwp || !rei || !rel || !tauc)) return RRTMG_LW_ERR_ARG;
+    if (icld_overlap >= 4 && !alpha) return RRTMG_LW_ERR_ARG;
+    if (irng != 0) irng = 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (memspace == RRTMG_LW_DEVICE) {
+        ColIn in{};
+        in.play = play; in.plev = plev; in.tlay = tlay; in.tlev = tlev; in.tsfc = tsfc; in.h2o = h2ovmr; in.o3 = o3vmr;
+        in.co2 = co2vmr; in.ch4 = ch4vmr; in.n2o = n2ovmr; in.o2 = o2vmr; in.cfc11 = cfc11vmr; in.cfc12 = cfc12vmr;
+        in.cfc22 = cfc22vmr; in.ccl4 = ccl4vmr; in.emis = emis; in.tauaer = tauaer;
+        in.cldfrac = cldfrac; in.ciwp = ciwp; in.clwp = clwp; in.rei = rei; in.rel = rel; in.tauc = tauc; in.alpha = alpha;
+        in.ld = ld; in.nlay = nlay;
+        ColOut out{uflx, dflx, hr, uflxc, dflxc, hrc, duflx_dt, duflxc_dt, ld};
+        return run_device(MODE_FUSED, ncol, nlay, icld_overlap, idrv, inflglw, iceflglw, liqflglw, permuteseed, irng, in,
+                          out, st);
+    }
+    const int chunk = G.chunk < ncol ? G.chunk : ncol;
+    const long P = ((chunk + 31) / 32) * 32;
+    const size_t per_col = (size_t)12 * nlay + 2 * (nlay + 1) + 1 + 16 + 16 * (size_t)nlay +
+                           (cloudy ? (size_t)6 * nlay + 16 * (size_t)nlay : 0) + 6 * (size_t)(nlay + 1) + 2 * (size_t)nlay;
+    int rc = ensure_stage(per_col * P + 64);
+    if (rc) return rc;
+    const int saved_chunk = G.chunk;
+    for (long c0 = 0; c0 < ncol; c0 += chunk) {
+        const int nc = (int)((ncol - c0) < chunk ? (ncol - c0) : chunk);
+        Stager sg{G.stage, 0, P, st};
+        ColIn in{};
+        double* d;
+#define IN2(field, src, rows) if (sg.in(src, &d, 1, ld, c0, nc, rows)) return RRTMG_LW_ERR_CUDA; in.field = d;
+        IN2(play, play, nlay) IN2(plev, plev, nlay + 1) IN2(tlay, tlay, nlay) IN2(tlev, tlev, nlay + 1) IN2(tsfc, tsfc, 1)
+        IN2(h2o, h2ovmr, nlay) IN2(o3, o3vmr, nlay) IN2(co2, co2vmr, nlay) IN2(ch4, ch4vmr, nlay) IN2(n2o, n2ovmr, nlay)
+        IN2(o2, o2vmr, nlay) IN2(cfc11, cfc11vmr, nlay) IN2(cfc12, cfc12vmr, nlay) IN2(cfc22, cfc22vmr, nlay)
+        IN2(ccl4, ccl4vmr, nlay) IN2(emis, emis, 16) IN2(tauaer, tauaer, (long)16 * nlay)
+        if (cloudy) {
+            IN2(cldfrac, cldfrac, nlay) IN2(ciwp, ciwp, nlay) IN2(clwp, clwp, nlay) IN2(rei, rei, nlay) IN2(rel, rel, nlay)
+            if (alpha) { IN2(alpha, alpha, nlay) }
+            if (sg.in(tauc, &d, 16, ld, c0, nc, nlay)) return RRTMG_LW_ERR_CUDA;
+            in.tauc = d;
+        }
+#undef IN2
+        in.ld = P; in.nlay = nlay;
+        ColOut out{};
+        out.ld = P;
+        out.uflx = sg.carve((size_t)P * (nlay + 1)); out.dflx = sg.carve((size_t)P * (nlay + 1));
+        out.uflxc = sg.carve((size_t)P * (nlay + 1)); out.dflxc = sg.carve((size_t)P * (nlay + 1));
+        out.duflx_dt = sg.carve((size_t)P * (nlay + 1)); out.duflxc_dt = sg.carve((size_t)P * (nlay + 1));
+        out.hr = sg.carve((size_t)P * nlay); out.hrc = sg.carve((size_t)P * nlay);
+        const long dbg_save = G.dbg_col;
+        if (G.dbg) G.dbg_col = dbg_save - c0;
+        G.chunk = chunk;
+        rc = run_device(MODE_FUSED, nc, nlay, icld_overlap, idrv, inflglw, iceflglw, liqflglw, permuteseed, irng, in, out, st);
+        G.chunk = saved_chunk;
+        G.dbg_col = dbg_save;
+        if (rc) return rc;
+        if (sg.out(uflx, out.uflx, 1, ld, c0, nc, nlay + 1) || sg.out(dflx, out.dflx, 1, ld, c0, nc, nlay + 1) ||
+            sg.out(uflxc, out.uflxc, 1, ld, c0, nc, nlay + 1) || sg.out(dflxc, out.dflxc, 1, ld, c0, nc, nlay + 1) ||
+            sg.out(hr, out.hr, 1, ld, c0, nc, nlay) || sg.out(hrc, out.hrc, 1, ld, c0, nc, nlay))
+            return RRTMG_LW_ERR_CUDA;
+        if (idrv == 1 && (sg.out(duflx_dt, out.duflx_dt, 1, ld, c0, nc, nlay + 1) ||
+                          sg.out(duflxc_dt, out.duflxc_dt, 1, ld, c0, nc, nlay + 1)))
+            return RRTMG_LW_ERR_CUDA;
+        CK(cudaStreamSynchronize(st));
+    }
+    return decode_status(nullptr, nullptr);
+}
+
+extern "C" int rrtmg_lw_b200_mcica_subcol_lw(int iplon, int ncol, int ld, int nlay, int icld, int permuteseed, int* irng,
+                                             const double* play, const double* cldfrac, const double* ciwp,
+                                             const double* clwp, const double* rei, const double* rel,
+                                             const double* tauc, const double* alpha, double* cldfmcl, double* ciwpmcl,
+                                             double* clwpmcl, double* reicmcl, double* relqmcl, double* taucmcl,
+                                             int memspace, void* stream) {
+    (void)iplon;
+    std::lock_guard<std::mutex> lk(G.mu);
+    if (!G.inited) return RRTMG_LW_ERR_NOT_INIT;
+    if (icld == 0) return RRTMG_LW_OK;  // mcica:257
+    if (icld < 0 || icld > 5) return RRTMG_LW_ERR_FLAG;
+    if (!irng || !check_common(ncol, ld, nlay) || nlay < 4) return RRTMG_LW_ERR_ARG;
+    if (!play || !cldfrac || !ciwp || !clwp || !rei || !rel || !tauc || !cldfmcl || !ciwpmcl || !clwpmcl || !reicmcl ||
+        !relqmcl || !taucmcl)
+        return RRTMG_LW_ERR_ARG;
+    if (icld >= 4 && !alpha) return RRTMG_LW_ERR_ARG;
+    if (*irng != 0) *irng = 1;
+    if (*irng == 1) return RRTMG_LW_ERR_ARG;  // Mersenne-Twister stream: not built yet
+    cudaStream_t st = (cudaStream_t)stream;
+    const int chunk = G.chunk < ncol ? G.chunk : ncol;
+    int rc = ensure_scratch(chunk, nlay);
+    if (rc) return rc;
+    const long P = ((chunk + 31) / 32) * 32;
+    if (memspace == RRTMG_LW_HOST) {
+        rc = ensure_stage(((size_t)7 * nlay + 16 * (size_t)nlay + 4 * 140 * (size_t)nlay + 2 * (size_t)nlay) * P + 64);
+        if (rc) return rc;
+    }
+    for (long c0 = 0; c0 < ncol; c0 += chunk) {
+        RunCfg r{};
+        r.ncol = (int)((ncol - c0) < chunk ? (ncol - c0) : chunk);
+        r.nlay = nlay; r.icld = icld; r.irng = 0; r.permuteseed = permuteseed;
+        ColIn in{};
+        in.nlay = nlay;
+        if (memspace == RRTMG_LW_DEVICE) {
+            r.c0 = c0;
+            in.play = play; in.cldfrac = cldfrac; in.ciwp = ciwp; in.clwp = clwp; in.rei = rei; in.rel = rel;
+            in.tauc = tauc; in.alpha = alpha; in.ld = ld;
+            launch_mcica_kiss(in, G.S, r, st);
+            launch_materialize(in, G.S, r, cldfmcl, ciwpmcl, clwpmcl, reicmcl, relqmcl, taucmcl, st);
+            G.launches += 2;
+        } else {
+            r.c0 = 0;
+            Stager sg{G.stage, 0, P, st};
+            double* d;
+#define IN2(field, src) if (sg.in(src, &d, 1, ld, c0, r.ncol, nlay)) return RRTMG_LW_ERR_CUDA; in.field = d;
+            IN2(play, play) IN2(cldfrac, cldfrac) IN2(ciwp, ciwp) IN2(clwp, clwp) IN2(rei, rei) IN2(rel, rel)
+            if (alpha) { IN2(alpha, alpha) }
+#undef IN2
+            if (sg.in(tauc, &d, 16, ld, c0, r.ncol, nlay)) return RRTMG_LW_ERR_CUDA;
+            in.tauc = d;
+            in.ld = P;
+            double* o_cld = sg.carve((size_t)140 * P * nlay); double* o_ciwp = sg.carve((size_t)140 * P * nlay);
+            double* o_clwp = sg.carve((size_t)140 * P * nlay); double* o_tauc = sg.carve((size_t)140 * P * nlay);
+            double* o_rei = sg.carve((size_t)P * nlay); double* o_rel = sg.carve((size_t)P * nlay);
+            launch_mcica_kiss(in, G.S, r, st);
+            launch_materialize(in, G.S, r, o_cld, o_ciwp, o_clwp, o_rei, o_rel, o_tauc, st);
+            G.launches += 2;
+            if (sg.out(cldfmcl, o_cld, 140, ld, c0, r.ncol, nlay) || sg.out(ciwpmcl, o_ciwp, 140, ld, c0, r.ncol, nlay) ||
+                sg.out(clwpmcl, o_clwp, 140, ld, c0, r.ncol, nlay) || sg.out(taucmcl, o_tauc, 140, ld, c0, r.ncol, nlay) ||
+                sg.out(reicmcl, o_rei, 1, ld, c0, r.ncol, nlay) || sg.out(relqmcl, o_rel, 1, ld, c0, r.ncol, nlay))
+                return RRTMG_LW_ERR_CUDA;
+            CK(cudaStreamSynchronize(st));
+        }
+        CK(cudaGetLastError());
+    }
+    if (memspace == RRTMG_LW_HOST) {
+        // the generator itself only STOPs on the KISS pressure ordering (mcica:465); radius checks belong to cldprmc
+        int rcs = decode_status(nullptr, nullptr);
+        return rcs == RRTMG_LW_ERR_KISS_PRESSURE ? rcs : RRTMG_LW_OK;
+    }
+    return RRTMG_LW_OK;
+}
+
+extern "C" int rrtmg_lw_b200_get_alpha(int iplon, int ncol, int ld, int nlayers, int icld, int idcor, double decorr_con,
+                                       const double* dz, const double* lat, int juldat, const double* cldfrac,
+                                       double* alpha, int memspace, void* stream) {
+    (void)iplon;
+    std::lock_guard<std::mutex> lk(G.mu);
+    if (!G.inited) return RRTMG_LW_ERR_NOT_INIT;
+    if (!check_common(ncol, ld, nlayers) || !dz || !lat || !cldfrac || !alpha) return RRTMG_LW_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int drk = G.H.ct.drk;
+    auto dkl = [&](double x) { return drk == 4 ? (double)(float)x : x; };
+    const double am1 = dkl(1.4315), am2 = dkl(2.1219), am4 = dkl(-25.584);  // mcica:121-123 default-kind literals
+    if (memspace == RRTMG_LW_DEVICE) {
+        launch_get_alpha(ncol, ld, nlayers, icld, idcor, decorr_con, dz, lat, juldat, cldfrac, alpha, am1, am2, am4, st);
+        G.launches++;
+        CK(cudaGetLastError());
+        return RRTMG_LW_OK;
+    }
+    const size_t n2 = (size_t)ld * nlayers;
+    int rc = ensure_stage(3 * n2 + ld + 64);
+    if (rc) return rc;
+    double *d_dz = G.stage, *d_cf = G.stage + n2, *d_al = G.stage + 2 * n2, *d_lat = G.stage + 3 * n2;
+    CK(cudaMemcpyAsync(d_dz, dz, n2 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_cf, cldfrac, n2 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_al, alpha, n2 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_lat, lat, (size_t)ncol * sizeof(double), cudaMemcpyHostToDevice, st));
+    launch_get_alpha(ncol, ld, nlayers, icld, idcor, decorr_con, d_dz, d_lat, juldat, d_cf, d_al, am1, am2, am4, st);
+    G.launches++;
+    CK(cudaMemcpyAsync(alpha, d_al, n2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return RRTMG_LW_OK;
+}
+
+extern "C" int rrtmg_lw_b200_sync(int* col, int* lay) {
+    std::lock_guard<std::mutex> lk(G.mu);
+    if (cudaDeviceSynchronize() != cudaSuccess) return RRTMG_LW_ERR_CUDA;
+    return decode_status(col, lay);
+}
+
+extern "C" int rrtmg_lw_b200_debug_capture(int col_plus1) {
+    std::lock_guard<std::mutex> lk(G.mu);
+    G.dbg = col_plus1 > 0;
+    G.dbg_col = col_plus1 - 1;
+    return RRTMG_LW_OK;
+}
+
+extern "C" int rrtmg_lw_b200_debug_stages(int icol, int* ints6, double* facs, double* taug, double* fracs, int* itr,
+                                          double* scal, unsigned char* mask) {
+    std::lock_guard<std::mutex> lk(G.mu);
+    if (!G.inited || !G.dbg || G.dbg_nlay <= 0) return RRTMG_LW_ERR_NOT_INIT;
+    if (icol != G.dbg_col) return RRTMG_LW_ERR_ARG;
+    const int nlay = G.dbg_nlay;
+    CK(cudaDeviceSynchronize());
+    if (ints6) CK(cudaMemcpy(ints6, G.S.dbg_ints, sizeof(int) * 6 * nlay, cudaMemcpyDeviceToHost));
+    if (facs) CK(cudaMemcpy(facs, G.S.dbg_facs, sizeof(double) * 4 * nlay, cudaMemcpyDeviceToHost));
+    if (taug) CK(cudaMemcpy(taug, G.S.dbg_taug, sizeof(double) * NGPT * nlay, cudaMemcpyDeviceToHost));
+    if (fracs) CK(cudaMemcpy(fracs, G.S.dbg_fracs, sizeof(double) * NGPT * nlay, cudaMemcpyDeviceToHost));
+    if (itr) CK(cudaMemcpy(itr, G.S.dbg_itr, sizeof(int) * 2 * NGPT * nlay, cudaMemcpyDeviceToHost));
+    if (scal) CK(cudaMemcpy(scal, G.S.dbg_scal, sizeof(double) * 2, cudaMemcpyDeviceToHost));
+    if (mask) {
+        // only meaningful for a single-chunk call; chunk-relative column = icol % chunk
+        const long P = G.S.pitch;
+        const long ic = icol % G.chunk;
+        std::vector<unsigned> w((size_t)5 * nlay);
+        for (int l = 0; l < nlay; ++l)
+            for (int k = 0; k < 5; ++k)
+                CK(cudaMemcpy(&w[(size_t)l * 5 + k], G.S.mask + ((size_t)l * 5 + k) * P + ic, sizeof(unsigned),
+                              cudaMemcpyDeviceToHost));
+        for (int l = 0; l < nlay; ++l)
+            for (int g = 0; g < NGPT; ++g) mask[(size_t)g * nlay + l] = (w[(size_t)l * 5 + (g >> 5)] >> (g & 31)) & 1u;
+    }
+    return RRTMG_LW_OK;
+}
+
+extern "C" long rrtmg_lw_b200_get_table(const char* name, double* out, long cap) {
+    std::lock_guard<std::mutex> lk(G.mu);
+    if (!G.inited || !name) return 0;
+    const std::string n(name);
+    const double* src = nullptr;
+    long cnt = 0;
+    if (n == "tau_tbl") { src = G.H.tau_tbl.data(); cnt = NTBL + 1; }
+    else if (n == "exp_tbl") { src = G.H.exp_tbl.data(); cnt = NTBL + 1; }
+    else if (n == "tfn_tbl") { src = G.H.tfn_tbl.data(); cnt = NTBL + 1; }
+    else if (n == "rwgt") { src = G.H.rwgt; cnt = 256; }
+    else {
+        for (auto& kv : G.H.named)
+            if (kv.first == n) { src = kv.second.data(); cnt = (long)kv.second.size(); break; }
+    }
+    if (src && out)
+        for (long i = 0; i < cnt && i < cap; ++i) out[i] = src[i];
+    return cnt;
+}
+
+extern "C" int rrtmg_lw_b200_set_chunk(int max_columns) {
+    std::lock_guard<std::mutex> lk(G.mu);
+    if (max_columns < 32) return RRTMG_LW_ERR_ARG;
+    G.chunk = max_columns;
+    return RRTMG_LW_OK;
+}
+
+extern "C" long rrtmg_lw_b200_launch_count(int reset) {
+    std::lock_guard<std::mutex> lk(G.mu);
+    const long v = G.launches;
+    if (reset) G.launches = 0;
+    return v;
+}
+
+extern "C" int rrtmg_lw_b200_set_timing(int enable) {
+    std::lock_guard<std::mutex> lk(G.mu);
+    G.timing = enable != 0;
+    return RRTMG_LW_OK;
+}
+
+extern "C" int rrtmg_lw_b200_last_timing(float* ms_band, float* ms_all) {
+    std::lock_guard<std::mutex> lk(G.mu);
+    if (ms_band) *ms_band = G.ms_band;
+    if (ms_all) *ms_all = G.ms_all;
+    return RRTMG_LW_OK;
+}
+
+extern "C" const char* rrtmg_lw_b200_strerror(int code) {
+    switch (code) {
+        case RRTMG_LW_OK: return "ok";
+        case RRTMG_LW_ERR_FLAG: return "INVALID ICLD / INFLAG = 1 OPTION NOT AVAILABLE WITH MCICA";
+        case RRTMG_LW_ERR_ICE_RADIUS: return "ICE RADIUS OUT OF BOUNDS";
+        case RRTMG_LW_ERR_LIQ_RADIUS: return "LIQUID EFFECTIVE RADIUS OUT OF BOUNDS";
+        case RRTMG_LW_ERR_KISS_PRESSURE: return "MCICA_SUBCOL: KISSVEC SEED GENERATOR REQUIRES PMID FROM BOTTOM FOUR LAYERS.";
+        case RRTMG_LW_ERR_CUDA: return "CUDA runtime error or no CUDA device (no CPU fallback exists)";
+        case RRTMG_LW_ERR_NOT_INIT: return "rrtmg_lw_b200_ini has not been called";
+        case RRTMG_LW_ERR_ARG: return "invalid argument";
+        default: return "unknown error";
+    }
+}
+
+extern "C" const char* rrtmg_lw_b200_version(void) { return "rrtmg_lw_b200 0.1 (sm_100a)"; }
+
+extern "C" void rrtmg_lw_b200_finalize(void) {
+    std::lock_guard<std::mutex> lk(G.mu);
+    free_scratch();
+    if (G.stage) cudaFree(G.stage);
+    G.stage = nullptr; G.stage_doubles = 0;
+    for (double** p : {&G.d_arena, &G.d_totplnk, &G.d_totplnkderiv, &G.d_exptfn, &G.d_tau, &G.d_absice2, &G.d_absice3,
+                       &G.d_absliq1}) {
+        if (*p) cudaFree(*p);
+        *p = nullptr;
+    }
+    if (G.d_gtab) cudaFree(G.d_gtab);
+    G.d_gtab = nullptr;
+    G.inited = false;
+}

@@ -1,0 +1,55 @@
+// lw_band_inst.cu -- instantiations of the band kernel; compiled once per -DLW_TU=n so the 16
+// bands x cloud modes x idrv variants build in parallel.
+#include "lw_band.cuh"
+#include "lw_launch.h"
+
+#ifndef LW_TU
+#error "compile with -DLW_TU=0..5"
+#endif
+
+#if LW_TU == 0
+#define LW_TU_BANDS(X) X(1) X(2) X(6) X(10)
+#elif LW_TU == 1
+#define LW_TU_BANDS(X) X(3) X(14)
+#elif LW_TU == 2
+#define LW_TU_BANDS(X) X(4) X(8)
+#elif LW_TU == 3
+#define LW_TU_BANDS(X) X(5) X(11)
+#elif LW_TU == 4
+#define LW_TU_BANDS(X) X(7) X(12) X(16)
+#else
+#define LW_TU_BANDS(X) X(9) X(13) X(15)
+#endif
+
+#define LW_CAT2(a, b) a##b
+#define LW_CAT(a, b) LW_CAT2(a, b)
+
+namespace lw {
+
+template <int B>
+static void launch_b(int cld, int idrv, const ColIn& in, const ColOut& out, const Scratch& s, const RunCfg& r,
+                     cudaStream_t st) {
+    const int threads = 128;
+    const int blocks = (r.ncol + threads - 1) / threads;
+#define LW_GO(CLD, IDRV) band_kernel<B, CLD, IDRV><<<blocks, threads, 0, st>>>(in, out, s, r)
+    if (cld == CLD_NONE) { if (idrv) LW_GO(CLD_NONE, 1); else LW_GO(CLD_NONE, 0); }
+    else if (cld == CLD_MASK) { if (idrv) LW_GO(CLD_MASK, 1); else LW_GO(CLD_MASK, 0); }
+    else { if (idrv) LW_GO(CLD_ARRAYS, 1); else LW_GO(CLD_ARRAYS, 0); }
+#undef LW_GO
+}
+
+bool LW_CAT(launch_band_tu, LW_TU)(int band, int cld, int idrv, const ColIn& in, const ColOut& out, const Scratch& s,
+                                   const RunCfg& r, cudaStream_t st) {
+    switch (band) {
+#define LW_CASE(b) case b: launch_b<b>(cld, idrv, in, out, s, r, st); return true;
+        LW_TU_BANDS(LW_CASE)
+#undef LW_CASE
+        default: return false;
+    }
+}
+
+cudaError_t LW_CAT(upload_constants_tu, LW_TU)(const ConstTab& c, const DevPtrs& d, const double (*refrat)[5]) {
+    return upload_constants_here(c, d, refrat);
+}
+
+}  // namespace lw

@@ -1,0 +1,69 @@
+// lw_device.cuh -- device-side data structures of the B200 RRTMG_LW path.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "lw_tables.h"
+
+namespace lw {
+
+// Caller arrays (API layout, see include/rrtmg_lw_b200.h).  Column i of the current chunk is
+// caller column c0 + i.
+struct ColIn {
+    const double *play, *plev, *tlay, *tlev, *tsfc;
+    const double *h2o, *o3, *co2, *ch4, *n2o, *o2, *cfc11, *cfc12, *cfc22, *ccl4;
+    const double *emis, *tauaer;
+    // strict rrtmg_lw() McICA arrays (140, ld, nlay) / (ld, nlay)
+    const double *cldfmcl, *taucmcl, *ciwpmcl, *clwpmcl, *reicmcl, *relqmcl;
+    // grid-mean cloud inputs of the fused entry (ld, nlay); tauc (16, ld, nlay)
+    const double *cldfrac, *ciwp, *clwp, *rei, *rel, *tauc, *alpha;
+    long ld;
+    int nlay;
+};
+
+struct ColOut {
+    double *uflx, *dflx, *hr, *uflxc, *dflxc, *hrc, *duflx_dt, *duflxc_dt;
+    long ld;
+};
+
+// per-(layer, column) fields written by the prep kernel (inatm + setcoef)
+enum Field {
+    F_FAC00, F_FAC01, F_FAC10, F_FAC11,
+    F_COLH2O, F_COLCO2, F_COLO3, F_COLN2O, F_COLCH4, F_COLO2, F_COLBRD, F_COLDRY,
+    F_SELFFAC, F_SELFFRAC, F_FORFAC, F_FORFRAC, F_MINORFRAC, F_SCALEMINOR, F_SCALEMINORN2,
+    F_WX1, F_WX2, F_WX3, F_WX4,
+    NFIELD
+};
+
+// cloud treatment of the band kernel
+enum CloudMode { CLD_NONE = 0, CLD_MASK = 1, CLD_ARRAYS = 2 };
+
+struct Scratch {
+    double* fld;        // NFIELD x nlay x pitch
+    int* ipack;         // nlay x pitch : jp | jt<<6 | jt1<<9 | indself<<12 | indfor<<16 | indminor<<18
+    double* pwvcm;      // pitch
+    int* laytrop;       // pitch
+    unsigned* mask;     // nlay x 5 x pitch : 140 sub-column cloud bits; bit 31 of word 4 = icldlyr
+    int* ctop;          // pitch : highest layer (1-based) with icldlyr = 1, 0 = cloud-free column
+    double* state;      // 5 x 16 x nlay x pitch : atrans, bbugas, atot, bbutot, efclfrac per (g, layer)
+    double* abscld;     // nlay x pitch : 1 - exp(-odcld) of the current band (CLD_MASK)
+    unsigned long long* status;  // sticky error word: code<<56 | (col+1)<<24 | lay
+    long pitch;         // columns per row of every scratch array (multiple of 32)
+    // debug capture of one column
+    int dbg_col;        // chunk-relative column or -1
+    double *dbg_taug, *dbg_fracs;  // (140, nlay)
+    int* dbg_itr;       // (140, nlay, 2)
+    int* dbg_ints;      // (nlay, 6)
+    double* dbg_facs;   // (nlay, 4)
+    double* dbg_scal;   // 2
+};
+
+struct RunCfg {
+    int ncol;        // columns in this chunk
+    long c0;         // first caller column of the chunk
+    int nlay;
+    int idrv;
+    int inflag, iceflag, liqflag;
+    int icld, irng, permuteseed;
+};
+
+}  // namespace lw

@@ -1,0 +1,411 @@
+// lw_kernels.cu -- column-parallel kernels around the band kernel: inatm + setcoef (prep), the
+// McICA sub-column generator (KISS / MT19937), cloud-flag scan for the strict rrtmg_lw() entry,
+// flux finalisation (fnet, heating rate), get_alpha, sub-column materialisation.
+#include <cstdio>
+
+#include "lw_band.cuh"
+#include "lw_launch.h"
+
+namespace lw {
+
+cudaError_t upload_constants_kernels(const ConstTab& c, const DevPtrs& d, const double (*refrat)[5]) {
+    return upload_constants_here(c, d, refrat);
+}
+
+__device__ __forceinline__ void raise(const Scratch& s, int code, long col, int lay) {
+    const unsigned long long v = ((unsigned long long)code << 56) | ((unsigned long long)(col + 1) << 24) |
+                                 (unsigned long long)(lay & 0xffffff);
+    atomicCAS(s.status, 0ull, v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// inatm (src/rrtmg_lw_rad.f90:755-870) + setcoef (src/rrtmg_lw_setcoef.f90:271-432) for one column
+// per thread.  The two whole-column sums (amttl, wvttl -> pwvcm) run in layer order, as in the
+// reference; everything else is per layer and goes to the column-innermost scratch.
+__global__ void __launch_bounds__(128) prep_kernel(ColIn in, Scratch s, RunCfg r) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= r.ncol) return;
+    const long ci = r.c0 + i;
+    const int nlay = r.nlay;
+    const long P = s.pitch, plane = (long)nlay * P;
+    const double amd = 28.9660, amw = 18.0160;
+    const double stpfac = 296. / 1013.;
+    const GTab& g = *D.g;
+    const bool dbg = s.dbg_col == i;
+    double amttl = 0.0, wvttl = 0.0;
+    int laytrop = 0;
+    double pz_lo = in.plev[ci];
+    const double pz0 = pz_lo;
+    for (int l = 0; l < nlay; ++l) {
+        const long a = ci + in.ld * l;
+        const long idx = (long)l * P + i;
+        const double pavel = in.play[a], tavel = in.tlay[a];
+        const double pz_hi = in.plev[ci + in.ld * (l + 1)];
+        const double h2o = in.h2o[a], co2 = in.co2[a], o3 = in.o3[a], n2o = in.n2o[a], ch4 = in.ch4[a], o2 = in.o2[a];
+        const double amm = (1. - h2o) * amd + h2o * amw;
+        const double coldry = (pz_lo - pz_hi) * 1.e3 * C.avogad / (1.e2 * C.grav * amm * (1. + h2o));
+        pz_lo = pz_hi;
+        double summol = 0.0;
+        summol = summol + co2; summol = summol + o3; summol = summol + n2o; summol = summol + 0.0;
+        summol = summol + ch4; summol = summol + o2;
+        const double wbrodl = coldry * (1. - summol);
+        const double w1 = coldry * h2o, w2 = coldry * co2, w3 = coldry * o3, w4 = coldry * n2o, w6 = coldry * ch4,
+                     w7 = coldry * o2;
+        amttl = amttl + coldry + w1;
+        wvttl = wvttl + w1;
+        double* F = s.fld + idx;
+        F[F_WX1 * plane] = coldry * in.ccl4[a] * 1.e-20;
+        F[F_WX2 * plane] = coldry * in.cfc11[a] * 1.e-20;
+        F[F_WX3 * plane] = coldry * in.cfc12[a] * 1.e-20;
+        F[F_WX4 * plane] = coldry * in.cfc22[a] * 1.e-20;
+
+        // setcoef
+        const double plog = log(pavel);
+        int jp = (int)(36. - 5 * (plog + 0.04));
+        jp = jp < 1 ? 1 : (jp > 58 ? 58 : jp);
+        const double fp = 5. * (ldg(&g.preflog[jp - 1]) - plog);
+        const double tr0 = ldg(&g.tref[jp - 1]), tr1 = ldg(&g.tref[jp]);
+        int jt = (int)(3. + (tavel - tr0) / 15.);
+        jt = jt < 1 ? 1 : (jt > 4 ? 4 : jt);
+        const double ft = ((tavel - tr0) / 15.) - (double)(jt - 3);
+        int jt1 = (int)(3. + (tavel - tr1) / 15.);
+        jt1 = jt1 < 1 ? 1 : (jt1 > 4 ? 4 : jt1);
+        const double ft1 = ((tavel - tr1) / 15.) - (double)(jt1 - 3);
+        const double water = w1 / coldry;
+        const double scalefac = pavel * stpfac / tavel;
+        double forfac = scalefac / (1. + water);
+        double selffac = water * forfac;
+        int indfor, indself = 0;
+        double forfrac, selffrac = 0.;
+        if (!(plog <= 4.56)) {
+            laytrop = laytrop + 1;
+            double factor = (332.0 - tavel) / 36.0;
+            indfor = min(2, max(1, (int)factor));
+            forfrac = factor - (double)indfor;
+            factor = (tavel - 188.0) / 7.2;
+            indself = min(9, max(1, (int)factor - 7));
+            selffrac = factor - (double)(indself + 7);
+        } else {
+            const double factor = (tavel - 188.0) / 36.0;
+            indfor = 3;
+            forfrac = factor - 1.0;
+        }
+        const double scaleminor = pavel / tavel;
+        const double scaleminorn2 = (pavel / tavel) * (wbrodl / (coldry + w1));
+        const double factor = (tavel - 180.8) / 7.2;
+        const int indminor = min(18, max(1, (int)factor));
+        const double minorfrac = factor - (double)indminor;
+        const double colh2o = 1.e-20 * w1;
+        double colco2 = 1.e-20 * w2, colo3 = 1.e-20 * w3, coln2o = 1.e-20 * w4, colch4 = 1.e-20 * w6;
+        const double colo2 = 1.e-20 * w7;
+        if (colco2 == 0.) colco2 = 1.e-32 * coldry;
+        if (colo3 == 0.) colo3 = 1.e-32 * coldry;
+        if (coln2o == 0.) coln2o = 1.e-32 * coldry;
+        if (colch4 == 0.) colch4 = 1.e-32 * coldry;
+        const double compfp = 1. - fp;
+        F[F_FAC10 * plane] = compfp * ft;
+        F[F_FAC00 * plane] = compfp * (1. - ft);
+        F[F_FAC11 * plane] = fp * ft1;
+        F[F_FAC01 * plane] = fp * (1. - ft1);
+        F[F_COLH2O * plane] = colh2o;
+        F[F_COLCO2 * plane] = colco2;
+        F[F_COLO3 * plane] = colo3;
+        F[F_COLN2O * plane] = coln2o;
+        F[F_COLCH4 * plane] = colch4;
+        F[F_COLO2 * plane] = colo2;
+        F[F_COLBRD * plane] = 1.e-20 * wbrodl;
+        F[F_COLDRY * plane] = coldry;
+        F[F_SELFFAC * plane] = colh2o * selffac;
+        F[F_SELFFRAC * plane] = selffrac;
+        F[F_FORFAC * plane] = colh2o * forfac;
+        F[F_FORFRAC * plane] = forfrac;
+        F[F_MINORFRAC * plane] = minorfrac;
+        F[F_SCALEMINOR * plane] = scaleminor;
+        F[F_SCALEMINORN2 * plane] = scaleminorn2;
+        s.ipack[idx] = jp | (jt << 6) | (jt1 << 9) | (indself << 12) | (indfor << 16) | (indminor << 18);
+        if (dbg) {
+            int* q = s.dbg_ints + 6 * l;
+            q[0] = jp; q[1] = jt; q[2] = jt1; q[3] = indself; q[4] = indfor; q[5] = indminor;
+            double* fq = s.dbg_facs + 4 * l;
+            fq[0] = compfp * (1. - ft); fq[1] = fp * (1. - ft1); fq[2] = compfp * ft; fq[3] = fp * ft1;
+        }
+    }
+    const double wvsh = (amw * wvttl) / (amd * amttl);
+    const double pwvcm = wvsh * (1.e3 * pz0) / (1.e2 * C.grav);
+    s.pwvcm[i] = pwvcm;
+    s.laytrop[i] = laytrop;
+    if (dbg) { s.dbg_scal[0] = laytrop; s.dbg_scal[1] = pwvcm; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// KISS generator step, src/mcica_subcol_gen_lw.f90:731-741 (INT32 wrap-around, logical shifts)
+struct Kiss {
+    unsigned s1, s2, s3, s4;
+    __device__ __forceinline__ double next() {
+        s1 = 69069u * s1 + 1327217885u;
+        s2 ^= s2 << 13; s2 ^= s2 >> 17; s2 ^= s2 << 5;
+        s3 = 18000u * (s3 & 65535u) + (s3 >> 16);
+        s4 = 30903u * (s4 & 65535u) + (s4 >> 16);
+        const int kiss = (int)(s1 + s2 + (s3 << 16) + s4);
+        return (double)kiss * 2.328306e-10 + 0.5;
+    }
+};
+
+// One thread = one column: draws its 140 x nlay (or 2 x that) numbers in the reference's order
+// (sub-column outer, layer inner), applies the overlap recurrence on the fly and packs the cloud
+// mask as 140 bits per layer.  generate_stochastic_clouds, mcica:442-679; icld 4/5 per the column
+// version mcica_subcol_gen_lw.1col.f90:543-611 (the GCM file does not compile as shipped).
+// Also validates the cloud-optics inputs the way cldprmc would STOP (cldprmc.f90:191-253).
+__global__ void __launch_bounds__(128) mcica_kiss_kernel(ColIn in, Scratch s, RunCfg r) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= r.ncol) return;
+    const long ci = r.c0 + i;
+    const int nlay = r.nlay;
+    const long P = s.pitch;
+    const int icld = r.icld;
+    unsigned mloc[LW_MAXLAY];  // mask word of the current 32 sub-columns, one per layer (L1-backed)
+    Kiss k;
+    {
+        const double p1 = in.play[ci] * 1.e2, p2 = in.play[ci + in.ld] * 1.e2;
+        if (p1 < p2) { raise(s, 4, ci, 1); s.ctop[i] = 0; return; }
+        const double p3 = in.play[ci + 2 * in.ld] * 1.e2, p4 = in.play[ci + 3 * in.ld] * 1.e2;
+        k.s1 = (unsigned)(int)((p1 - (double)(int)p1) * 1000000000.0);
+        k.s2 = (unsigned)(int)((p2 - (double)(int)p2) * 1000000000.0);
+        k.s3 = (unsigned)(int)((p3 - (double)(int)p3) * 1000000000.0);
+        k.s4 = (unsigned)(int)((p4 - (double)(int)p4) * 1000000000.0);
+        for (int n = 0; n < r.permuteseed; ++n) k.next();
+    }
+    const double cldmin = 1.0e-20;
+    for (int sc = 0; sc < NGPT; ++sc) {
+        const unsigned bit = 1u << (sc & 31);
+        if ((sc & 31) == 0)
+            for (int l = 0; l < nlay; ++l) mloc[l] = 0u;
+        double prev = 0.;
+        double rmax = 0.;
+        if (icld == 3) rmax = k.next();
+        for (int l = 0; l < nlay; ++l) {
+            double cf = in.cldfrac[ci + in.ld * l];
+            if (cf < cldmin) cf = 0.;
+            double x;
+            if (icld == 3) {
+                x = rmax;
+            } else {
+                x = k.next();
+                if (icld >= 4) {
+                    const double x2 = k.next();
+                    if (l > 0 && x2 < in.alpha[ci + in.ld * l]) x = prev;
+                } else if (icld == 2 && l > 0) {
+                    double cfm = in.cldfrac[ci + in.ld * (l - 1)];
+                    if (cfm < cldmin) cfm = 0.;
+                    if (prev > 1. - cfm) x = prev; else x = x * (1. - cfm);
+                }
+            }
+            prev = x;
+            if (x >= 1. - cf) mloc[l] |= bit;
+        }
+        if ((sc & 31) == 31 || sc == NGPT - 1)
+            for (int l = 0; l < nlay; ++l) s.mask[((long)l * 5 + (sc >> 5)) * P + i] = mloc[l];
+    }
+    // per-layer cloud flag (icldlyr), column cloud top, and cldprmc input validation
+    int ctop = 0;
+    for (int l = 0; l < nlay; ++l) {
+        unsigned any = 0;
+        for (int w = 0; w < 5; ++w) any |= s.mask[((long)l * 5 + w) * P + i];
+        if (any) {
+            s.mask[((long)l * 5 + 4) * P + i] |= 0x80000000u;
+            ctop = l + 1;
+            const long a = ci + in.ld * l;
+            const double ciwp = in.ciwp[a], clwp = in.clwp[a];
+            bool taubig = false;
+            if (in.tauc) for (int b = 0; b < 16; ++b) taubig |= in.tauc[b + 16 * a] >= cldmin;
+            if ((ciwp + clwp) >= cldmin || taubig) {
+                if (r.inflag == 1) raise(s, 1, ci, l + 1);
+                if (r.inflag == 2) {
+                    if (ciwp != 0.0) {
+                        const double rad = in.rei[a];
+                        if ((r.iceflag == 0 && rad < 10.0) || (r.iceflag == 1 && (rad < 13.0 || rad > 130.)) ||
+                            (r.iceflag == 2 && (rad < 5.0 || rad > 131.0)) || (r.iceflag == 3 && (rad < 5.0 || rad > 140.0)))
+                            raise(s, 2, ci, l + 1);
+                    }
+                    if (clwp != 0.0 && r.liqflag == 1) {
+                        const double rad = in.rel[a];
+                        if (rad < 2.5 || rad > 60.) raise(s, 3, ci, l + 1);
+                    }
+                }
+            }
+        }
+    }
+    s.ctop[i] = ctop;
+}
+
+// Cloud flags for the strict rrtmg_lw() entry: one warp scans the 140 sub-column fractions of a
+// (column, layer); icldlyr = any(cldfmc == 1) (rtrnmc.f90:316-329); validates like cldprmc.
+__global__ void __launch_bounds__(128) cldflags_kernel(ColIn in, Scratch s, RunCfg r) {
+    const int lane = threadIdx.x & 31;
+    const long wid = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long total = (long)r.ncol * r.nlay;
+    if (wid >= total) return;
+    const int l = (int)(wid / r.ncol);
+    const int i = (int)(wid % r.ncol);
+    const long ci = r.c0 + i;
+    const long a = ci + in.ld * l;
+    const double* cf = in.cldfmcl + 140 * a;
+    bool one = false;
+    int bad = 0;
+    for (int g = lane; g < 140; g += 32) {
+        const double c = cf[g];
+        one |= (c == 1.);
+        if (c >= 1.e-20) {
+            const double ciwp = in.ciwpmcl[140 * a + g], clwp = in.clwpmcl[140 * a + g];
+            if ((ciwp + clwp) >= 1.e-20 || in.taucmcl[140 * a + g] >= 1.e-20) {
+                if (r.inflag == 1) bad = 1;
+                if (r.inflag == 2) {
+                    if (ciwp != 0.0) {
+                        const double rad = in.reicmcl[a];
+                        if ((r.iceflag == 0 && rad < 10.0) || (r.iceflag == 1 && (rad < 13.0 || rad > 130.)) ||
+                            (r.iceflag == 2 && (rad < 5.0 || rad > 131.0)) || (r.iceflag == 3 && (rad < 5.0 || rad > 140.0)))
+                            bad = 2;
+                    }
+                    if (clwp != 0.0 && r.liqflag == 1) {
+                        const double rad = in.relqmcl[a];
+                        if ((rad < 2.5 || rad > 60.) && bad == 0) bad = 3;
+                    }
+                }
+            }
+        }
+    }
+    const unsigned any = __ballot_sync(0xffffffffu, one);
+    const unsigned anybad = __ballot_sync(0xffffffffu, bad != 0);
+    if (anybad) {
+        const int src = __ffs(anybad) - 1;
+        const int code = __shfl_sync(0xffffffffu, bad, src);
+        if (lane == 0) raise(s, code, ci, l + 1);
+    }
+    if (lane == 0) {
+        s.mask[((long)l * 5 + 4) * s.pitch + i] = any ? 0x80000000u : 0u;
+        if (any) atomicMax(&s.ctop[i], l + 1);
+    }
+}
+
+__global__ void zero_int_kernel(int* p, long n) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// flux close-out: x fluxfac, net flux, heating rate; clear = total where no cloud was seen.
+// rtrnmc.f90:569-593 and the output index shift of rad.f90:572-590.
+__global__ void __launch_bounds__(128) finalize_kernel(ColIn in, ColOut out, Scratch s, RunCfg r, int cloudy) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= r.ncol) return;
+    const long ci = r.c0 + i;
+    const int nlay = r.nlay;
+    const bool sep = cloudy && s.ctop[i] > 0;
+    double fnet_lo = 0., fnetc_lo = 0., pz_lo = 0.;
+    for (int lev = 0; lev <= nlay; ++lev) {
+        const long o = ci + out.ld * lev;
+        const double u = out.uflx[o] * C.fluxfac;
+        const double d = out.dflx[o] * C.fluxfac;
+        double uc, dc;
+        if (sep) { uc = out.uflxc[o] * C.fluxfac; dc = out.dflxc[o] * C.fluxfac; }
+        else { uc = u; dc = d; }
+        out.uflx[o] = u; out.dflx[o] = d; out.uflxc[o] = uc; out.dflxc[o] = dc;
+        if (r.idrv == 1 && !sep) out.duflxc_dt[o] = out.duflx_dt[o];
+        const double fnet = u - d, fnetc = uc - dc;
+        const double pz = in.plev[ci + in.ld * lev];
+        if (lev > 0) {
+            const long oh = ci + out.ld * (lev - 1);
+            out.hr[oh] = C.heatfac * (fnet_lo - fnet) / (pz_lo - pz);
+            out.hrc[oh] = C.heatfac * (fnetc_lo - fnetc) / (pz_lo - pz);
+        }
+        fnet_lo = fnet; fnetc_lo = fnetc; pz_lo = pz;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// get_alpha, src/mcica_subcol_gen_lw.f90:129-178
+__global__ void get_alpha_kernel(int ncol, long ld, int nlay, int icld, int idcor, double decorr_con, const double* dz,
+                                 const double* lat, int juldat, const double* cldfrac, double* alpha, double am1,
+                                 double am2, double am4) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ncol) return;
+    if (icld != 4 && icld != 5) return;
+    double decorr_len;
+    if (idcor == 1) {
+        const double amr = 7.0;
+        double am3;
+        if (juldat > 181) am3 = -4. * amr / 365. * (juldat - 272);
+        else am3 = 4. * amr / 365. * (juldat - 91);
+        const double d = lat[i] - am3;
+        const double decorr_lat = am1 + am2 * exp(-(d * d) / (am4 * am4));
+        decorr_len = decorr_lat * 1.e3;
+    } else {
+        decorr_len = decorr_con;
+    }
+    double decorr_inv = 1.0;
+    if (decorr_len >= 0.0) decorr_inv = 1.0 / decorr_len;
+    alpha[i] = 0.0;
+    for (int k = 1; k < nlay; ++k) {
+        double a = exp(-(0.5 * (dz[i + ld * k] + dz[i + ld * (k - 1)])) * decorr_inv);
+        if (icld == 5 && cldfrac[i + ld * k] == 0.0 && cldfrac[i + ld * (k - 1)] > 0.0) a = 0.0;
+        alpha[i + ld * k] = a;
+    }
+}
+
+// Sub-column arrays of mcica_subcol_lw from the packed mask (mcica:658-679): one thread per
+// (g, column, layer) element, g fastest -> coalesced 8-byte stores.
+__global__ void materialize_kernel(ColIn in, Scratch s, RunCfg r, double* cldfmcl, double* ciwpmcl, double* clwpmcl,
+                                   double* reicmcl, double* relqmcl, double* taucmcl) {
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long total = (long)r.ncol * r.nlay * NGPT;
+    if (t >= total) return;
+    const int g = (int)(t % NGPT);
+    const long cl = t / NGPT;
+    const int i = (int)(cl % r.ncol);
+    const int l = (int)(cl / r.ncol);
+    const long ci = r.c0 + i;
+    const long a = ci + in.ld * l;
+    const unsigned w = s.mask[((long)l * 5 + (g >> 5)) * s.pitch + i];
+    const bool on = (w >> (g & 31)) & 1u;
+    const long o = g + 140 * a;
+    // 0-based band of g-point g (ngb, src/rrtmg_lw_init.f90:362-377)
+    constexpr int goff[NBND] = {0, 10, 22, 38, 52, 68, 76, 88, 96, 108, 114, 122, 130, 134, 136, 138};
+    int band = 0;
+#pragma unroll
+    for (int b = 1; b < NBND; ++b) band += (g >= goff[b]);
+    cldfmcl[o] = on ? 1. : 0.;
+    clwpmcl[o] = on ? in.clwp[a] : 0.;
+    ciwpmcl[o] = on ? in.ciwp[a] : 0.;
+    taucmcl[o] = on ? in.tauc[band + 16 * a] : 0.;
+    if (g == 0) { reicmcl[a] = in.rei[a]; relqmcl[a] = in.rel[a]; }
+}
+
+// ---------------------------------------------------------------------------------------------
+static inline int nblk(long n, int b) { return (int)((n + b - 1) / b); }
+
+void launch_prep(const ColIn& in, const Scratch& s, const RunCfg& r, cudaStream_t st) {
+    prep_kernel<<<nblk(r.ncol, 128), 128, 0, st>>>(in, s, r);
+}
+void launch_mcica_kiss(const ColIn& in, const Scratch& s, const RunCfg& r, cudaStream_t st) {
+    mcica_kiss_kernel<<<nblk(r.ncol, 128), 128, 0, st>>>(in, s, r);
+}
+void launch_cldflags(const ColIn& in, const Scratch& s, const RunCfg& r, cudaStream_t st) {
+    zero_int_kernel<<<nblk(r.ncol, 256), 256, 0, st>>>(s.ctop, r.ncol);
+    cldflags_kernel<<<nblk((long)r.ncol * r.nlay * 32, 128), 128, 0, st>>>(in, s, r);
+}
+void launch_finalize(const ColIn& in, const ColOut& out, const Scratch& s, const RunCfg& r, int cloudy, cudaStream_t st) {
+    finalize_kernel<<<nblk(r.ncol, 128), 128, 0, st>>>(in, out, s, r, cloudy);
+}
+void launch_get_alpha(int ncol, long ld, int nlay, int icld, int idcor, double decorr_con, const double* dz,
+                      const double* lat, int juldat, const double* cldfrac, double* alpha, double am1, double am2,
+                      double am4, cudaStream_t st) {
+    get_alpha_kernel<<<nblk(ncol, 128), 128, 0, st>>>(ncol, ld, nlay, icld, idcor, decorr_con, dz, lat, juldat, cldfrac,
+                                                      alpha, am1, am2, am4);
+}
+void launch_materialize(const ColIn& in, const Scratch& s, const RunCfg& r, double* cldfmcl, double* ciwpmcl,
+                        double* clwpmcl, double* reicmcl, double* relqmcl, double* taucmcl, cudaStream_t st) {
+    const long total = (long)r.ncol * r.nlay * NGPT;
+    materialize_kernel<<<nblk(total, 256), 256, 0, st>>>(in, s, r, cldfmcl, ciwpmcl, clwpmcl, reicmcl, relqmcl, taucmcl);
+}
+
+}  // namespace lw

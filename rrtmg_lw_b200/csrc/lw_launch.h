@@ -1,0 +1,33 @@
+// lw_launch.h -- host-callable launchers of the kernels (one set per translation unit).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "lw_device.cuh"
+
+#ifndef LW_MAXLAY
+#define LW_MAXLAY 640  // >= mxlay = 603 of modules/parrrtm.f90:31
+#endif
+#define LW_NUM_BAND_TUS 6
+
+namespace lw {
+struct DevPtrs;
+
+void launch_prep(const ColIn&, const Scratch&, const RunCfg&, cudaStream_t);
+void launch_mcica_kiss(const ColIn&, const Scratch&, const RunCfg&, cudaStream_t);
+void launch_cldflags(const ColIn&, const Scratch&, const RunCfg&, cudaStream_t);
+void launch_finalize(const ColIn&, const ColOut&, const Scratch&, const RunCfg&, int cloudy, cudaStream_t);
+void launch_get_alpha(int ncol, long ld, int nlay, int icld, int idcor, double decorr_con, const double* dz,
+                      const double* lat, int juldat, const double* cldfrac, double* alpha, double am1, double am2,
+                      double am4, cudaStream_t);
+void launch_materialize(const ColIn&, const Scratch&, const RunCfg&, double* cldfmcl, double* ciwpmcl, double* clwpmcl,
+                        double* reicmcl, double* relqmcl, double* taucmcl, cudaStream_t);
+cudaError_t upload_constants_kernels(const ConstTab&, const DevPtrs&, const double (*refrat)[5]);
+
+// band kernels: each TU handles a subset of bands; returns false when the band is not its own
+#define LW_DECL_TU(n)                                                                                         \
+    bool launch_band_tu##n(int band, int cld, int idrv, const ColIn&, const ColOut&, const Scratch&, const RunCfg&, \
+                           cudaStream_t);                                                                     \
+    cudaError_t upload_constants_tu##n(const ConstTab&, const DevPtrs&, const double (*refrat)[5]);
+LW_DECL_TU(0) LW_DECL_TU(1) LW_DECL_TU(2) LW_DECL_TU(3) LW_DECL_TU(4) LW_DECL_TU(5)
+#undef LW_DECL_TU
+}  // namespace lw
