@@ -139,3 +139,27 @@ def make_batch(ncol: int, nlay: int = 72, cloudy: bool = False, aerosol: bool = 
         b.dz = 287.05 * tlay / 9.8066 * torch.log(plev[:-1] / plev[1:])
     b.meta = dict(seed=seed, cloudy=cloudy, aerosol=aerosol, stress_co2=stress_co2)
     return b
+
+
+def batch_from_profile(prof: dict, ncol: int = 1, device="cpu") -> Batch:
+    """GCM-style inputs from one parsed column-mode profile (tests/golden/std_atm.json, made by
+    tools/make_golden.py from run_examples_std_atm/input_rrtm_*): pavel/tavel -> play/tlay,
+    pz/tz -> plev/tlev, molecular mixing ratios (h2o, co2, o3, n2o, co, ch4, o2) -> vmr arrays.
+    The column is replicated ncol times.  (The column-mode program derives coldry from the file's
+    broadening-gas column, the GCM entry from the level pressures, src/rrtmg_lw_rad.f90:807-809, so
+    the k-dependent goldens are comparable only approximately through this path.)"""
+    f64 = torch.float64
+    nlay = prof["nlayers"]
+
+    def col(v):
+        return torch.tensor(v, dtype=f64, device=device)[:, None].repeat(1, ncol).contiguous()
+
+    wkl = torch.tensor(prof["wkl"], dtype=f64, device=device)   # (nlay, 7)
+    z = torch.zeros(nlay, ncol, dtype=f64, device=device)
+    g = lambda m: wkl[:, m][:, None].repeat(1, ncol).contiguous()  # noqa: E731
+    return Batch(ncol=ncol, nlay=nlay, play=col(prof["pavel"]), plev=col(prof["pz"]), tlay=col(prof["tavel"]),
+                 tlev=col(prof["tz"]), tsfc=torch.full((ncol,), prof["tbound"], dtype=f64, device=device),
+                 h2ovmr=g(0), co2vmr=g(1), o3vmr=g(2), n2ovmr=g(3), ch4vmr=g(5), o2vmr=g(6),
+                 cfc11vmr=z.clone(), cfc12vmr=z.clone(), cfc22vmr=z.clone(), ccl4vmr=z.clone(),
+                 emis=torch.ones(NBND, ncol, dtype=f64, device=device),
+                 tauaer=torch.zeros(NBND, nlay, ncol, dtype=f64, device=device), meta=dict(profile=True))

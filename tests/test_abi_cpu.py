@@ -1,0 +1,70 @@
+"""The C-ABI library loads and exports every symbol include/rrtmg_lw_b200.h declares (no
+compute calls -- there is no GPU in the CPU test tier), and the host mirror refuses to run
+without the CUDA path."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    txt = open(os.path.join(ROOT, "include", "rrtmg_lw_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(rrtmg_lw_b200_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    from rrtmg_lw_b200 import api
+    names = _declared()
+    assert len(names) >= 14 and "rrtmg_lw_b200_rrtmg_lw" in names and "rrtmg_lw_b200_ini" in names
+    lib = ctypes.CDLL(api.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), "missing export " + n
+
+
+def test_strerror_and_version_do_not_need_a_gpu():
+    from rrtmg_lw_b200 import api
+    L = api.lib()
+    assert b"ICE RADIUS" in L.rrtmg_lw_b200_strerror(2)
+    assert b"LIQUID" in L.rrtmg_lw_b200_strerror(3)
+    assert b"sm_100a" in L.rrtmg_lw_b200_version()
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device init must fail with ERR_CUDA (5), and compute entries with
+    ERR_NOT_INIT (6) -- never a silent CPU path."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from rrtmg_lw_b200 import api, kdata
+    with pytest.raises(api.RrtmgLwError) as e:
+        api.rrtmg_lw_ini(1004.0, kdata.synthetic_blob())
+    assert e.value.code == 5
+    z = np.zeros((4, 2))
+    with pytest.raises(api.RrtmgLwError) as e2:
+        api.get_alpha(1, 2, 4, 4, 0, 2500.0, z, np.zeros(2), 1, z, z.copy())
+    assert e2.value.code == 6
+
+
+def test_kdata_header_matches_python_layout():
+    from rrtmg_lw_b200 import kdata
+    arr = kdata.karrays()
+    assert len(arr) == 115 and kdata.KDATA_DOUBLES == 211856
+    txt = open(os.path.join(ROOT, "include", "rrtmg_lw_kdata_layout.h")).read()
+    assert "#define RRTMG_LW_KDATA_DOUBLES 211856" in txt
+
+
+def test_product_does_not_reference_the_oracle():
+    """Nothing under rrtmg_lw_b200/ may import, link or call the oracle."""
+    pkg = os.path.join(ROOT, "rrtmg_lw_b200")
+    for dp, _, files in os.walk(pkg):
+        if "_generated" in dp:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")) or f == "Makefile":
+                t = open(os.path.join(dp, f)).read()
+                assert "oracle" not in t.lower().replace("oracle/_ref", ""), os.path.join(dp, f)

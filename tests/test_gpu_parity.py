@@ -1,0 +1,268 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on identical seeded inputs.
+
+Bars (BASELINE.json north_star): integer work bit-exact (interpolation indices, table indices,
+McICA masks); FP64 fluxes within 1e-6 W m-2 and heating rates within 1e-6 K day-1.
+"""
+import numpy as np
+import pytest
+import torch
+
+from rrtmg_lw_b200 import driver, synth
+
+pytestmark = pytest.mark.gpu
+
+FLUX_TOL = 1e-6   # W m-2
+HR_TOL = 1e-6     # K day-1
+KEYS = ("uflx", "dflx", "uflxc", "dflxc", "hr", "hrc")
+
+
+def _np(x):
+    return x.detach().cpu().numpy() if hasattr(x, "detach") else x
+
+
+def _check(got, ref, idrv=0, what=""):
+    keys = KEYS + (("duflx_dt", "duflxc_dt") if idrv else ())
+    for k in keys:
+        tol = HR_TOL if k.startswith("hr") else FLUX_TOL
+        err = float(np.abs(_np(got[k]) - ref[k]).max())
+        assert err <= tol, (what, k, err)
+
+
+def test_clear_sky_batch_and_stage_ints(gpu, oracle):
+    """Config 2 shape (clear, idrv=0, 72 layers) at a size the oracle does in seconds."""
+    b = synth.make_batch(2048, 72)
+    ref = oracle.rrtmg_lw(b, nthreads=8)
+    gpu.debug_capture(1234)
+    got = driver.run_clear_or_strict(b, device="cuda:0")
+    gpu.sync()
+    _check(got, ref, what="clear")
+    assert np.array_equal(_np(got["uflx"]), _np(got["uflxc"]))
+    s = oracle.column_stages(b, 1234)
+    d = gpu.debug_stages(1234, 72)
+    gpu.debug_capture(None)
+    assert np.array_equal(s["ints6"], d["ints6"]), "jp/jt/jt1/indself/indfor/indminor must be bit-exact"
+    assert s["laytrop"] == d["laytrop"]
+    assert np.array_equal(s["itr"], d["itr"]), "rtrnmc table indices must be bit-exact"
+    assert np.array_equal(s["fracs"], d["fracs"])
+    rel = np.abs(s["taug"] - d["taug"]) / np.maximum(np.abs(s["taug"]), 1e-300)
+    assert rel.max() < 1e-13   # only libm log/exp/pow rounding may differ
+    assert (s["taug"] == d["taug"]).mean() > 0.9
+
+
+@pytest.mark.parametrize("icld", [1, 2, 3])
+def test_mcica_mask_bit_exact(gpu, oracle, icld):
+    b = synth.make_batch(300, 72, cloudy=True)
+    ref = oracle.mcica_subcol_lw(b, icld, permuteseed=7, irng=0)
+    got = driver.run_mcica_subcol(b, icld, permuteseed=7, device="cuda:0")
+    for k in ("cldfmcl", "ciwpmcl", "clwpmcl", "taucmcl", "reicmcl", "relqmcl"):
+        assert np.array_equal(_np(got[k]), ref[k]), (icld, k)
+    assert ref["cldfmcl"].sum() > 0
+
+
+@pytest.mark.parametrize("icld", [4, 5])
+def test_exponential_overlap_masks_and_alpha(gpu, oracle, icld):
+    b = synth.make_batch(200, 72, cloudy=True)
+    al_ref = oracle.get_alpha(b, icld, idcor=1, juldat=200)
+    al = np.zeros_like(al_ref)
+    gpu.get_alpha(1, b.ncol, b.nlay, icld, 1, 2500.0, b.dz.numpy().copy(), b.lat.numpy().copy(), 200,
+                  b.cldfrac.numpy().copy(), al)
+    assert np.abs(al - al_ref).max() < 1e-15   # exp() rounding only
+    ref = oracle.mcica_subcol_lw(b, icld, permuteseed=2, irng=0, alpha=al)
+    got = driver.run_mcica_subcol(b, icld, permuteseed=2, alpha=al, device="cuda:0")
+    assert np.array_equal(_np(got["cldfmcl"]), ref["cldfmcl"])
+
+
+@pytest.mark.parametrize("icld,idrv,aer", [(2, 0, False), (1, 1, True), (3, 0, True), (5, 1, True)])
+def test_fused_cloudy_matches_oracle(gpu, oracle, icld, idrv, aer):
+    """Configs 3/4 shapes: generator + radiation fused on the device vs mcica_subcol_lw ->
+    rrtmg_lw in the oracle (icld 5 with idcor = 1 alpha, aerosol tau, idrv = 1)."""
+    b = synth.make_batch(512, 72, cloudy=True, aerosol=aer)
+    alpha = oracle.get_alpha(b, icld, idcor=1, juldat=200) if icld >= 4 else None
+    mc = oracle.mcica_subcol_lw(b, icld, permuteseed=1, irng=0, alpha=alpha)
+    ref = oracle.rrtmg_lw(b, icld=icld, idrv=idrv, inflglw=2, iceflglw=3, liqflglw=1, mc=mc, nthreads=8)
+    assert ref["rc"] == 0
+    got = driver.run_fused(b, icld=icld, idrv=idrv, alpha=alpha, device="cuda:0")
+    gpu.sync()
+    _check(got, ref, idrv, what="fused icld=%d" % icld)
+    # clouds really matter in this batch
+    assert np.abs(ref["dflx"][0] - ref["dflxc"][0]).max() > 1.0
+
+
+@pytest.mark.parametrize("iceflag,liqflag", [(0, 0), (1, 1), (2, 1), (3, 1)])
+def test_strict_rrtmg_lw_with_mcica_arrays(gpu, oracle, iceflag, liqflag):
+    """The literal rrtmg_lw() boundary: (140,ncol,nlay) sub-column arrays in, all ice/liquid options."""
+    b = synth.make_batch(192, 72, cloudy=True, aerosol=True)
+    b.rei = b.rei.clamp(15.0, 125.0)
+    mc = oracle.mcica_subcol_lw(b, 2, permuteseed=3, irng=0)
+    ref = oracle.rrtmg_lw(b, icld=2, idrv=1, inflglw=2, iceflglw=iceflag, liqflglw=liqflag, mc=mc, nthreads=8)
+    assert ref["rc"] == 0
+    got = driver.run_clear_or_strict(b, icld=2, idrv=1, inflglw=2, iceflglw=iceflag, liqflglw=liqflag, mc=mc,
+                                     device="cuda:0")
+    gpu.sync()
+    _check(got, ref, 1, what="strict ice=%d" % iceflag)
+    # host-pointer call gives the same numbers as the device-pointer call
+    goth = driver.run_clear_or_strict(b, icld=2, idrv=1, inflglw=2, iceflglw=iceflag, liqflglw=liqflag, mc=mc)
+    for k in KEYS:
+        assert np.array_equal(goth[k], _np(got[k])), k
+
+
+def test_strict_general_cloud_arrays(gpu, oracle):
+    """rrtmg_lw() accepts arbitrary per-g cloud arrays: fractional cldfmcl (only == 1 counts as
+    cloudy in rtrnmc, T9), per-g water paths, inflag = 0 with prescribed tau."""
+    b = synth.make_batch(128, 40, cloudy=True)
+    rng = np.random.default_rng(5)
+    shp = (b.nlay, b.ncol, 140)
+    cf = np.where(rng.random(shp) < 0.15, 1.0, np.where(rng.random(shp) < 0.1, rng.random(shp), 0.0))
+    mc = dict(cldfmcl=cf, taucmcl=rng.random(shp) * 3 * (cf > 0), ciwpmcl=rng.random(shp) * 20 * (cf > 0),
+              clwpmcl=rng.random(shp) * 40 * (cf > 0), reicmcl=30 + 50 * rng.random(shp[:2]),
+              relqmcl=5 + 10 * rng.random(shp[:2]))
+    for inflag in (0, 2):
+        ref = oracle.rrtmg_lw(b, icld=1, inflglw=inflag, iceflglw=3, liqflglw=1, mc=mc, nthreads=8)
+        assert ref["rc"] == 0
+        got = driver.run_clear_or_strict(b, icld=1, inflglw=inflag, iceflglw=3, liqflglw=1, mc=mc, device="cuda:0")
+        gpu.sync()
+        _check(got, ref, what="general inflag=%d" % inflag)
+
+
+def test_inflag0_fused_prescribed_tau(gpu, oracle):
+    b = synth.make_batch(128, 72, cloudy=True)
+    b.tauc = (2.0 * torch.rand(b.nlay, b.ncol, 16, dtype=torch.float64)) * (b.cldfrac > 0)[..., None]
+    mc = oracle.mcica_subcol_lw(b, 2, permuteseed=1, irng=0)
+    ref = oracle.rrtmg_lw(b, icld=2, inflglw=0, mc=mc, nthreads=8)
+    got = driver.run_fused(b, icld=2, inflglw=0, iceflglw=0, liqflglw=0, device="cuda:0")
+    gpu.sync()
+    _check(got, ref, what="inflag0")
+
+
+def test_std_atm_profiles_and_planck_known_answer(gpu, oracle, std_atm):
+    """Config 1: the reference's own example profiles (51-60 layers) through the same ABI; the
+    surface upward flux reproduces the shipped output files (data-independent known answer)."""
+    for case, d in std_atm.items():
+        b = synth.batch_from_profile(d["input"], ncol=3)
+        ref = oracle.rrtmg_lw(b)
+        got = driver.run_clear_or_strict(b)   # host-pointer call
+        _check(got, ref, what=case)
+        assert abs(got["uflx"][0, 0] - d["output"][-1][2]) < 1.5e-3
+
+
+def test_137_layers_and_stress_gases(gpu, oracle):
+    """Config 5 layer count; CO2 3x / N2O 1.9x the reference mixing ratios exercise the pow() paths
+    (taumol.f90:550,736,1355,...)."""
+    b = synth.make_batch(256, 137, cloudy=True, stress_co2=True)
+    mc = oracle.mcica_subcol_lw(b, 2, permuteseed=1, irng=0)
+    ref = oracle.rrtmg_lw(b, icld=2, inflglw=2, iceflglw=3, liqflglw=1, mc=mc, nthreads=8)
+    got = driver.run_fused(b, icld=2, device="cuda:0")
+    gpu.sync()
+    _check(got, ref, what="137 layers")
+
+
+def test_chunking_and_leading_dimension_invariance(gpu, oracle):
+    """Results do not depend on the internal chunk size nor on ld > ncol (GCM pcols chunks)."""
+    b = synth.make_batch(500, 72, cloudy=True)
+    a = driver.run_fused(b, icld=2, device="cuda:0")
+    gpu.set_chunk(96)
+    try:
+        c = driver.run_fused(b, icld=2, device="cuda:0")
+        h = driver.run_fused(b, icld=2)
+    finally:
+        gpu.set_chunk(32768)
+    for k in KEYS:
+        assert torch.equal(a[k], c[k]), k
+        assert np.array_equal(_np(a[k]), h[k]), k
+    # ld > ncol: run on the first 321 columns of the 500-column arrays
+    from rrtmg_lw_b200 import api
+    conv = driver._conv(b, "cuda:0")
+    at = driver.atm_args(b, conv)
+    cl = [conv(x) for x in (b.cldfrac, b.ciwp, b.clwp, b.rei, b.rel, b.tauc)]
+    out = driver._outputs(b.nlay, b.ncol, like=at[0])
+    api.rrtmg_lw_mcica(321, b.nlay, 2, 0, 1, 0, *at, 2, 3, 1, *cl, None, conv(b.tauaer), out["uflx"], out["dflx"],
+                       out["hr"], out["uflxc"], out["dflxc"], out["hrc"], None, None, ld=500)
+    gpu.sync()
+    for k in KEYS:
+        assert torch.equal(out[k][:, :321], a[k][:, :321]), k
+        assert float(out[k][:, 321:].abs().max()) == 0.0
+
+
+def test_error_codes_match_reference_stops(gpu):
+    from rrtmg_lw_b200 import api
+    b = synth.make_batch(64, 30, cloudy=True)
+    b.cldfrac[:] = 0.5; b.ciwp[:] = 5.0; b.clwp[:] = 5.0
+    b.rei[:] = 150.0
+    with pytest.raises(api.RrtmgLwError) as e:
+        driver.run_fused(b, icld=1)
+    assert e.value.code == 2
+    b.rei[:] = 50.0; b.rel[:] = 70.0
+    with pytest.raises(api.RrtmgLwError) as e:
+        driver.run_fused(b, icld=1)
+    assert e.value.code == 3
+    b.rel[:] = 10.0
+    with pytest.raises(api.RrtmgLwError) as e:
+        driver.run_fused(b, icld=1, inflglw=1)
+    assert e.value.code == 1
+    b.play[0], b.play[1] = b.play[1].clone(), b.play[0].clone()
+    with pytest.raises(api.RrtmgLwError) as e:
+        driver.run_fused(b, icld=1)
+    assert e.value.code == 4
+    with pytest.raises(api.RrtmgLwError) as e:
+        driver.run_fused(synth.make_batch(8, 30, cloudy=True), icld=9)
+    assert e.value.code == 1
+
+
+def test_default_real_kind_8(gpu, oracle, kblob):
+    """Semantics of the shipped -r8 makefiles: both sides switch their default-kind literals."""
+    from oracle import orc
+    from rrtmg_lw_b200 import api
+    b = synth.make_batch(256, 72, cloudy=True)
+    try:
+        orc.ini(kblob, 1004.0, 8)
+        api.rrtmg_lw_ini(1004.0, kblob, 8)
+        assert np.array_equal(api.get_table("tau_tbl"), orc.get_table("tau_tbl"))
+        mc = orc.mcica_subcol_lw(b, 2, permuteseed=1, irng=0)
+        ref8 = orc.rrtmg_lw(b, icld=2, inflglw=2, iceflglw=3, liqflglw=1, mc=mc, nthreads=8)
+        got8 = driver.run_fused(b, icld=2, device="cuda:0")
+        api.sync()
+        _check(got8, ref8, what="drk8")
+    finally:
+        orc.ini(kblob, 1004.0, 4)
+        api.rrtmg_lw_ini(1004.0, kblob, 4)
+    ref4 = orc.rrtmg_lw(b, icld=2, inflglw=2, iceflglw=3, liqflglw=1, mc=mc, nthreads=8)
+    # the two Fortran builds differ by more than the parity tolerance
+    assert np.abs(ref4["uflx"] - ref8["uflx"]).max() > 1e-6
+
+
+def test_init_tables_bit_identical(gpu, oracle):
+    ngc = [10, 12, 16, 14, 16, 8, 12, 8, 12, 6, 8, 8, 4, 2, 2, 2]
+    for n in ("tau_tbl", "exp_tbl", "tfn_tbl", "rwgt"):
+        assert np.array_equal(gpu.get_table(n), oracle.get_table(n)), n
+    from rrtmg_lw_b200 import kdata
+    for band, name, lead, gfirst, _ in kdata.karrays():
+        red = ("absa" if name == "kao" else "absb" if name == "kbo" else
+               "ka" + name[3:] if name.startswith("kao") else "kb" + name[3:] if name.startswith("kbo") else name[:-1])
+        a, o = gpu.get_table("%d:%s" % (band, red)), oracle.get_table("%d:%s" % (band, red))
+        assert a.size == lead * ngc[band - 1] and np.array_equal(a, o), (band, red)
+
+
+def test_full_size_column_independence(gpu, oracle):
+    """At a bench-scale batch (131072 columns, chunked), every column's result equals the result
+    of the same column run through the oracle alone: a sample of 192 columns is checked."""
+    n = 131072
+    b = synth.make_batch(n, 72, cloudy=True, device="cuda:0")
+    got = driver.run_fused(b, icld=2, device="cuda:0")
+    gpu.sync()
+    idx = torch.randperm(n, generator=torch.Generator().manual_seed(1))[:192]
+    sub = synth.Batch(ncol=192, nlay=72, **{k: None for k in ()},
+                      play=b.play[:, idx].cpu(), plev=b.plev[:, idx].cpu(), tlay=b.tlay[:, idx].cpu(),
+                      tlev=b.tlev[:, idx].cpu(), tsfc=b.tsfc[idx].cpu(), h2ovmr=b.h2ovmr[:, idx].cpu(),
+                      o3vmr=b.o3vmr[:, idx].cpu(), co2vmr=b.co2vmr[:, idx].cpu(), ch4vmr=b.ch4vmr[:, idx].cpu(),
+                      n2ovmr=b.n2ovmr[:, idx].cpu(), o2vmr=b.o2vmr[:, idx].cpu(), cfc11vmr=b.cfc11vmr[:, idx].cpu(),
+                      cfc12vmr=b.cfc12vmr[:, idx].cpu(), cfc22vmr=b.cfc22vmr[:, idx].cpu(),
+                      ccl4vmr=b.ccl4vmr[:, idx].cpu(), emis=b.emis[:, idx].cpu(), tauaer=b.tauaer[:, :, idx].cpu(),
+                      cldfrac=b.cldfrac[:, idx].cpu(), ciwp=b.ciwp[:, idx].cpu(), clwp=b.clwp[:, idx].cpu(),
+                      rei=b.rei[:, idx].cpu(), rel=b.rel[:, idx].cpu(), tauc=b.tauc[:, idx].cpu())
+    sub = synth.Batch(**{k: (v.contiguous() if hasattr(v, "contiguous") else v) for k, v in sub.__dict__.items()})
+    mc = oracle.mcica_subcol_lw(sub, 2, permuteseed=1, irng=0)
+    ref = oracle.rrtmg_lw(sub, icld=2, inflglw=2, iceflglw=3, liqflglw=1, mc=mc, nthreads=8)
+    for k in KEYS:
+        tol = HR_TOL if k.startswith("hr") else FLUX_TOL
+        err = float(np.abs(got[k][:, idx.to("cuda:0")].cpu().numpy() - ref[k]).max())
+        assert err <= tol, (k, err)
