@@ -1,0 +1,354 @@
+#!/usr/bin/env python3
+"""Benchmark of the RRTMG_LW longwave hot path on B200 (BASELINE.json metric: columns/s,
+72 layers, 140 g-points, McICA cloudy).
+
+    python bench.py --gpus N --steps K --warmup W            # this implementation
+    python bench.py --impl reference --gpus N --steps K ...  # CPU reference arm (oracle port)
+
+One "step" = one pass of the hot path (mcica_subcol_lw -> rrtmg_lw, fused device entry) over the
+rank's column batch.  N > 1: one process per GPU (torchrun), the column batch is block-partitioned,
+no data-path collective; value = columns of all ranks / max-over-ranks device time ("weak").
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NLAY = 72
+WORKLOAD = "C3: McICA cloudy, icld=2 max-random (KISS), inflglw=2 iceflglw=3 liqflglw=1, 72 layers, 140 g-points"
+
+
+def env_int(k, d):
+    try:
+        return int(os.environ.get(k, d))
+    except ValueError:
+        return d
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (profiling recipe's clocks line)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_sample_run(ncol, nthreads, seed_off=0, block=128):
+    """The oracle (CPU restatement) on `ncol` cloudy columns: McICA generation + rrtmg_lw in column
+    blocks spread over `nthreads` host threads.  Returns seconds."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import orc
+    from rrtmg_lw_b200 import synth
+
+    blocks = []
+    for i, c0 in enumerate(range(0, ncol, block)):
+        blocks.append(synth.make_batch(min(block, ncol - c0), NLAY, cloudy=True, col_offset=1000 + seed_off + i))
+
+    def work(b):
+        mc = orc.mcica_subcol_lw(b, 2, permuteseed=1, irng=0)
+        r = orc.rrtmg_lw(b, icld=2, idrv=0, inflglw=2, iceflglw=3, liqflglw=1, mc=mc, nthreads=1)
+        assert r["rc"] == 0
+        return float(r["uflx"][0, 0])
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=nthreads) as ex:
+        list(ex.map(work, blocks))
+    return time.perf_counter() - t0
+
+
+def run_reference(args, rank):
+    """Reference arm: the reference's own CPU algorithm for the path.  Its Fortran cannot be built
+    in this image (no Fortran compiler; k-data missing), so the arm is the C++ restatement
+    (oracle, kind "port") on all host cores, each step a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    from oracle import orc
+    from rrtmg_lw_b200 import kdata
+    orc.ini(kdata.synthetic_blob(), 1004.0, 4)
+    cores = os.cpu_count() or 1
+    ncol = min(args.ref_cols or 256 * cores, 65536)
+    ncol = max(ncol, 512)
+    for w in range(max(args.warmup, 1)):
+        cpu_sample_run(min(ncol, 64 * cores), cores, seed_off=w)
+    t = 0.0
+    for s in range(args.steps):
+        t += cpu_sample_run(ncol, cores, seed_off=10 + s)
+    val = ncol * args.steps / t
+    sample = "%d columns x %d layers per step, blocks of 128 columns over %d threads, oracle C++ port -O2 -ffp-contract=off" % (ncol, NLAY, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": "columns/sec", "value": val, "unit": "columns/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "columns/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "columns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def make_device_batch(ncol, device, seed_off):
+    """Device-resident synthetic batch generated in pieces (bounded temporaries)."""
+    import torch
+
+    from rrtmg_lw_b200 import synth
+    piece = 65536
+    parts = []
+    for i, c0 in enumerate(range(0, ncol, piece)):
+        parts.append(synth.make_batch(min(piece, ncol - c0), NLAY, cloudy=True, device=device,
+                                      col_offset=seed_off * 4096 + i))
+    if len(parts) == 1:
+        return parts[0]
+    b0 = parts[0]
+    kw = {}
+    for k, v in b0.__dict__.items():
+        if hasattr(v, "shape") and v is not None:
+            if k == "tsfc" or k == "lat":
+                kw[k] = torch.cat([getattr(p, k) for p in parts], dim=0)
+            elif k == "tauc":
+                kw[k] = torch.cat([getattr(p, k) for p in parts], dim=1).contiguous()
+            else:
+                kw[k] = torch.cat([getattr(p, k) for p in parts], dim=-1).contiguous()
+            for p in parts:
+                setattr(p, k, None)
+        else:
+            kw[k] = v
+    kw["ncol"] = ncol
+    return synth.Batch(**kw)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ncol", type=int, default=1048576, help="columns per GPU")
+    ap.add_argument("--chunk", type=int, default=262144, help="columns per internal pass")
+    ap.add_argument("--e2e-cols", type=int, default=131072)
+    ap.add_argument("--ref-cols", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from rrtmg_lw_b200 import api, driver, kdata
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = "cuda:%d" % local
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    blob = kdata.synthetic_blob()
+    api.rrtmg_lw_ini(1004.0, blob, 4)
+    api.set_chunk(args.chunk)
+
+    ncol = args.ncol
+    b = make_device_batch(ncol, dev, rank)
+    out = driver._outputs(NLAY, ncol, like=b.play)
+    conv = driver._conv(b, dev)
+    at = driver.atm_args(b, conv)
+    cl = [b.cldfrac, b.ciwp, b.clwp, b.rei, b.rel, b.tauc]
+
+    def step():
+        api.rrtmg_lw_mcica(ncol, NLAY, 2, 0, 1, 0, *at, 2, 3, 1, *cl, None, b.tauaer, out["uflx"], out["dflx"],
+                           out["hr"], out["uflxc"], out["dflxc"], out["hrc"], None, None)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    api.sync()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    api.launch_count(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = api.launch_count(reset=True)
+    clocks = sampler.stop() if rank == 0 else None
+    api.sync()
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * ncol * args.steps / (ms * 1e-3)
+
+    # instrumented extra step: CUDA events (library, launching stream) around the band kernels
+    api.set_timing(True)
+    step()
+    torch.cuda.synchronize()
+    ms_band, ms_all = api.last_timing()
+    api.set_timing(False)
+
+    res = None
+    if rank == 0:
+        # ---- roofline of the dominant kernel group (the 16 band kernels of a pass)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        fp64_peak = api.fp64_peak()
+        flops_per_col = 606259.0      # op-counting oracle, DESIGN.md section "Algorithmic work"
+        bytes_per_col = (37 * NLAY + 19 + 6 * NLAY + 4) * 8.0   # API words in + out, SURVEY 8(d)
+        cols_per_s_band = ncol / (ms_band * 1e-3)
+        roof = {
+            "bound": "fp64", "kernel": "band_kernel<1..16,CLD_MASK,0> (16 launches per pass)",
+            "achieved": flops_per_col * cols_per_s_band / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+            "frac": flops_per_col * cols_per_s_band / 1e12 / fp64_peak,
+            "peak_source": "DFMA microbenchmark run in this process (rrtmg_lw_b200_fp64_peak)",
+            "flops_per_column": flops_per_col, "band_kernels_ms_per_step": ms_band, "all_kernels_ms_per_step": ms_all,
+            "traffic": None,
+            "hbm": {"achieved": bytes_per_col * cols_per_s_band / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": bytes_per_col * cols_per_s_band / 1e9 / hbm_peak, "bytes_per_column": bytes_per_col,
+                    "peak_source": hbm_src},
+        }
+        prof = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(prof):
+            try:
+                roof["traffic"] = json.load(open(prof)).get("dram_bytes_per_step")
+            except (OSError, ValueError):
+                pass
+        res = {
+            "metric": "columns/sec", "value": value, "unit": "columns/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "columns_per_gpu": ncol, "layers": NLAY, "chunk_columns": args.chunk,
+                       "entry": "rrtmg_lw_b200_rrtmg_lw_mcica (device pointers)", "l2": "inputs (>=20 GB) larger than L2",
+                       "fma": "off (-fmad=false)"},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof,
+        }
+
+    # ---- e2e: same metric through the C ABI with HOST (pinned) buffers, H2D + D2H inside the timed region
+    ne = min(args.e2e_cols, ncol)
+    hb = {}
+    names = ["play", "plev", "tlay", "tlev", "tsfc", "h2ovmr", "o3vmr", "co2vmr", "ch4vmr", "n2ovmr", "o2vmr",
+             "cfc11vmr", "cfc12vmr", "cfc22vmr", "ccl4vmr", "emis", "cldfrac", "ciwp", "clwp", "rei", "rel", "tauaer"]
+    for k in names:
+        src = getattr(b, k)
+        sl = src[..., :ne].contiguous()
+        pin = torch.empty(sl.shape, dtype=sl.dtype, pin_memory=True)
+        pin.copy_(sl)
+        hb[k] = pin.numpy()
+    tauc_h = torch.zeros((NLAY, ne, 16), dtype=torch.float64, pin_memory=True).numpy()
+    ho = {k: torch.empty((n, ne), dtype=torch.float64, pin_memory=True).numpy()
+          for k, n in (("uflx", NLAY + 1), ("dflx", NLAY + 1), ("uflxc", NLAY + 1), ("dflxc", NLAY + 1), ("hr", NLAY), ("hrc", NLAY))}
+    h2d = sum(v.nbytes for v in hb.values()) + tauc_h.nbytes
+    d2h = sum(v.nbytes for v in ho.values())
+
+    def step_e2e():
+        api.rrtmg_lw_mcica(ne, NLAY, 2, 0, 1, 0, *[hb[k] for k in names[:16]], 2, 3, 1, hb["cldfrac"], hb["ciwp"],
+                           hb["clwp"], hb["rei"], hb["rel"], tauc_h, None, hb["tauaer"], ho["uflx"], ho["dflx"],
+                           ho["hr"], ho["uflxc"], ho["dflxc"], ho["hrc"], None, None)
+
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    ke = max(2, min(args.steps, 5))
+    for _ in range(ke):
+        step_e2e()
+    torch.cuda.synchronize()
+    te = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([te], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        te = float(t.item())
+    if rank == 0:
+        res["e2e"] = {"value": world * ne * ke / te, "unit": "columns/s", "h2d_bytes_per_step": h2d,
+                      "d2h_bytes_per_step": d2h, "columns_per_step": ne, "steps": ke,
+                      "note": "host pinned buffers -> rrtmg_lw_b200_rrtmg_lw_mcica(HOST) -> host; result fluxes read back"}
+        # sanity of the timed outputs
+        res["checks"] = {"toa_up_mean": float(out["uflx"][-1].mean()), "sfc_down_mean": float(out["dflx"][0].mean()),
+                         "host_equals_device": bool(np.array_equal(ho["uflx"], out["uflx"][:, :ne].cpu().numpy()))}
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import orc
+            orc.ini(blob, 1004.0, 4)
+            cores = os.cpu_count() or 1
+            nc = max(512, min(192 * cores, 32768))
+            cpu_sample_run(min(nc, 32 * cores), cores)
+            tc = cpu_sample_run(nc, cores, seed_off=3)
+            res["cpu_baseline"] = {"value": nc / tc, "unit": "columns/s", "cores": cores, "kind": "port",
+                                   "sample": "%d columns x %d layers (McICA generation + rrtmg_lw), blocks of 128 over %d "
+                                             "threads; C++ restatement of the reference, g++ -O2 -ffp-contract=off "
+                                             "(no Fortran compiler in the image)" % (nc, NLAY, cores)}
+        print(json.dumps(res))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -110,11 +110,12 @@ int rrtmg_lw_b200_rrtmg_lw_mcica(int ncol, int ld, int nlay, int icld_overlap, i
  * col/lay (1-based, may be NULL) receive the first offending column and layer. */
 int rrtmg_lw_b200_sync(int* col, int* lay);
 
-/* Stage dump of ONE column (0-based icol) of the most recent rrtmg_lw/rrtmg_lw_mcica call made
- * with debug capture enabled (rrtmg_lw_b200_debug_capture(1)); host pointers, any may be NULL:
+/* Stage dump of ONE column: rrtmg_lw_b200_debug_capture(icol + 1) arms the capture of caller column
+ * icol (0-based) for the following rrtmg_lw/rrtmg_lw_mcica calls (0 disarms);
+ * rrtmg_lw_b200_debug_stages(icol, ...) reads it back.  Host pointers, any may be NULL:
  *   ints6 (6,nlay) jp,jt,jt1,indself,indfor,indminor ; facs (4,nlay) fac00,fac01,fac10,fac11
  *   taug,fracs (nlay,140) ; itr (2,nlay,140) ; scal = {laytrop, pwvcm} ; mask (nlay,140) 0/1 bytes */
-int rrtmg_lw_b200_debug_capture(int enable);
+int rrtmg_lw_b200_debug_capture(int icol_plus_1);
 int rrtmg_lw_b200_debug_stages(int icol, int* ints6, double* facs, double* taug, double* fracs, int* itr,
                                double* scal, unsigned char* mask);
 
@@ -131,6 +132,10 @@ long rrtmg_lw_b200_launch_count(int reset);
  * call when timing capture is enabled with rrtmg_lw_b200_set_timing(1). */
 int rrtmg_lw_b200_set_timing(int enable);
 int rrtmg_lw_b200_last_timing(float* ms_band_kernels, float* ms_all_kernels);
+
+/* Measured FP64 FMA throughput of the current device in TFLOP/s (an FMA = 2 flops); the FP64
+ * roofline denominator used by bench.py. */
+int rrtmg_lw_b200_fp64_peak(double* tflops);
 
 const char* rrtmg_lw_b200_strerror(int code);
 const char* rrtmg_lw_b200_version(void);

@@ -124,6 +124,33 @@ def get_alpha(b, icld, idcor=0, decorr_con=2500.0, juldat=1):
     return alpha
 
 
+def count_ops(kdata_blob, b, icld=0, idrv=0, irng=0, alpha=None, default_real_kind=4):
+    """Algorithmic FP64 operation count per column (op-counting build liborc_count.so):
+    returns dict(add, mul, div, exp, log, pow, flops) averaged over the batch's columns for
+    rrtmg_lw() itself (the McICA generator's 2 flops per draw are integer-dominated and excluded)."""
+    global _lib
+    path = os.path.join(_HERE, "liborc_count.so")
+    if not os.path.exists(path):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "liborc_count.so"])
+    saved = _lib
+    try:
+        _lib = C.CDLL(path)
+        _lib.orc_get_table.restype = C.c_long
+        ini(kdata_blob, 1004.0, default_real_kind)
+        mc = mcica_subcol_lw(b, icld, 1, irng, alpha) if icld > 0 else None
+        out = (C.c_longlong * 6)()
+        _lib.orc_opcount(out, 1)
+        r = rrtmg_lw(b, icld=icld, idrv=idrv, inflglw=2, iceflglw=3, liqflglw=1, mc=mc, nthreads=1)
+        assert r["rc"] == 0
+        _lib.orc_opcount(out, 1)
+    finally:
+        _lib = saved
+    names = ("add", "mul", "div", "exp", "log", "pow")
+    d = {n: out[i] / b.ncol for i, n in enumerate(names)}
+    d["flops"] = d["add"] + d["mul"] + d["div"]
+    return d
+
+
 def mt_stream(seed, n):
     ints = np.zeros(n, dtype=np.uint32); reals = np.zeros(n)
     lib().orc_mt_stream(seed, n, ints.ctypes.data_as(C.POINTER(C.c_uint)), _p(reals))

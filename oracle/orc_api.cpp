@@ -1,11 +1,10 @@
 // orc_api.cpp -- ORACLE (test infrastructure): rrtmg_lw driver + inatm and the C entry points.
 // Follows src/rrtmg_lw_rad.f90:449-593 (rrtmg_lw) and :755-922 (inatm).
-#include "orc_api.h"
-
 #include <cstdio>
 #include <cstdlib>
 
 #include "orc_common.h"
+#include "orc_api.h"
 
 namespace orc {
 int init(double cpdair, const double* st, const double* kdata, int drk);
@@ -221,4 +220,15 @@ extern "C" long orc_get_table(const char* name, double* out, long cap) {
     }
     if (out) for (long i = 0; i < cnt && i < cap; ++i) out[i] = src[i];
     return cnt;
+}
+
+// op-counting build only (liborc_count.so): counters of the calling thread since the last reset
+extern "C" void orc_opcount(long long* out6, int reset) {
+#ifdef ORC_COUNT_OPS
+    if (out6) { out6[0] = g_ops.add; out6[1] = g_ops.mul; out6[2] = g_ops.div; out6[3] = g_ops.exp; out6[4] = g_ops.log; out6[5] = g_ops.pow; }
+    if (reset) g_ops = OpCount{0, 0, 0, 0, 0, 0};
+#else
+    if (out6) for (int i = 0; i < 6; ++i) out6[i] = -1;
+    (void)reset;
+#endif
 }

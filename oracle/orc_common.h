@@ -24,6 +24,51 @@
 #include <string>
 #include <vector>
 
+#ifdef ORC_COUNT_OPS
+// Op-counting build (liborc_count.so): every `double` of the oracle sources becomes a wrapper
+// that counts executed +,-,*,/ and libm calls, giving the ALGORITHMIC FP64 work per column that
+// the roofline figure in bench.py / DESIGN.md uses.
+namespace orc {
+struct OpCount { long long add, mul, div, exp, log, pow; };
+extern thread_local OpCount g_ops;
+struct Real {
+    double v;
+    Real() = default;
+    Real(double x) : v(x) {}
+    Real(float x) : v(x) {}
+    Real(int x) : v(x) {}
+    Real(long x) : v((double)x) {}
+    explicit operator int() const { return (int)v; }
+    explicit operator float() const { return (float)v; }
+    explicit operator bool() const { return v != 0; }
+    Real operator-() const { return Real(-v); }
+};
+#define ORC_BIN(op, ctr)                                                                   \
+    inline Real operator op(Real a, Real b) { g_ops.ctr++; return Real(a.v op b.v); }      \
+    inline Real operator op(Real a, double b) { g_ops.ctr++; return Real(a.v op b); }      \
+    inline Real operator op(double a, Real b) { g_ops.ctr++; return Real(a op b.v); }      \
+    inline Real operator op(Real a, int b) { g_ops.ctr++; return Real(a.v op b); }         \
+    inline Real operator op(int a, Real b) { g_ops.ctr++; return Real(a op b.v); }
+ORC_BIN(+, add) ORC_BIN(-, add) ORC_BIN(*, mul) ORC_BIN(/, div)
+#undef ORC_BIN
+#define ORC_CMP(op)                                                    \
+    inline bool operator op(Real a, Real b) { return a.v op b.v; }     \
+    inline bool operator op(Real a, double b) { return a.v op b; }     \
+    inline bool operator op(double a, Real b) { return a op b.v; }
+ORC_CMP(<) ORC_CMP(>) ORC_CMP(<=) ORC_CMP(>=) ORC_CMP(==) ORC_CMP(!=)
+#undef ORC_CMP
+}  // namespace orc
+namespace std {
+inline orc::Real exp(orc::Real x) { orc::g_ops.exp++; return orc::Real(std::exp(x.v)); }
+inline orc::Real log(orc::Real x) { orc::g_ops.log++; return orc::Real(std::log(x.v)); }
+inline orc::Real asin(orc::Real x) { return orc::Real(std::asin(x.v)); }
+inline orc::Real pow(orc::Real x, orc::Real y) { orc::g_ops.pow++; return orc::Real(std::pow(x.v, y.v)); }
+inline orc::Real pow(orc::Real x, double y) { orc::g_ops.pow++; return orc::Real(std::pow(x.v, y)); }
+inline orc::Real fmod(orc::Real x, double y) { return orc::Real(std::fmod(x.v, y)); }
+}  // namespace std
+#define double orc::Real
+#endif
+
 namespace orc {
 
 constexpr int NBND = 16;    // nbndlw  modules/parrrtm.f90:35

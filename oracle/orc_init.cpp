@@ -11,6 +11,9 @@
 namespace orc {
 
 State G;
+#ifdef ORC_COUNT_OPS
+thread_local OpCount g_ops = {0, 0, 0, 0, 0, 0};
+#endif
 
 void Column::resize(int nl) {
     nlayers = nl;

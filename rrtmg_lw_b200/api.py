@@ -24,7 +24,9 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "librrtmg_lw_b200.so")
+# RRTMG_LW_B200_LIB selects an alternative build of the same CUDA library (e.g. the FMA-contracted
+# variant librrtmg_lw_b200_fma.so); it is never a non-CUDA implementation.
+LIB_PATH = os.environ.get("RRTMG_LW_B200_LIB") or os.path.join(_HERE, "lib", "librrtmg_lw_b200.so")
 
 HOST, DEVICE = 0, 1
 _dp = C.POINTER(C.c_double)
@@ -208,6 +210,15 @@ def get_table(name):
     if n:
         lib().rrtmg_lw_b200_get_table(name.encode(), _ptr(out), n)
     return out
+
+
+def fp64_peak():
+    """Measured FP64 FMA peak of the current device in TFLOP/s."""
+    v = C.c_double(0)
+    rc = lib().rrtmg_lw_b200_fp64_peak(C.byref(v))
+    if rc:
+        raise RrtmgLwError(rc, "fp64_peak")
+    return v.value
 
 
 def finalize():

@@ -679,6 +679,12 @@ extern "C" const char* rrtmg_lw_b200_strerror(int code) {
     }
 }
 
+extern "C" int rrtmg_lw_b200_fp64_peak(double* tflops) {
+    std::lock_guard<std::mutex> lk(G.mu);
+    if (!tflops) return RRTMG_LW_ERR_ARG;
+    return measure_fp64_peak(tflops, 5) ? RRTMG_LW_ERR_CUDA : RRTMG_LW_OK;
+}
+
 extern "C" const char* rrtmg_lw_b200_version(void) { return "rrtmg_lw_b200 0.1 (sm_100a)"; }
 
 extern "C" void rrtmg_lw_b200_finalize(void) {

@@ -29,9 +29,18 @@ namespace lw {
 template <int B>
 static void launch_b(int cld, int idrv, const ColIn& in, const ColOut& out, const Scratch& s, const RunCfg& r,
                      cudaStream_t st) {
-    const int threads = 128;
+    const int threads = BAND_THREADS;
     const int blocks = (r.ncol + threads - 1) / threads;
-#define LW_GO(CLD, IDRV) band_kernel<B, CLD, IDRV><<<blocks, threads, 0, st>>>(in, out, s, r)
+    const size_t smem = Ring<B>::BYTES;
+#define LW_GO(CLD, IDRV)                                                                                  \
+    do {                                                                                                  \
+        static bool attr_set = false;                                                                     \
+        if (!attr_set) {                                                                                  \
+            cudaFuncSetAttribute(band_kernel<B, CLD, IDRV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            attr_set = true;                                                                              \
+        }                                                                                                 \
+        band_kernel<B, CLD, IDRV><<<blocks, threads, smem, st>>>(in, out, s, r);                          \
+    } while (0)
     if (cld == CLD_NONE) { if (idrv) LW_GO(CLD_NONE, 1); else LW_GO(CLD_NONE, 0); }
     else if (cld == CLD_MASK) { if (idrv) LW_GO(CLD_MASK, 1); else LW_GO(CLD_MASK, 0); }
     else { if (idrv) LW_GO(CLD_ARRAYS, 1); else LW_GO(CLD_ARRAYS, 0); }

@@ -409,3 +409,48 @@ void launch_materialize(const ColIn& in, const Scratch& s, const RunCfg& r, doub
 }
 
 }  // namespace lw
+
+// ---------------------------------------------------------------------------------------------
+// FP64 pipe peak: 8 independent DFMA chains per thread.  Used by bench.py as the measured FP64
+// roofline denominator (MEASURED_PEAKS.json carries HBM and bf16 only).
+namespace lw {
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double seed) {
+    double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
+    const double m = 0.999999, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = __fma_rn(a0, m, c); a1 = __fma_rn(a1, m, c); a2 = __fma_rn(a2, m, c); a3 = __fma_rn(a3, m, c);
+            a4 = __fma_rn(a4, m, c); a5 = __fma_rn(a5, m, c); a6 = __fma_rn(a6, m, c); a7 = __fma_rn(a7, m, c);
+        }
+    }
+    const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 12345.678) out[0] = s;  // keep the chains alive
+}
+// returns TFLOP/s counting an FMA as 2 flops, best of `reps`
+int measure_fp64_peak(double* tflops, int reps) {
+    double* d = nullptr;
+    if (cudaMalloc((void**)&d, 8) != cudaSuccess) return 1;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    const int blocks = sms * 8, threads = 256, iters = 4096;
+    double best = 0;
+    for (int r = 0; r < reps + 1; ++r) {
+        cudaEventRecord(e0);
+        fp64_peak_kernel<<<blocks, threads>>>(d, iters, 1.0 + r);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double fl = 2.0 * 64.0 * iters * (double)blocks * threads;
+        const double tf = fl / (ms * 1e-3) / 1e12;
+        if (r > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d);
+    *tflops = best;
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+}  // namespace lw
