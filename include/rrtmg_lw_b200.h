@@ -61,6 +61,12 @@ enum { RRTMG_LW_HOST = 0, RRTMG_LW_DEVICE = 1 };
  *                     8 = of the shipped `-r8` makefiles (affects default-kind literals only) */
 int rrtmg_lw_b200_ini(double cpdair, const double* kdata, long nkdata, int default_real_kind);
 
+/* Array-by-array alternative to building the blob: hand over one unreduced k-array of
+ * modules/rrlw_kgNN.f90 (e.g. band 3, "kao", 585*16 doubles, Fortran element order) as the
+ * reference's lw_kgbNN left it; after all RRTMG_LW_NKARRAYS arrays were put,
+ * rrtmg_lw_b200_ini(cpdair, NULL, 0, kind) consumes them.  n must equal 16*lead of the array. */
+int rrtmg_lw_b200_kdata_put(int band, const char* name, const double* data, long n);
+
 /* Replaces rrtmg_lw (src/rrtmg_lw_rad.f90:99-595), argument for argument.
  * icld is inout (clamped to 2 when outside [0,3], :470).  duflx_dt/duflxc_dt may be NULL
  * when idrv == 0.  The McICA arrays are read only when *icld >= 1. */

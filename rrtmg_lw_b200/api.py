@@ -89,10 +89,24 @@ def _stream(space):
 def rrtmg_lw_ini(cpdair: float, kdata: np.ndarray, default_real_kind: int = 4):
     """Replaces ``rrtmg_lw_ini(cpdair)``.  ``kdata`` = unreduced k-distribution blob
     (``rrtmg_lw_b200.kdata``; the reference compiles these numbers in)."""
-    k = np.ascontiguousarray(kdata, dtype=np.float64)
-    rc = lib().rrtmg_lw_b200_ini(float(cpdair), _ptr(k), k.size, int(default_real_kind))
+    if kdata is None:   # arrays were staged one by one with kdata_put
+        rc = lib().rrtmg_lw_b200_ini(float(cpdair), None, 0, int(default_real_kind))
+    else:
+        k = np.ascontiguousarray(kdata, dtype=np.float64)
+        rc = lib().rrtmg_lw_b200_ini(float(cpdair), _ptr(k), k.size, int(default_real_kind))
     if rc:
         raise RrtmgLwError(rc, "rrtmg_lw_ini")
+
+
+def kdata_put(band: int, name: str, array: np.ndarray):
+    """Hand over one unreduced k-array (Fortran element order) -- what the Fortran shim does after
+    the reference's ``lw_kgbNN``; ``rrtmg_lw_ini(cpdair, None)`` then consumes the staged arrays."""
+    a = np.ascontiguousarray(np.asarray(array, dtype=np.float64).ravel(order="F"))
+    L = lib()
+    L.rrtmg_lw_b200_kdata_put.argtypes = [C.c_int, C.c_char_p, _dp, C.c_long]
+    rc = L.rrtmg_lw_b200_kdata_put(int(band), name.encode(), _ptr(a), a.size)
+    if rc:
+        raise RrtmgLwError(rc, "kdata_put(%d,%s)" % (band, name))
 
 
 def rrtmg_lw(ncol, nlay, icld, idrv, play, plev, tlay, tlev, tsfc, h2ovmr, o3vmr, co2vmr, ch4vmr, n2ovmr, o2vmr,

@@ -217,8 +217,43 @@ bool check_common(int ncol, int ld, int nlay) { return ncol >= 1 && ld >= ncol &
 
 using namespace lw;
 
+// Array-by-array staging of the unreduced k-data (what a Fortran shim has at hand after the
+// reference's lw_kgb01..16 filled modules rrlw_kg01..16); rrtmg_lw_b200_ini(.., NULL, 0, ..) then
+// consumes the staged blob.
+static std::vector<double> g_kstage;
+static std::vector<char> g_khave;
+
+extern "C" int rrtmg_lw_b200_kdata_put(int band, const char* name, const double* data, long n) {
+    std::lock_guard<std::mutex> lk(G.mu);
+    if (!name || !data) return RRTMG_LW_ERR_ARG;
+    if (g_kstage.empty()) {
+        g_kstage.assign(RRTMG_LW_KDATA_DOUBLES, 0.0);
+        g_khave.assign(RRTMG_LW_NKARRAYS, 0);
+    }
+    size_t off = 0;
+    for (int k = 0; k < RRTMG_LW_NKARRAYS; ++k) {
+        const rrtmg_lw_karray_desc& d = RRTMG_LW_KARRAYS[k];
+        const size_t cnt = (size_t)16 * d.lead;
+        if (d.band == band && std::strcmp(d.name, name) == 0) {
+            if ((size_t)n != cnt) return RRTMG_LW_ERR_ARG;
+            std::memcpy(g_kstage.data() + off, data, cnt * sizeof(double));
+            g_khave[k] = 1;
+            return RRTMG_LW_OK;
+        }
+        off += cnt;
+    }
+    return RRTMG_LW_ERR_ARG;  // unknown (band, name)
+}
+
 extern "C" int rrtmg_lw_b200_ini(double cpdair, const double* kdata, long nkdata, int default_real_kind) {
     std::lock_guard<std::mutex> lk(G.mu);
+    if (!kdata && nkdata == 0) {
+        if (g_khave.empty()) return RRTMG_LW_ERR_ARG;
+        for (char h : g_khave)
+            if (!h) return RRTMG_LW_ERR_ARG;  // an array was never supplied
+        kdata = g_kstage.data();
+        nkdata = RRTMG_LW_KDATA_DOUBLES;
+    }
     if (!kdata || nkdata != RRTMG_LW_KDATA_DOUBLES) return RRTMG_LW_ERR_ARG;
     if (default_real_kind != 4 && default_real_kind != 8) return RRTMG_LW_ERR_ARG;
     int ndev = 0;

@@ -50,6 +50,37 @@ def test_no_cpu_fallback():
     assert e2.value.code == 6
 
 
+def test_kdata_put_validates_name_and_size():
+    """Array-by-array k-data hand-over (the Fortran shim's route): wrong size / unknown name are
+    rejected with ERR_ARG (7); ini without the complete set is rejected too."""
+    from rrtmg_lw_b200 import api, kdata
+    arrs = kdata.synthetic_kdata()
+    api.kdata_put(3, "kao", arrs[(3, "kao")])
+    with pytest.raises(api.RrtmgLwError) as e:
+        api.kdata_put(3, "kao", arrs[(3, "kao")][:10])
+    assert e.value.code == 7
+    with pytest.raises(api.RrtmgLwError) as e:
+        api.kdata_put(3, "nonsense", arrs[(3, "kao")])
+    assert e.value.code == 7
+    with pytest.raises(api.RrtmgLwError) as e:
+        api.rrtmg_lw_ini(1004.0, None)
+    assert e.value.code == 7   # incomplete set
+
+
+def test_fortran_shim_binds_only_exported_symbols():
+    """Every bind(C, name=...) of fortran/rrtmg_lw_b200_shim.f90 is an export of the library and
+    every k-array it hands over exists in the layout header."""
+    from rrtmg_lw_b200 import api, kdata
+    txt = open(os.path.join(ROOT, "fortran", "rrtmg_lw_b200_shim.f90")).read()
+    names = set(re.findall(r"bind\(C, name='([a-z0-9_]+)'\)", txt))
+    assert len(names) >= 6
+    lib = ctypes.CDLL(api.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), n
+    puts = set((int(b), n) for b, n in re.findall(r"call put\((\d+), '([a-z0-9_]+)'", txt))
+    assert puts == set((a[0], a[1]) for a in kdata.karrays())
+
+
 def test_kdata_header_matches_python_layout():
     from rrtmg_lw_b200 import kdata
     arr = kdata.karrays()
