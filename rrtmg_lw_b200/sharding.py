@@ -1,0 +1,95 @@
+"""Column sharding of the longwave path over ``torch.distributed`` ranks (one process per GPU).
+
+Columns are independent (``src/rrtmg_lw_rad.f90:486``) and the KISS McICA streams are seeded per
+column (``src/mcica_subcol_gen_lw.f90:467-470``), so the column axis is block-partitioned and the
+data path needs NO collective; the only exchange is the optional gather of the flux / heating-rate
+arrays.  The Mersenne-Twister stream (``irng=1``) is one sequence over (sub-column, column, layer)
+whose values depend on how the batch is split, so it is refused here.
+
+Pure plumbing: nothing in this module computes radiation.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import synth
+
+OUT_KEYS = ("uflx", "dflx", "hr", "uflxc", "dflxc", "hrc")
+OUT_KEYS_DRV = OUT_KEYS + ("duflx_dt", "duflxc_dt")
+
+# how each Batch field is sliced along the column axis: index of the column dimension
+_COL_DIM = {"tsfc": 0, "lat": 0, "tauc": 1}
+
+
+def block_range(ncol: int, world: int, rank: int):
+    """Contiguous block partition: rank r owns columns [r*ceil(ncol/world), ...) (may be empty)."""
+    per = -(-ncol // world)
+    lo = min(rank * per, ncol)
+    return lo, min(lo + per, ncol)
+
+
+def shard_batch(b: "synth.Batch", world: int, rank: int) -> "synth.Batch":
+    """The rank's column block of a batch (views made contiguous; layer 1 stays the surface)."""
+    lo, hi = block_range(b.ncol, world, rank)
+    kw = {}
+    for k, v in b.__dict__.items():
+        if torch.is_tensor(v):
+            d = _COL_DIM.get(k, v.dim() - 1)
+            kw[k] = v.narrow(d, lo, hi - lo).contiguous()
+        else:
+            kw[k] = v
+    kw["ncol"] = hi - lo
+    return synth.Batch(**kw)
+
+
+def gather_outputs(local: dict, ncol_total: int, idrv: int = 0, dst: int | None = None, group=None) -> dict | None:
+    """Gather the per-rank output blocks ``(nlev, ncol_local)`` into ``(nlev, ncol_total)``.
+
+    ``dst=None``: every rank receives the full arrays (all_gather); otherwise only ``dst`` does.
+    Uneven last blocks are padded to the common block width for the collective and trimmed after.
+    Works on NCCL (CUDA tensors) and gloo (CPU tensors).
+    """
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    per = -(-ncol_total // world)
+    keys = OUT_KEYS_DRV if idrv else OUT_KEYS
+    # one packed buffer -> one collective: rows of all arrays stacked
+    rows = [torch.as_tensor(local[k]) for k in keys]
+    nloc = rows[0].shape[-1]
+    pack = torch.cat(rows, dim=0)
+    if nloc < per:
+        pack = torch.cat([pack, pack.new_zeros((pack.shape[0], per - nloc))], dim=1)
+    pack = pack.contiguous()
+    backend_nccl = pack.is_cuda
+    if dst is None or not backend_nccl:
+        # gloo has no gather for every build; all_gather is universally available
+        bufs = [torch.empty_like(pack) for _ in range(world)]
+        dist.all_gather(bufs, pack, group=group)
+    else:
+        bufs = [torch.empty_like(pack) for _ in range(world)] if rank == dst else None
+        dist.gather(pack, bufs, dst=dst, group=group)
+    if dst is not None and rank != dst:
+        return None
+    full = torch.cat(bufs, dim=1)[:, :ncol_total]
+    out, r0 = {}, 0
+    for k, t in zip(keys, rows):
+        out[k] = full[r0:r0 + t.shape[0]].contiguous()
+        r0 += t.shape[0]
+    return out
+
+
+def run_sharded(b: "synth.Batch", run_local, idrv: int = 0, irng: int = 0, gather_to: int | None = None, group=None):
+    """Run ``run_local(shard) -> dict`` on this rank's column block and gather the outputs.
+
+    ``run_local`` is the caller's per-rank invocation of the CUDA path (``driver.run_fused`` on the
+    GPU box); tests substitute a stand-in to exercise the partition/gather logic on CPU.
+    """
+    if irng != 0:
+        raise ValueError("irng=1 (Mersenne Twister) is one global stream over all columns of a call; "
+                         "its values depend on the partition -- use irng=0 (KISS) on the sharded path")
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    shard = shard_batch(b, world, rank)
+    local = run_local(shard)
+    return gather_outputs(local, b.ncol, idrv=idrv, dst=gather_to, group=group)

@@ -1,0 +1,96 @@
+"""N > 1 host logic on CPU: block partition of the column axis and the output gather, with
+world_size-2 gloo processes.  The per-rank "compute" is the CPU oracle here (tests may use it as
+a checker); on the GPU box the same code path runs driver.run_fused per rank (tests/test_gpu_parity)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from rrtmg_lw_b200 import sharding, synth
+
+
+def test_block_range_covers_all_columns():
+    for ncol in (1, 5, 64, 1000, 1036800):
+        for world in (1, 2, 3, 8):
+            seen = []
+            for r in range(world):
+                lo, hi = sharding.block_range(ncol, world, r)
+                assert 0 <= lo <= hi <= ncol
+                seen.extend(range(lo, hi) if ncol <= 1000 else [lo, hi])
+            if ncol <= 1000:
+                assert seen == list(range(ncol))
+            else:
+                assert seen[0] == 0 and seen[-1] == ncol
+
+
+def test_shard_batch_slices_every_field():
+    b = synth.make_batch(37, 12, cloudy=True, aerosol=True)
+    parts = [sharding.shard_batch(b, 3, r) for r in range(3)]
+    assert sum(p.ncol for p in parts) == 37
+    assert torch.equal(torch.cat([p.play for p in parts], dim=-1), b.play)
+    assert torch.equal(torch.cat([p.tsfc for p in parts], dim=0), b.tsfc)
+    assert torch.equal(torch.cat([p.tauc for p in parts], dim=1), b.tauc)
+    assert torch.equal(torch.cat([p.tauaer for p in parts], dim=-1), b.tauaer)
+    assert torch.equal(torch.cat([p.emis for p in parts], dim=-1), b.emis)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, ncol, nlay, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import orc
+        from rrtmg_lw_b200 import kdata
+        orc.ini(kdata.synthetic_blob(), 1004.0, 4)
+        b = synth.make_batch(ncol, nlay, cloudy=True)
+
+        def run_local(shard):
+            mc = orc.mcica_subcol_lw(shard, 2, permuteseed=1, irng=0)
+            r = orc.rrtmg_lw(shard, icld=2, idrv=0, inflglw=2, iceflglw=3, liqflglw=1, mc=mc, nthreads=1)
+            assert r["rc"] == 0
+            return {k: torch.from_numpy(np.ascontiguousarray(r[k])) for k in sharding.OUT_KEYS}
+
+        full = sharding.run_sharded(b, run_local)                    # all ranks get everything
+        only0 = sharding.run_sharded(b, run_local, gather_to=0)      # only rank 0
+        assert (only0 is None) == (rank != 0)
+        with pytest.raises(ValueError):
+            sharding.run_sharded(b, run_local, irng=1)
+        if rank == 0:
+            q.put({k: v.numpy() for k, v in full.items()})
+            assert all(torch.equal(only0[k], full[k]) for k in full)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_run_equals_single_process(oracle):
+    """world_size 2, uneven split (37 columns): the gathered result equals the unsharded run bit for
+    bit -- the KISS streams are per column, so the partition must not change anything."""
+    ncol, nlay = 37, 16
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, ncol, nlay, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    b = synth.make_batch(ncol, nlay, cloudy=True)
+    mc = oracle.mcica_subcol_lw(b, 2, permuteseed=1, irng=0)
+    ref = oracle.rrtmg_lw(b, icld=2, idrv=0, inflglw=2, iceflglw=3, liqflglw=1, mc=mc)
+    for k in sharding.OUT_KEYS:
+        assert np.array_equal(got[k], ref[k]), k
