@@ -180,6 +180,8 @@ def main():
     ap.add_argument("--e2e-cols", type=int, default=131072)
     ap.add_argument("--ref-cols", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--band-kernel", type=int, default=3, choices=[2, 3],
+                    help="3 = one thread per (column, g-point); 2 = one thread per (column, band)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
@@ -202,6 +204,7 @@ def main():
     blob = kdata.synthetic_blob()
     api.rrtmg_lw_ini(1004.0, blob, 4)
     api.set_chunk(args.chunk)
+    api.set_option("band_kernel", args.band_kernel)
 
     ncol = args.ncol
     b = make_device_batch(ncol, dev, rank)

@@ -183,6 +183,13 @@ def set_chunk(n):
         raise RrtmgLwError(rc, "set_chunk")
 
 
+def set_option(name, value):
+    """Tuning switches of the library (``rrtmg_lw_b200_set_option``), e.g. ``("band_kernel", 3)``."""
+    rc = lib().rrtmg_lw_b200_set_option(str(name).encode(), int(value))
+    if rc:
+        raise RrtmgLwError(rc, "set_option(%s)" % name)
+
+
 def launch_count(reset=False):
     return int(lib().rrtmg_lw_b200_launch_count(1 if reset else 0))
 

@@ -9,7 +9,7 @@
 
 #include "../../include/rrtmg_lw_b200.h"
 #include "../../include/rrtmg_lw_kdata_layout.h"
-#include "lw_band.cuh"
+#include "lw_gband.cuh"
 #include "lw_launch.h"
 
 // numeric blob of tools/extract_static_tables.py, embedded at build time
@@ -36,6 +36,8 @@ struct Ctx {
     double* stage = nullptr;
     size_t stage_doubles = 0;
     int chunk = 32768;
+    int band_kernel = 3;  // 3 = g-lane kernel (lw_gband.cuh), 2 = column-lane kernel (lw_band.cuh)
+    int sms = 0;
     long launches = 0;
     bool dbg = false;
     long dbg_col = -1;  // requested by debug_capture: always column given at debug_stages time? (we capture col 0..)
@@ -93,6 +95,21 @@ int ensure_scratch(long cols, int nlay) {
     if (A(&S.state, (size_t)5 * 16 * plane)) return RRTMG_LW_ERR_CUDA;
     if (A(&S.abscld, plane)) return RRTMG_LW_ERR_CUDA;
     if (A(&S.status, (size_t)1)) return RRTMG_LW_ERR_CUDA;
+    // g-lane path: layer-fastest copies, level-fastest band fluxes, per-resident-warp state slots
+    S.LP = ((nlay + 15) / 16) * 16;
+    S.LP1 = ((nlay + 1 + 15) / 16) * 16;
+    if (G.sms == 0) {
+        int dev = 0;
+        CK(cudaGetDevice(&dev));
+        CK(cudaDeviceGetAttribute(&G.sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    S.gwarps = G.sms * GB_WARPS;
+    if (A(&S.fldT, (size_t)NFIELD * P * S.LP)) return RRTMG_LW_ERR_CUDA;
+    if (A(&S.ipackT, (size_t)P * S.LP)) return RRTMG_LW_ERR_CUDA;
+    if (A(&S.maskT, (size_t)5 * P * S.LP)) return RRTMG_LW_ERR_CUDA;
+    if (A(&S.fluxT, (size_t)6 * P * S.LP1)) return RRTMG_LW_ERR_CUDA;
+    if (A(&S.gstate, (size_t)S.gwarps * nlay * 64)) return RRTMG_LW_ERR_CUDA;
+    if (A(&S.gstateB, (size_t)S.gwarps * nlay * 128)) return RRTMG_LW_ERR_CUDA;
     CK(cudaMemset(S.status, 0, sizeof(unsigned long long)));
     if (A(&S.dbg_taug, (size_t)NGPT * nlay)) return RRTMG_LW_ERR_CUDA;
     if (A(&S.dbg_fracs, (size_t)NGPT * nlay)) return RRTMG_LW_ERR_CUDA;
@@ -134,6 +151,13 @@ bool launch_band(int band, int cld, int idrv, const ColIn& in, const ColOut& out
            launch_band_tu4(band, cld, idrv, in, out, s, r, st) || launch_band_tu5(band, cld, idrv, in, out, s, r, st);
 }
 
+bool launch_gband(int band, int cld, int grid, const ColIn& in, const Scratch& s, const RunCfg& r, cudaStream_t st) {
+    return launch_gband_tu0(band, cld, grid, in, s, r, st) || launch_gband_tu1(band, cld, grid, in, s, r, st) ||
+           launch_gband_tu2(band, cld, grid, in, s, r, st) || launch_gband_tu3(band, cld, grid, in, s, r, st) ||
+           launch_gband_tu4(band, cld, grid, in, s, r, st) || launch_gband_tu5(band, cld, grid, in, s, r, st) ||
+           launch_gband_tu6(band, cld, grid, in, s, r, st) || launch_gband_tu7(band, cld, grid, in, s, r, st);
+}
+
 enum Mode { MODE_STRICT = 0, MODE_FUSED = 1 };
 
 // Device-resident pipeline over column chunks.  `in`/`out` hold device pointers with their ld.
@@ -167,13 +191,23 @@ int run_device(Mode mode, int ncol, int nlay, int icld, int idrv, int inflag, in
         launch_prep(in, S, r, st); G.launches++;
         if (cld == CLD_MASK) { launch_mcica_kiss(in, S, r, st); G.launches++; }
         if (cld == CLD_ARRAYS) { launch_cldflags(in, S, r, st); G.launches += 2; }
+        if (G.band_kernel == 3) { launch_transposes(S, r, cld != CLD_NONE, st); G.launches += cld != CLD_NONE ? 3 : 2; }
         if (G.timing) CK(cudaEventRecord(G.ev[1], st));
-        for (int b = 1; b <= NBND; ++b) {
-            if (!launch_band(b, cld, idrv, in, out, S, r, st)) return RRTMG_LW_ERR_ARG;
-            G.launches++;
+        if (G.band_kernel == 3) {
+            for (int b = 1; b <= NBND; ++b) {
+                if (!launch_gband(b, cld, G.sms, in, S, r, st)) return RRTMG_LW_ERR_ARG;
+                G.launches++;
+            }
+        } else {
+            for (int b = 1; b <= NBND; ++b) {
+                if (!launch_band(b, cld, idrv, in, out, S, r, st)) return RRTMG_LW_ERR_ARG;
+                G.launches++;
+            }
         }
         if (G.timing) CK(cudaEventRecord(G.ev[2], st));
-        launch_finalize(in, out, S, r, cld != CLD_NONE, st); G.launches++;
+        if (G.band_kernel == 3) launch_finalizeT(in, out, S, r, cld != CLD_NONE, st);
+        else launch_finalize(in, out, S, r, cld != CLD_NONE, st);
+        G.launches++;
         if (G.timing) {
             CK(cudaEventRecord(G.ev[3], st));
             CK(cudaEventSynchronize(G.ev[3]));
@@ -329,6 +363,14 @@ extern "C" int rrtmg_lw_b200_ini(double cpdair, const double* kdata, long nkdata
     CK(upload_constants_tu3(H.ct, dp, rr));
     CK(upload_constants_tu4(H.ct, dp, rr));
     CK(upload_constants_tu5(H.ct, dp, rr));
+    CK(upload_constants_gtu0(H.ct, dp, rr));
+    CK(upload_constants_gtu1(H.ct, dp, rr));
+    CK(upload_constants_gtu2(H.ct, dp, rr));
+    CK(upload_constants_gtu3(H.ct, dp, rr));
+    CK(upload_constants_gtu4(H.ct, dp, rr));
+    CK(upload_constants_gtu5(H.ct, dp, rr));
+    CK(upload_constants_gtu6(H.ct, dp, rr));
+    CK(upload_constants_gtu7(H.ct, dp, rr));
     CK(cudaDeviceSynchronize());
     G.inited = true;
     return RRTMG_LW_OK;
@@ -678,6 +720,17 @@ extern "C" int rrtmg_lw_b200_set_chunk(int max_columns) {
     if (max_columns < 32) return RRTMG_LW_ERR_ARG;
     G.chunk = max_columns;
     return RRTMG_LW_OK;
+}
+
+extern "C" int rrtmg_lw_b200_set_option(const char* name, int value) {
+    std::lock_guard<std::mutex> lk(G.mu);
+    if (!name) return RRTMG_LW_ERR_ARG;
+    if (std::strcmp(name, "band_kernel") == 0) {
+        if (value != 2 && value != 3) return RRTMG_LW_ERR_ARG;
+        G.band_kernel = value;
+        return RRTMG_LW_OK;
+    }
+    return RRTMG_LW_ERR_ARG;
 }
 
 extern "C" long rrtmg_lw_b200_launch_count(int reset) {

@@ -48,6 +48,15 @@ struct Scratch {
     double* abscld;     // nlay x pitch : 1 - exp(-odcld) of the current band (CLD_MASK)
     unsigned long long* status;  // sticky error word: code<<56 | (col+1)<<24 | lay
     long pitch;         // columns per row of every scratch array (multiple of 32)
+    // ---- g-lane band kernel (lw_gband.cuh): layer-fastest copies and per-warp state slots
+    double* fldT;       // NFIELD x pitch x LP   (layer fastest)
+    int* ipackT;        // pitch x LP
+    unsigned* maskT;    // 5 x pitch x LP
+    double* fluxT;      // 6 x pitch x LP1 : dflx, dflxc, uflx, uflxc, duflx_dt, duflxc_dt band sums, level fastest
+    double* gstate;     // per resident warp: nlay x 2 x 32 (atrans, bbugas of lane's (column, g))
+    double* gstateB;    // per resident warp: nlay x 4 x 32 (atot, bbutot, efclfrac, cldfmc), cloudy layers only
+    int LP, LP1;        // padded layer / level extents (multiples of 16)
+    int gwarps;         // resident warps the state slots were sized for (grid x warps per CTA)
     // debug capture of one column
     int dbg_col;        // chunk-relative column or -1
     double *dbg_taug, *dbg_fracs;  // (140, nlay)

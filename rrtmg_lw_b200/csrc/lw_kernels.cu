@@ -322,6 +322,60 @@ __global__ void __launch_bounds__(128) finalize_kernel(ColIn in, ColOut out, Scr
     }
 }
 
+// flux close-out for the g-lane path: band sums are level-fastest in s.fluxT (6 x pitch x LP1)
+__global__ void __launch_bounds__(128) finalizeT_kernel(ColIn in, ColOut out, Scratch s, RunCfg r, int cloudy) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= r.ncol) return;
+    const long ci = r.c0 + i;
+    const int nlay = r.nlay;
+    const bool sep = cloudy && s.ctop[i] > 0;
+    const long fxs = s.pitch * (long)s.LP1;
+    const double* fx = s.fluxT + (long)i * s.LP1;
+    double fnet_lo = 0., fnetc_lo = 0., pz_lo = 0.;
+    for (int lev = 0; lev <= nlay; ++lev) {
+        const long o = ci + out.ld * lev;
+        const double d = fx[lev] * C.fluxfac;
+        const double u = fx[2 * fxs + lev] * C.fluxfac;
+        double uc, dc;
+        if (sep) { dc = fx[fxs + lev] * C.fluxfac; uc = fx[3 * fxs + lev] * C.fluxfac; }
+        else { uc = u; dc = d; }
+        out.uflx[o] = u; out.dflx[o] = d; out.uflxc[o] = uc; out.dflxc[o] = dc;
+        if (r.idrv == 1) {
+            const double du = fx[4 * fxs + lev];
+            out.duflx_dt[o] = du;
+            out.duflxc_dt[o] = sep ? fx[5 * fxs + lev] : du;
+        }
+        const double fnet = u - d, fnetc = uc - dc;
+        const double pz = in.plev[ci + in.ld * lev];
+        if (lev > 0) {
+            const long oh = ci + out.ld * (lev - 1);
+            out.hr[oh] = C.heatfac * (fnet_lo - fnet) / (pz_lo - pz);
+            out.hrc[oh] = C.heatfac * (fnetc_lo - fnetc) / (pz_lo - pz);
+        }
+        fnet_lo = fnet; fnetc_lo = fnetc; pz_lo = pz;
+    }
+}
+
+// column-fastest planes -> layer-fastest planes: dst[(p*P + i)*LP + l] = src[p*pstride + l*lstride + i]
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ src, T* __restrict__ dst, long pstride,
+                                                        long lstride, int nlay, int ncol, long P, int LP) {
+    __shared__ T tile[32][33];
+    const int p = blockIdx.z;
+    const int c0 = blockIdx.x * 32, l0 = blockIdx.y * 32;
+    const T* sp = src + (long)p * pstride;
+    T* dp = dst + (long)p * P * LP;
+    for (int k = threadIdx.y; k < 32; k += 8) {
+        const int l = l0 + k, c = c0 + threadIdx.x;
+        if (l < nlay && c < ncol) tile[k][threadIdx.x] = sp[(long)l * lstride + c];
+    }
+    __syncthreads();
+    for (int k = threadIdx.y; k < 32; k += 8) {
+        const int c = c0 + k, l = l0 + threadIdx.x;
+        if (c < ncol && l < nlay) dp[(long)c * LP + l] = tile[threadIdx.x][k];
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // get_alpha, src/mcica_subcol_gen_lw.f90:129-178
 __global__ void get_alpha_kernel(int ncol, long ld, int nlay, int icld, int idcor, double decorr_con, const double* dz,
@@ -395,6 +449,21 @@ void launch_cldflags(const ColIn& in, const Scratch& s, const RunCfg& r, cudaStr
 }
 void launch_finalize(const ColIn& in, const ColOut& out, const Scratch& s, const RunCfg& r, int cloudy, cudaStream_t st) {
     finalize_kernel<<<nblk(r.ncol, 128), 128, 0, st>>>(in, out, s, r, cloudy);
+}
+void launch_finalizeT(const ColIn& in, const ColOut& out, const Scratch& s, const RunCfg& r, int cloudy, cudaStream_t st) {
+    finalizeT_kernel<<<nblk(r.ncol, 128), 128, 0, st>>>(in, out, s, r, cloudy);
+}
+void launch_transposes(const Scratch& s, const RunCfg& r, int with_mask, cudaStream_t st) {
+    const dim3 blk(32, 8);
+    const long plane = (long)r.nlay * s.pitch;
+    const dim3 g1(nblk(r.ncol, 32), nblk(r.nlay, 32), NFIELD);
+    transpose_kernel<double><<<g1, blk, 0, st>>>(s.fld, s.fldT, plane, s.pitch, r.nlay, r.ncol, s.pitch, s.LP);
+    const dim3 g2(nblk(r.ncol, 32), nblk(r.nlay, 32), 1);
+    transpose_kernel<int><<<g2, blk, 0, st>>>(s.ipack, s.ipackT, plane, s.pitch, r.nlay, r.ncol, s.pitch, s.LP);
+    if (with_mask) {
+        const dim3 g3(nblk(r.ncol, 32), nblk(r.nlay, 32), 5);
+        transpose_kernel<unsigned><<<g3, blk, 0, st>>>(s.mask, s.maskT, s.pitch, 5 * s.pitch, r.nlay, r.ncol, s.pitch, s.LP);
+    }
 }
 void launch_get_alpha(int ncol, long ld, int nlay, int icld, int idcor, double decorr_con, const double* dz,
                       const double* lat, int juldat, const double* cldfrac, double* alpha, double am1, double am2,

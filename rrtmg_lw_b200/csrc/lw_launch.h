@@ -31,4 +31,14 @@ cudaError_t upload_constants_kernels(const ConstTab&, const DevPtrs&, const doub
     cudaError_t upload_constants_tu##n(const ConstTab&, const DevPtrs&, const double (*refrat)[5]);
 LW_DECL_TU(0) LW_DECL_TU(1) LW_DECL_TU(2) LW_DECL_TU(3) LW_DECL_TU(4) LW_DECL_TU(5)
 #undef LW_DECL_TU
+
+// g-lane band kernels (lw_gband.cuh): grid = persistent CTAs
+#define LW_NUM_GBAND_TUS 8
+#define LW_DECL_GTU(n)                                                                                      \
+    bool launch_gband_tu##n(int band, int cld, int grid, const ColIn&, const Scratch&, const RunCfg&, cudaStream_t); \
+    cudaError_t upload_constants_gtu##n(const ConstTab&, const DevPtrs&, const double (*refrat)[5]);
+LW_DECL_GTU(0) LW_DECL_GTU(1) LW_DECL_GTU(2) LW_DECL_GTU(3) LW_DECL_GTU(4) LW_DECL_GTU(5) LW_DECL_GTU(6) LW_DECL_GTU(7)
+#undef LW_DECL_GTU
+void launch_transposes(const Scratch&, const RunCfg&, int with_mask, cudaStream_t);
+void launch_finalizeT(const ColIn&, const ColOut&, const Scratch&, const RunCfg&, int cloudy, cudaStream_t);
 }  // namespace lw
