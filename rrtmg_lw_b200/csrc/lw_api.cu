@@ -108,8 +108,9 @@ int ensure_scratch(long cols, int nlay) {
     if (A(&S.ipackT, (size_t)P * S.LP)) return RRTMG_LW_ERR_CUDA;
     if (A(&S.maskT, (size_t)5 * P * S.LP)) return RRTMG_LW_ERR_CUDA;
     if (A(&S.fluxT, (size_t)6 * P * S.LP1)) return RRTMG_LW_ERR_CUDA;
-    if (A(&S.gstate, (size_t)S.gwarps * nlay * 64)) return RRTMG_LW_ERR_CUDA;
-    if (A(&S.gstateB, (size_t)S.gwarps * nlay * 128)) return RRTMG_LW_ERR_CUDA;
+    if (A(&S.fluxC, (size_t)6 * P * (nlay + 1))) return RRTMG_LW_ERR_CUDA;
+    if (A(&S.gstate, (size_t)S.gwarps * nlay * 128)) return RRTMG_LW_ERR_CUDA;
+    if (A(&S.gstateB, (size_t)S.gwarps * nlay * 256)) return RRTMG_LW_ERR_CUDA;
     CK(cudaMemset(S.status, 0, sizeof(unsigned long long)));
     if (A(&S.dbg_taug, (size_t)NGPT * nlay)) return RRTMG_LW_ERR_CUDA;
     if (A(&S.dbg_fracs, (size_t)NGPT * nlay)) return RRTMG_LW_ERR_CUDA;

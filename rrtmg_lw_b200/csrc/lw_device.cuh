@@ -53,8 +53,9 @@ struct Scratch {
     int* ipackT;        // pitch x LP
     unsigned* maskT;    // 5 x pitch x LP
     double* fluxT;      // 6 x pitch x LP1 : dflx, dflxc, uflx, uflxc, duflx_dt, duflxc_dt band sums, level fastest
-    double* gstate;     // per resident warp: nlay x 2 x 32 (atrans, bbugas of lane's (column, g))
-    double* gstateB;    // per resident warp: nlay x 4 x 32 (atot, bbutot, efclfrac, cldfmc), cloudy layers only
+    double* fluxC;      // 6 x (nlay+1) x pitch : same sums of the narrow bands, column fastest
+    double* gstate;     // per resident warp: nlay x 4 x 32 (atrans, bbugas of the lane's two g-points)
+    double* gstateB;    // per resident warp: nlay x 8 x 32 (atot, bbutot, efclfrac, cldfmc), cloudy layers only
     int LP, LP1;        // padded layer / level extents (multiples of 16)
     int gwarps;         // resident warps the state slots were sized for (grid x warps per CTA)
     // debug capture of one column

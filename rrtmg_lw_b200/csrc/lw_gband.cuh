@@ -1,41 +1,58 @@
-// lw_gband.cuh -- the g-lane band kernel: one thread per (column, g-point) of one spectral band.
+// lw_gband.cuh -- the g-lane band kernel: the g-points of one (column, band) are spread over the
+// lanes of a "unit", two adjacent g-points per thread.
 //
 // Same physics as lw_band.cuh (taugbN -> cldprmc -> rtrnmc of one band; src/rrtmg_lw_taumol.f90,
 // src/rrtmg_lw_cldprmc.f90:164-271, src/rrtmg_lw_rtrnmc.f90:251-563), mapped for the memory system:
-//   * a warp holds UPW = 32/NGP columns ("units"), NGP = lanes per unit (NG rounded up to 2/4/8/16);
-//     lane g of a unit owns g-point g, so one k-table row (stored g-fastest, lw_tables.h) is ONE
-//     contiguous 16..128-byte access per unit instead of 32 scattered lines per load;
+//   * a warp holds UPW = 32/LPU columns ("units"), LPU = lanes per unit (NG/2 rounded up to
+//     2/4/8); lane j of a unit owns g-points 2j, 2j+1, so one k-table row (stored g-fastest,
+//     lw_tables.h) is ONE contiguous 32..128-byte access per unit made of 16-byte loads, instead
+//     of 32 scattered lines per load when lanes are columns;
 //   * the g-independent work of a layer (binary-species interpolation weights, continuum and
 //     minor-gas factors, Planck terms, cloud optics) is NOT replicated across the unit's lanes:
-//     in the "S-step" lane k of a unit does it for layer (top - k) of the current block of NGP
+//     in the "S-step" lane k of a unit does it for layer (top - k) of the current block of LPU
 //     layers and writes a record into the warp's shared-memory ring; in the "G-step" all lanes
-//     of the unit read the record of the current layer (a broadcast) and evaluate their g-point;
+//     of the unit read the record of the current layer (a broadcast) and evaluate their g-points;
 //   * the exp/tfn transmittance table (10 001 x 16 B) lives in shared memory: a gathered lookup
 //     costs bank conflicts, not one L1 tag pass per 128-byte line;
 //   * the vertical recurrences (radld/radlu, total and clear stream, d/dTs) run in registers;
 //     the per-(g,layer) transmittance/source pair needed again on the way up goes to a
 //     per-resident-warp slot (CTAs are persistent, so the slots total a few tens of MB and
-//     stay in L2), written and read as 256-byte rows;
-//   * the g-point -> band reduction is a transposing butterfly over the unit's lanes: NGP
-//     quantities (levels x streams) are reduced with NGP-1 exchanges and lane k ends up with
-//     quantity k, which it adds to the level-fastest band-flux scratch (coalesced per unit).
+//     stay in L2), written and read as full 256-byte rows, read four layers ahead;
+//   * the g-point -> band reduction is a butterfly over the unit's lanes; the lane that owns a
+//     (level, stream) keeps the sum and adds it to the band-flux scratch, whose running value
+//     it fetched at the start of the block;
+//   * wide bands (LPU = 8) read layer-fastest copies of the per-layer inputs (a unit's S-step
+//     reads 8 consecutive layers of one column), narrow bands (LPU <= 4) the column-fastest
+//     originals (8..16 consecutive columns of one layer): every S-step load is >= 64 contiguous
+//     bytes per unit group; the band-flux scratch follows the same choice.
 // Bit-exactness policy as in lw_band.cuh: everything feeding a table index keeps the reference's
 // association order (-fmad=false); only the g-sum order differs (tree instead of sequential,
 // SURVEY T16).
 #pragma once
+#include <type_traits>
+
 #include "lw_band.cuh"
 
 namespace lw {
 
-constexpr int GB_WARPS = 8;
+#ifndef GB_NWARPS
+#define GB_NWARPS 8
+#endif
+constexpr int GB_WARPS = GB_NWARPS;
 constexpr int GB_THREADS = GB_WARPS * 32;
-constexpr int GB_ETAB_BYTES = ((NTBL + 1) * 16 + 255) / 256 * 256;
+#ifndef GB_ETAB_SMEM
+#define GB_ETAB_SMEM 1   // 1: exp/tfn table in shared memory; 0: gathered through L1 (leaves ~160 KB of L1)
+#endif
+constexpr int GB_ETAB_BYTES = GB_ETAB_SMEM ? ((NTBL + 1) * 16 + 255) / 256 * 256 : 0;
 
 template <int B>
 struct GLanes {
     static constexpr int NG = NGC[B - 1];
-    static constexpr int NGP = NG > 8 ? 16 : (NG > 4 ? 8 : (NG > 2 ? 4 : 2));
-    static constexpr int UPW = 32 / NGP;
+    static constexpr int GPT = NG >= 4 ? 2 : 1;        // g-points per thread
+    static constexpr int NH = NG / GPT;                // threads a unit needs
+    static constexpr int LPU = NH > 4 ? 8 : (NH > 2 ? 4 : 2);  // lanes per unit
+    static constexpr int UPW = 32 / LPU;               // units (columns) per warp
+    static constexpr bool LAYER_FASTEST = LPU >= 8;    // which copy of the per-layer inputs / flux scratch is used
 };
 
 // per-band feature switches of the S-step record
@@ -72,7 +89,8 @@ struct GRec {
     static constexpr int NSLOT = S_CLD + 3;
 };
 constexpr int GB_MAXSLOT = 32;
-constexpr int GB_RING_DOUBLES = GB_MAXSLOT * 32;  // per warp
+constexpr int GB_RING_POS = 32;                   // records a warp's ring holds
+constexpr int GB_RING_DOUBLES = GB_MAXSLOT * GB_RING_POS;  // per warp
 constexpr size_t GB_SMEM_BYTES = (size_t)GB_ETAB_BYTES + (size_t)GB_WARPS * GB_RING_DOUBLES * sizeof(double);
 
 // layer-fastest accessor of the prep fields for BandLayer::setup
@@ -155,7 +173,7 @@ __device__ __forceinline__ void xreduce(double (&q)[N], int g) {
 template <int B>
 __device__ __forceinline__ void rec_store(double* p, const BandLayer<B>& W) {
     using R = GRec<B>;
-    auto put = [&](int slot, double v) { p[slot * 32] = v; };
+    auto put = [&](int slot, double v) { p[slot * GB_RING_POS] = v; };
     int rowa = 0, rowb = 0, na = 0, nb = 0;
     if (W.lower) {
         if constexpr (R::BIN_LO) {
@@ -196,7 +214,7 @@ __device__ __forceinline__ void rec_store(double* p, const BandLayer<B>& W) {
 template <int B>
 __device__ __forceinline__ void rec_load(const double* p, BandLayer<B>& W) {
     using R = GRec<B>;
-    auto get = [&](int slot) { return p[slot * 32]; };
+    auto get = [&](int slot) { return p[slot * GB_RING_POS]; };
     const double iw = get(R::S_INTS);
     const int wa = __double2loint(iw), wb = __double2hiint(iw);
     const int rowa = wa & 4095, rowb = (wa >> 12) & 4095;
@@ -238,42 +256,80 @@ __device__ __forceinline__ void rec_load(const double* p, BandLayer<B>& W) {
     if constexpr (R::CORR) W.corradj = get(R::S_CORR);
 }
 
+
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ double comp(const D2& v, int k) { return k == 0 ? v.x : v.y; }
+__device__ __forceinline__ double comp(double v, int) { return v; }
+
+// sum over the LPU lanes of a unit of NS interleaved quantities: on return every lane holds the
+// unit total of quantity (j % NS) (NS = 1 or 2), j = lane index inside the unit
+template <int LPU, int NS>
+__device__ __forceinline__ double unit_sum(double a, double b, int j) {
+    double v;
+    if constexpr (NS == 2) {
+        const bool hi = (j & 1) != 0;
+        const double send = hi ? a : b;
+        const double keep = hi ? b : a;
+        v = keep + shfl_xor_d(send, 1);
+#pragma unroll
+        for (int m = 2; m < LPU; m <<= 1) v = v + shfl_xor_d(v, m);
+    } else {
+        v = a;
+#pragma unroll
+        for (int m = 1; m < LPU; m <<= 1) v = v + shfl_xor_d(v, m);
+    }
+    return v;
+}
+
 template <int B, int CLD>
 __global__ void __launch_bounds__(GB_THREADS, 1) gband_kernel(ColIn in, Scratch s, RunCfg r) {
-    constexpr int NG = NGC[B - 1];
-    constexpr int G0 = GOFF[B - 1];
-    constexpr int NGP = GLanes<B>::NGP;
-    constexpr int UPW = GLanes<B>::UPW;
-    constexpr int NSD = CLD != CLD_NONE ? 2 : 1;  // streams per level: total (+ clear)
+    using GL = GLanes<B>;
     using R = GRec<B>;
+    constexpr int NG = GL::NG, GPT = GL::GPT, LPU = GL::LPU, UPW = GL::UPW;
+    constexpr bool LF = GL::LAYER_FASTEST;
+    constexpr int G0 = GOFF[B - 1];
+    constexpr int NSD = CLD != CLD_NONE ? 2 : 1;  // streams per level: total (+ clear)
+    constexpr int SB = GB_RING_POS / UPW;         // layers per S-step ( = LPU with 8 warps)
+    constexpr int LPR = LPU / NSD;                // levels per flush: lane j owns (level j / NSD, stream j % NSD)
+    constexpr int UB = LPR > 4 ? LPR : 4;         // levels per batch of state loads on the way up
+    constexpr int RS = GB_RING_POS;
+    constexpr bool FIRST = B == 1 || B == 6;      // first band writing its flux scratch (layer-fastest: 1, column-fastest: 6)
+    using V = typename std::conditional<GPT == 2, D2, double>::type;
     static_assert(R::NSLOT <= GB_MAXSLOT, "ring record too large");
+    static_assert(SB == LPU && SB % LPR == 0 && UB % LPR == 0, "block geometry");
     extern __shared__ __align__(16) unsigned char gb_smem[];
-    double2* etab = reinterpret_cast<double2*>(gb_smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double* ring = reinterpret_cast<double*>(gb_smem + GB_ETAB_BYTES) + warp * GB_RING_DOUBLES;
-
+#if GB_ETAB_SMEM
+    double2* etab = reinterpret_cast<double2*>(gb_smem);
     for (int k = threadIdx.x; k <= NTBL; k += GB_THREADS) etab[k] = __ldg(D.exptfn + k);
     __syncthreads();
+#else
+    const double2* etab = D.exptfn;
+#endif
 
-    const int u = lane / NGP, g = lane % NGP;
-    const bool gact = g < NG;
+    const int u = lane / LPU, j = lane % LPU;
+    const int g0 = j * GPT;          // first g-point of this thread
+    const bool gact = g0 < NG;
     const int nlay = r.nlay;
     const long P = s.pitch;
     const int LP = s.LP, LP1 = s.LP1;
-    const long fstride = P * LP;
+    const long plane = (long)nlay * P;
     const double rec_6 = 0.166667;
     const double bpade = C.bpade;
     const double* tp = D.totplnk + 181 * (B - 1);
     const double delw = C.delwave[B - 1];
     const int gw = blockIdx.x * GB_WARPS + warp;
     const int total_warps = gridDim.x * GB_WARPS;
-    double* st0 = s.gstate + (size_t)gw * nlay * 64 + lane;    // [l0][2][32]
-    double* stB = s.gstateB + (size_t)gw * nlay * 128 + lane;  // [l0][4][32]
+    // state slots of this resident warp: [l0][2*GPT][32] and (cloudy layers) [l0][4*GPT][32]
+    double* st0 = s.gstate + (size_t)gw * nlay * 128 + lane;
+    double* stB = s.gstateB + (size_t)gw * nlay * 256 + lane;
     const long ngroups = (r.ncol + UPW - 1) / UPW;
     // ring position of (unit u, record k) = k*UPW + u: the UPW units read consecutive 8-byte words
-    double* ring_w = ring + (g * UPW + u);
+    double* ring_w = ring + (j * UPW + u);
     const double* ring_r = ring + u;
+    const int og = j / NSD, ost = j % NSD;  // flush ownership of this lane
 
     auto planck = [&](double t) {
         int it = (int)(t - 159.);
@@ -321,45 +377,90 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gband_kernel(ColIn in, Scratch 
             }
         }
         const double reflect = 1. - semiss;
-        double* fx = s.fluxT + (long)i * LP1;  // + stream * P * LP1 + level
-        const long fxs = P * LP1;
+        // band-flux scratch: element (stream, level) of this column
+        auto fxp = [&](int stream, int level) -> double* {
+            if constexpr (LF) return s.fluxT + ((long)stream * P + i) * LP1 + level;
+            else return s.fluxC + ((long)stream * (nlay + 1) + level) * P + i;
+        };
+        // L2 prefetch of the per-layer inputs of the S-block that starts at layer `top`
+        auto prefetch_block = [&](int top) {
+            const int lev_s = top - j;
+            if (lev_s < 1) return;
+            const int l0 = lev_s - 1;
+            const long a = ci + in.ld * l0;
+            prefetch_l2(in.tlay + a);
+            prefetch_l2(in.tlev + a);
+            prefetch_l2(in.tauaer + ci + in.ld * (l0 + (long)nlay * (B - 1)));
+            constexpr unsigned fmask = band_fields(B);
+            if constexpr (LF) {
+                // one line of a field row covers 16 layers: lane j fetches fields j, j + LPU, ...
+                const int lb = top - 1 - (SB - 1) < 0 ? 0 : top - SB;
+                for (int f = j; f < NFIELD; f += LPU)
+                    if (fmask & (1u << f)) prefetch_l2(s.fldT + ((long)f * P + i) * LP + lb);
+            } else {
+#pragma unroll
+                for (int f = 0; f < NFIELD; ++f)
+                    if (fmask & (1u << f)) prefetch_l2(s.fld + (long)f * plane + (long)l0 * P + i);
+            }
+        };
 
-        double radld = 0., radclrd = 0.;
-        double pf_sfc = 0.;  // fracs(1, g): Planck fraction of the surface layer (for rad0 and d_rad0_dt)
+        double radld[GPT], radclrd[GPT], pf_sfc[GPT];
+#pragma unroll
+        for (int k = 0; k < GPT; ++k) { radld[k] = 0.; radclrd[k] = 0.; pf_sfc[k] = 0.; }
 
         // ------------------------------------------------------------ downward sweep, rtrnmc.f90:350-455
-        const int nblk = (nlay + NGP - 1) / NGP;
-        for (int blk = 0; blk < nblk; ++blk) {
-            const int lev_top = nlay - blk * NGP;
-            // ---- S-step: lane g prepares layer lev_top - g of its unit
+        double acc = 0., oldf = 0.;
+        int flev = 0;  // level this lane flushes next
+        for (int top = nlay; top >= 1; top -= SB) {
+            // ---- S-step: lane j prepares layer top - j of its unit
             {
-                const int lev_s = lev_top - g;
+                const int lev_s = top - j;
                 if (lev_s >= 1) {
                     const int l0 = lev_s - 1;
                     const long a = ci + in.ld * l0;
-                    const LayerT L{s.fldT + (long)i * LP + l0, fstride};
                     double pavel = 0.;
                     if constexpr (B == 1 || B == 2) pavel = in.play[a];
                     BandLayer<B> W;
                     W.jm0 = 0; W.jm1 = 0; W.jpl = 0; W.inds = 0; W.indf = 0; W.indm = 0; W.r0 = 0; W.r1 = 0;
-                    W.setup(L, s.ipackT[(long)i * LP + l0], lev_s <= laytrop, pavel);
+                    unsigned w4 = 0, mlo = 0, mhi = 0;
+                    constexpr int wlo = G0 >> 5, sh = G0 & 31;
+                    if constexpr (LF) {
+                        const LayerT L{s.fldT + (long)i * LP + l0, P * LP};
+                        W.setup(L, s.ipackT[(long)i * LP + l0], lev_s <= laytrop, pavel);
+                        if constexpr (CLD != CLD_NONE) {
+                            w4 = s.maskT[((long)4 * P + i) * LP + l0];
+                            if constexpr (CLD == CLD_MASK) {
+                                mlo = s.maskT[((long)wlo * P + i) * LP + l0];
+                                if constexpr (sh + NG > 32) mhi = s.maskT[((long)(wlo + 1) * P + i) * LP + l0];
+                            }
+                        }
+                    } else {
+                        const LayerRef L{s, (long)l0 * P + i, plane};
+                        W.setup(L, s.ipack[(long)l0 * P + i], lev_s <= laytrop, pavel);
+                        if constexpr (CLD != CLD_NONE) {
+                            const unsigned* mw = s.mask + ((long)l0 * 5) * P + i;
+                            w4 = mw[4 * P];
+                            if constexpr (CLD == CLD_MASK) {
+                                mlo = mw[(long)wlo * P];
+                                if constexpr (sh + NG > 32) mhi = mw[(long)(wlo + 1) * P];
+                            }
+                        }
+                    }
                     rec_store<B>(ring_w, W);
                     const double blay = planck(in.tlay[a]);
                     const double plev_dn = planck(in.tlev[a]);            // planklev(lev-1)
                     const double plev_up = planck(in.tlev[a + in.ld]);    // planklev(lev)
-                    ring_w[(R::S_PLK + 0) * 32] = blay;
-                    ring_w[(R::S_PLK + 1) * 32] = plev_up - blay;
-                    ring_w[(R::S_PLK + 2) * 32] = plev_dn - blay;
-                    ring_w[(R::S_PLK + 3) * 32] = in.tauaer[ci + in.ld * (l0 + (long)nlay * (B - 1))];
+                    ring_w[(R::S_PLK + 0) * RS] = blay;
+                    ring_w[(R::S_PLK + 1) * RS] = plev_up - blay;
+                    ring_w[(R::S_PLK + 2) * RS] = plev_dn - blay;
+                    ring_w[(R::S_PLK + 3) * RS] = in.tauaer[ci + in.ld * (l0 + (long)nlay * (B - 1))];
                     if constexpr (CLD != CLD_NONE) {
-                        const unsigned w4 = s.maskT[((long)4 * P + i) * LP + l0];
                         int cw = (w4 >> 31) ? 1 : 0;
                         if constexpr (CLD == CLD_MASK) {
                             double odcld_b = 0., abscld_b = 0.;
                             if (cw) {
-                                constexpr int wlo = G0 >> 5, sh = G0 & 31;
-                                unsigned lo = s.maskT[((long)wlo * P + i) * LP + l0] >> sh;
-                                if constexpr (sh + NG > 32) lo |= s.maskT[((long)(wlo + 1) * P + i) * LP + l0] << (32 - sh);
+                                unsigned lo = mlo >> sh;
+                                if constexpr (sh + NG > 32) lo |= mhi << (32 - sh);
                                 const unsigned bits = lo & ((1u << NG) - 1u);
                                 if (bits) {
                                     const double ciwp = in.ciwp[a], clwp = in.clwp[a];
@@ -370,248 +471,288 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gband_kernel(ColIn in, Scratch 
                                 }
                                 cw |= (int)(bits << 1);
                             }
-                            ring_w[(R::S_CLD + 0) * 32] = odcld_b;
-                            ring_w[(R::S_CLD + 1) * 32] = abscld_b;
+                            ring_w[(R::S_CLD + 0) * RS] = odcld_b;
+                            ring_w[(R::S_CLD + 1) * RS] = abscld_b;
                         }
-                        ring_w[(R::S_CLD + 2) * 32] = __hiloint2double(0, cw);
+                        ring_w[(R::S_CLD + 2) * RS] = __hiloint2double(0, cw);
                     }
                 }
+                if (top - SB >= 1) prefetch_block(top - SB);
             }
             __syncwarp();
-            // ---- G-step
-            double q[NGP];
-#pragma unroll
-            for (int jj = 0; jj < NGP; ++jj) {
-                const int lev = lev_top - jj;
+            const int nin = top < SB ? top : SB;
+            for (int jj = 0; jj < nin; ++jj) {
+                const int lev = top - jj;
+                const int l0 = lev - 1;
+                if ((jj % LPR) == 0) {
+                    // this lane will own (level lev - 1 - og, stream ost) of the coming flush: fetch the running band sum early
+                    flev = lev - 1 - og;
+                    if constexpr (!FIRST) {
+                        if (live && flev >= 0) oldf = __ldcg(fxp(ost, flev));
+                    }
+                }
+                // ---- G-step for layer lev
                 double v_tot = 0., v_clr = 0.;
-                if (lev >= 1) {
-                    const int l0 = lev - 1;
+                {
                     const double* rp = ring_r + jj * UPW;
                     BandLayer<B> W;
                     rec_load<B>(rp, W);
-                    const double blay = rp[(R::S_PLK + 0) * 32];
-                    const double dplankup = rp[(R::S_PLK + 1) * 32];
-                    const double dplankdn = rp[(R::S_PLK + 2) * 32];
-                    const double taua = rp[(R::S_PLK + 3) * 32];
+                    const double blay = rp[(R::S_PLK + 0) * RS];
+                    const double dplankup = rp[(R::S_PLK + 1) * RS];
+                    const double dplankdn = rp[(R::S_PLK + 2) * RS];
+                    const double taua = rp[(R::S_PLK + 3) * RS];
                     bool cldlyr = false;
                     unsigned bits = 0;
                     double odcld_b = 0., abscld_b = 0.;
                     if constexpr (CLD != CLD_NONE) {
-                        const int cw = __double2loint(rp[(R::S_CLD + 2) * 32]);
+                        const int cw = __double2loint(rp[(R::S_CLD + 2) * RS]);
                         cldlyr = (cw & 1) != 0;
                         if constexpr (CLD == CLD_MASK) {
                             bits = ((unsigned)cw) >> 1;
-                            odcld_b = rp[(R::S_CLD + 0) * 32];
-                            abscld_b = rp[(R::S_CLD + 1) * 32];
+                            odcld_b = rp[(R::S_CLD + 0) * RS];
+                            abscld_b = rp[(R::S_CLD + 1) * RS];
                         }
                     }
                     if (gact) {
-                        double tg, plfrac;
-                        W.eval(g, tg, plfrac);
-                        const double taut = tg + taua;  // rad.f90:548-553
-                        double odepth = secdiff * taut;
-                        if (odepth < 0.0) odepth = 0.0;
-                        int d0 = -1, d1 = -1;
-                        double atrans, bbugas, bbd;
-                        if (CLD != CLD_NONE && cldlyr) {
-                            double cf, odc, ef;
-                            if constexpr (CLD == CLD_MASK) {
-                                const bool on = (bits >> g) & 1u;
-                                cf = on ? 1. : 0.; odc = on ? odcld_b : 0.; ef = on ? abscld_b : 0.;
-                            } else {
-                                // strict rrtmg_lw(): per-g cloud arrays (g fastest -> coalesced over the unit's lanes)
-                                const long a = ci + in.ld * l0;
-                                const long ag = (G0 + g) + 140 * a;
-                                cf = in.cldfmcl[ag];
-                                double tauc = in.taucmcl[ag];
-                                const double ciwp = in.ciwpmcl[ag], clwp = in.clwpmcl[ag];
-                                if (cf >= 1.e-20) tauc = cld_tauc<B>(r, ciwp, clwp, tauc, in.reicmcl[a], in.relqmcl[a]);
-                                if (cf == 1.) {
-                                    odc = secdiff * tauc;
-                                    ef = (1. - exp(-odc)) * cf;
+                        V tgv, pfv;
+                        W.template evalv<V>(g0, tgv, pfv);
+#pragma unroll
+                        for (int k = 0; k < GPT; ++k) {
+                            const int g = g0 + k;
+                            const double tg = comp(tgv, k), plfrac = comp(pfv, k);
+                            const double taut = tg + taua;  // rad.f90:548-553
+                            double odepth = secdiff * taut;
+                            if (odepth < 0.0) odepth = 0.0;
+                            int d0 = -1, d1 = -1;
+                            double atrans, bbugas, bbd;
+                            if (CLD != CLD_NONE && cldlyr) {
+                                double cf, odc, ef;
+                                if constexpr (CLD == CLD_MASK) {
+                                    const bool on = (bits >> g) & 1u;
+                                    cf = on ? 1. : 0.; odc = on ? odcld_b : 0.; ef = on ? abscld_b : 0.;
                                 } else {
-                                    odc = 0.; ef = 0.;
+                                    // strict rrtmg_lw(): per-g cloud arrays (g fastest -> coalesced over the unit's lanes)
+                                    const long a = ci + in.ld * l0;
+                                    const long ag = (G0 + g) + 140 * a;
+                                    cf = in.cldfmcl[ag];
+                                    double tauc = in.taucmcl[ag];
+                                    const double ciwp = in.ciwpmcl[ag], clwp = in.clwpmcl[ag];
+                                    if (cf >= 1.e-20) tauc = cld_tauc<B>(r, ciwp, clwp, tauc, in.reicmcl[a], in.relqmcl[a]);
+                                    if (cf == 1.) {
+                                        odc = secdiff * tauc;
+                                        ef = (1. - exp(-odc)) * cf;
+                                    } else {
+                                        odc = 0.; ef = 0.;
+                                    }
                                 }
-                            }
-                            // cloudy layer, rtrnmc.f90:358-425
-                            double odtot = odepth + odc;
-                            double atot, bbutot, gassrc, bbdtot;
-                            if (odtot < 0.06) {
-                                atrans = odepth - 0.5 * odepth * odepth;
-                                const double odepth_rec = rec_6 * odepth;
-                                gassrc = plfrac * (blay + dplankdn * odepth_rec) * atrans;
-                                atot = odtot - 0.5 * odtot * odtot;
-                                const double odtot_rec = rec_6 * odtot;
-                                bbdtot = plfrac * (blay + dplankdn * odtot_rec);
-                                bbd = plfrac * (blay + dplankdn * odepth_rec);
-                                bbugas = plfrac * (blay + dplankup * odepth_rec);
-                                bbutot = plfrac * (blay + dplankup * odtot_rec);
-                            } else if (odepth <= 0.06) {
-                                atrans = odepth - 0.5 * odepth * odepth;
-                                const double odepth_rec = rec_6 * odepth;
-                                gassrc = plfrac * (blay + dplankdn * odepth_rec) * atrans;
-                                odtot = odepth + odc;
-                                const double tblind = odtot / (bpade + odtot);
-                                const int ittot = (int)(10000.0 * tblind + 0.5);
-                                d1 = ittot;
-                                const double2 et = etab[ittot];
-                                const double tfactot = et.y;
-                                bbdtot = plfrac * (blay + tfactot * dplankdn);
-                                bbd = plfrac * (blay + dplankdn * odepth_rec);
-                                atot = 1. - et.x;
-                                bbugas = plfrac * (blay + dplankup * odepth_rec);
-                                bbutot = plfrac * (blay + tfactot * dplankup);
+                                // cloudy layer, rtrnmc.f90:358-425
+                                double odtot = odepth + odc;
+                                double atot, bbutot, gassrc, bbdtot;
+                                if (odtot < 0.06) {
+                                    atrans = odepth - 0.5 * odepth * odepth;
+                                    const double odepth_rec = rec_6 * odepth;
+                                    gassrc = plfrac * (blay + dplankdn * odepth_rec) * atrans;
+                                    atot = odtot - 0.5 * odtot * odtot;
+                                    const double odtot_rec = rec_6 * odtot;
+                                    bbdtot = plfrac * (blay + dplankdn * odtot_rec);
+                                    bbd = plfrac * (blay + dplankdn * odepth_rec);
+                                    bbugas = plfrac * (blay + dplankup * odepth_rec);
+                                    bbutot = plfrac * (blay + dplankup * odtot_rec);
+                                } else if (odepth <= 0.06) {
+                                    atrans = odepth - 0.5 * odepth * odepth;
+                                    const double odepth_rec = rec_6 * odepth;
+                                    gassrc = plfrac * (blay + dplankdn * odepth_rec) * atrans;
+                                    odtot = odepth + odc;
+                                    const double tblind = odtot / (bpade + odtot);
+                                    const int ittot = (int)(10000.0 * tblind + 0.5);
+                                    d1 = ittot;
+                                    const double2 et = etab[ittot];
+                                    const double tfactot = et.y;
+                                    bbdtot = plfrac * (blay + tfactot * dplankdn);
+                                    bbd = plfrac * (blay + dplankdn * odepth_rec);
+                                    atot = 1. - et.x;
+                                    bbugas = plfrac * (blay + dplankup * odepth_rec);
+                                    bbutot = plfrac * (blay + tfactot * dplankup);
+                                } else {
+                                    double tblind = odepth / (bpade + odepth);
+                                    const int itgas = (int)(10000.0 * tblind + 0.5);
+                                    d0 = itgas;
+                                    odepth = ldg(D.tau_tbl + itgas);
+                                    const double2 eg = etab[itgas];
+                                    atrans = 1. - eg.x;
+                                    const double tfacgas = eg.y;
+                                    gassrc = atrans * plfrac * (blay + tfacgas * dplankdn);
+                                    odtot = odepth + odc;
+                                    tblind = odtot / (bpade + odtot);
+                                    const int ittot = (int)(10000.0 * tblind + 0.5);
+                                    d1 = ittot;
+                                    const double2 et = etab[ittot];
+                                    const double tfactot = et.y;
+                                    bbdtot = plfrac * (blay + tfactot * dplankdn);
+                                    bbd = plfrac * (blay + tfacgas * dplankdn);
+                                    atot = 1. - et.x;
+                                    bbugas = plfrac * (blay + tfacgas * dplankup);
+                                    bbutot = plfrac * (blay + tfactot * dplankup);
+                                }
+                                radld[k] = radld[k] - radld[k] * (atrans + ef * (1. - atrans)) + gassrc + cf * (bbdtot * atot - gassrc);
+                                double* sB = stB + ((size_t)l0 * 4 * GPT + 4 * k) * 32;
+                                __stcg(sB, atot);
+                                __stcg(sB + 32, bbutot);
+                                __stcg(sB + 64, ef);
+                                __stcg(sB + 96, cf);
                             } else {
-                                double tblind = odepth / (bpade + odepth);
-                                const int itgas = (int)(10000.0 * tblind + 0.5);
-                                d0 = itgas;
-                                odepth = ldg(D.tau_tbl + itgas);
-                                const double2 eg = etab[itgas];
-                                atrans = 1. - eg.x;
-                                const double tfacgas = eg.y;
-                                gassrc = atrans * plfrac * (blay + tfacgas * dplankdn);
-                                odtot = odepth + odc;
-                                tblind = odtot / (bpade + odtot);
-                                const int ittot = (int)(10000.0 * tblind + 0.5);
-                                d1 = ittot;
-                                const double2 et = etab[ittot];
-                                const double tfactot = et.y;
-                                bbdtot = plfrac * (blay + tfactot * dplankdn);
-                                bbd = plfrac * (blay + tfacgas * dplankdn);
-                                atot = 1. - et.x;
-                                bbugas = plfrac * (blay + tfacgas * dplankup);
-                                bbutot = plfrac * (blay + tfactot * dplankup);
+                                // clear layer, rtrnmc.f90:426-445
+                                if (odepth <= 0.06) {
+                                    atrans = odepth - 0.5 * odepth * odepth;
+                                    odepth = rec_6 * odepth;
+                                    bbd = plfrac * (blay + dplankdn * odepth);
+                                    bbugas = plfrac * (blay + dplankup * odepth);
+                                } else {
+                                    const double tblind = odepth / (bpade + odepth);
+                                    const int itr = (int)(10000.0 * tblind + 0.5);
+                                    d0 = itr;
+                                    const double2 e = etab[itr];
+                                    atrans = 1. - e.x;
+                                    const double tausfac = e.y;
+                                    bbd = plfrac * (blay + tausfac * dplankdn);
+                                    bbugas = plfrac * (blay + tausfac * dplankup);
+                                }
+                                radld[k] = radld[k] + (bbd - radld[k]) * atrans;
                             }
-                            radld = radld - radld * (atrans + ef * (1. - atrans)) + gassrc + cf * (bbdtot * atot - gassrc);
-                            __stcg(stB + ((size_t)l0 * 4 + 0) * 32, atot);
-                            __stcg(stB + ((size_t)l0 * 4 + 1) * 32, bbutot);
-                            __stcg(stB + ((size_t)l0 * 4 + 2) * 32, ef);
-                            __stcg(stB + ((size_t)l0 * 4 + 3) * 32, cf);
-                        } else {
-                            // clear layer, rtrnmc.f90:426-445
-                            if (odepth <= 0.06) {
-                                atrans = odepth - 0.5 * odepth * odepth;
-                                odepth = rec_6 * odepth;
-                                bbd = plfrac * (blay + dplankdn * odepth);
-                                bbugas = plfrac * (blay + dplankup * odepth);
-                            } else {
-                                const double tblind = odepth / (bpade + odepth);
-                                const int itr = (int)(10000.0 * tblind + 0.5);
-                                d0 = itr;
-                                const double2 e = etab[itr];
-                                atrans = 1. - e.x;
-                                const double tausfac = e.y;
-                                bbd = plfrac * (blay + tausfac * dplankdn);
-                                bbugas = plfrac * (blay + tausfac * dplankup);
+                            __stcg(st0 + ((size_t)l0 * 2 * GPT + 2 * k) * 32, atrans);
+                            __stcg(st0 + ((size_t)l0 * 2 * GPT + 2 * k + 1) * 32, bbugas);
+                            if (CLD != CLD_NONE) {
+                                // clear-sky stream: identical to the total stream above the highest cloudy layer
+                                if (lev <= ctop) radclrd[k] = radclrd[k] + (bbd - radclrd[k]) * atrans;
+                                else radclrd[k] = radld[k];
                             }
-                            radld = radld + (bbd - radld) * atrans;
+                            if (lev == 1) pf_sfc[k] = plfrac;
+                            if (dbg) {
+                                const long o = (long)(G0 + g) * nlay + l0;
+                                s.dbg_taug[o] = tg; s.dbg_fracs[o] = plfrac;
+                                s.dbg_itr[2 * o] = d0; s.dbg_itr[2 * o + 1] = d1;
+                            }
                         }
-                        __stcg(st0 + ((size_t)l0 * 2 + 0) * 32, atrans);
-                        __stcg(st0 + ((size_t)l0 * 2 + 1) * 32, bbugas);
-                        if (CLD != CLD_NONE) {
-                            // clear-sky stream: identical to the total stream above the highest cloudy layer
-                            if (lev <= ctop) radclrd = radclrd + (bbd - radclrd) * atrans;
-                            else radclrd = radld;
-                        }
-                        v_tot = radld;
-                        v_clr = radclrd;
-                        if (lev == 1) pf_sfc = plfrac;
-                        if (dbg) {
-                            const long o = (long)(G0 + g) * nlay + l0;
-                            s.dbg_taug[o] = tg; s.dbg_fracs[o] = plfrac;
-                            s.dbg_itr[2 * o] = d0; s.dbg_itr[2 * o + 1] = d1;
-                        }
+                        v_tot = radld[0];
+                        v_clr = radclrd[0];
+                        if constexpr (GPT == 2) { v_tot = v_tot + radld[1]; v_clr = v_clr + radclrd[1]; }
                     }
                 }
-                // push (level lev-1: total [, clear]) and flush when the reduction buffer is full
-                const int n0 = (jj * NSD) % NGP;
-                q[n0] = v_tot;
-                if constexpr (NSD == 2) q[n0 + 1] = v_clr;
-                if ((jj * NSD + NSD) % NGP == 0) {
-                    xreduce<NGP>(q, g);
-                    // lane g holds push number nb + g of this block, nb = first push of this flush
-                    const int nb = jj * NSD + NSD - NGP;
-                    const int pj = (nb + g) / NSD, pst = (nb + g) % NSD;
-                    const int plev = lev_top - pj;  // layer whose lower boundary (level plev-1) the value belongs to
-                    if (live && plev >= 1) {
-                        double* f = fx + (long)pst * fxs + (plev - 1);
-                        const double add = (q[0] * 0.5) * delw;
-                        if constexpr (B == 1) __stcg(f, 0.0 + add); else __stcg(f, __ldcg(f) + add);
+                // g-sum of this level's radiances; the owning lane keeps it until the flush
+                {
+                    const double sum = unit_sum<LPU, NSD>(v_tot, v_clr, j);
+                    if (og == (jj % LPR)) acc = sum;
+                    if ((jj % LPR) == LPR - 1 || lev == 1) {
+                        if (live && flev >= 0 && og <= (jj % LPR)) {
+                            const double add = (acc * 0.5) * delw;
+                            if constexpr (FIRST) __stcg(fxp(ost, flev), 0.0 + add); else __stcg(fxp(ost, flev), oldf + add);
+                        }
                     }
                 }
             }
             __syncwarp();
         }
-        if constexpr (B == 1) {
+        if constexpr (FIRST) {
             // downward flux at the top of the atmosphere is never touched by the sweep: drad(nlayers) = 0
-            if (live && g < NSD) __stcg(fx + (long)g * fxs + nlay, 0.0);
+            if (live && j < NSD) __stcg(fxp(j, nlay), 0.0);
         }
 
         // ------------------------------------------------------------ surface, rtrnmc.f90:465-484
-        double radlu = 0., radclru = 0., d_radlu = 0., d_radclru = 0.;
-        if (gact) {
-            const double rad0 = pf_sfc * plankbnd;
-            radlu = rad0 + reflect * radld;
-            radclru = rad0 + reflect * radclrd;
-            d_radlu = pf_sfc * dplankbnd_dt;
-            d_radclru = d_radlu;
+        double radlu[GPT], radclru[GPT], d_radlu[GPT], d_radclru[GPT];
+#pragma unroll
+        for (int k = 0; k < GPT; ++k) {
+            radlu[k] = 0.; radclru[k] = 0.; d_radlu[k] = 0.; d_radclru[k] = 0.;
+            if (gact) {
+                const double rad0 = pf_sfc[k] * plankbnd;
+                radlu[k] = rad0 + reflect * radld[k];
+                radclru[k] = rad0 + reflect * radclrd[k];
+                d_radlu[k] = pf_sfc[k] * dplankbnd_dt;
+                d_radclru[k] = d_radlu[k];
+            }
         }
         // ------------------------------------------------------------ upward sweep, rtrnmc.f90:486-529
-        // levels 0..nlay in blocks of NGP; level 0 is the surface (no layer update)
-        const int nblk_up = (nlay + 1 + NGP - 1) / NGP;
-        for (int blk = 0; blk < nblk_up; ++blk) {
-            const int lev_base = blk * NGP;
-            int cflag = 0;
-            if constexpr (CLD != CLD_NONE) {
-                const int lev_s = lev_base + g;
-                if (lev_s >= 1 && lev_s <= nlay) cflag = (int)(s.maskT[((long)4 * P + i) * LP + (lev_s - 1)] >> 31);
-            }
-            double q[NGP], qd[NGP];
+        // levels 0..nlay in batches of UB; level 0 is the surface (no layer update)
+        double accd = 0., oldd = 0.;
+        for (int base = 0; base <= nlay; base += UB) {
+            double sa[UB][GPT], sb[UB][GPT];
+            unsigned cfl[UB];
 #pragma unroll
-            for (int jj = 0; jj < NGP; ++jj) {
-                const int lev = lev_base + jj;
-                bool cldlyr = false;
-                if constexpr (CLD != CLD_NONE) cldlyr = __shfl_sync(0xffffffffu, cflag, u * NGP + jj) != 0;
-                if (lev >= 1 && lev <= nlay && gact) {
+            for (int q = 0; q < UB; ++q) {
+                const int lev = base + q;
+                cfl[q] = 0;
+                if (lev >= 1 && lev <= nlay) {
                     const int l0 = lev - 1;
-                    const double atrans = __ldcg(st0 + ((size_t)l0 * 2 + 0) * 32);
-                    const double bbugas = __ldcg(st0 + ((size_t)l0 * 2 + 1) * 32);
-                    if (CLD != CLD_NONE && cldlyr) {
-                        const double atot = __ldcg(stB + ((size_t)l0 * 4 + 0) * 32);
-                        const double bbutot = __ldcg(stB + ((size_t)l0 * 4 + 1) * 32);
-                        const double ef = __ldcg(stB + ((size_t)l0 * 4 + 2) * 32);
-                        const double cf = __ldcg(stB + ((size_t)l0 * 4 + 3) * 32);
-                        const double gassrc = bbugas * atrans;
-                        radlu = radlu - radlu * (atrans + ef * (1. - atrans)) + gassrc + cf * (bbutot * atot - gassrc);
-                        if (r.idrv == 1) d_radlu = d_radlu * cf * (1.0 - atot) + d_radlu * (1.0 - cf) * (1.0 - atrans);
-                    } else {
-                        radlu = radlu + (bbugas - radlu) * atrans;
-                        if (r.idrv == 1) d_radlu = d_radlu * (1.0 - atrans);
+                    if (gact) {
+#pragma unroll
+                        for (int k = 0; k < GPT; ++k) {
+                            sa[q][k] = __ldcg(st0 + ((size_t)l0 * 2 * GPT + 2 * k) * 32);
+                            sb[q][k] = __ldcg(st0 + ((size_t)l0 * 2 * GPT + 2 * k + 1) * 32);
+                        }
                     }
-                    if (CLD != CLD_NONE) {
-                        radclru = radclru + (bbugas - radclru) * atrans;
-                        if (r.idrv == 1) d_radclru = d_radclru * (1.0 - atrans);
+                    if constexpr (CLD != CLD_NONE) {
+                        if constexpr (LF) cfl[q] = s.maskT[((long)4 * P + i) * LP + l0];
+                        else cfl[q] = s.mask[((long)l0 * 5 + 4) * P + i];
                     }
                 }
-                const int n0 = (jj * NSD) % NGP;
-                q[n0] = radlu; qd[n0] = d_radlu;
-                if constexpr (NSD == 2) { q[n0 + 1] = radclru; qd[n0 + 1] = d_radclru; }
-                if ((jj * NSD + NSD) % NGP == 0) {
-                    const int nb = jj * NSD + NSD - NGP;
-                    const int pj = (nb + g) / NSD, pst = (nb + g) % NSD;
-                    const int plev = lev_base + pj;
-                    xreduce<NGP>(q, g);
-                    if (live && plev <= nlay) {
-                        double* f = fx + (long)(2 + pst) * fxs + plev;
-                        const double add = (q[0] * 0.5) * delw;
-                        if constexpr (B == 1) __stcg(f, 0.0 + add); else __stcg(f, __ldcg(f) + add);
+            }
+#pragma unroll
+            for (int q = 0; q < UB; ++q) {
+                const int lev = base + q;
+                if (lev <= nlay) {  // warp-uniform
+                    if ((q % LPR) == 0) {
+                        flev = lev + og;
+                        if constexpr (!FIRST) {
+                            if (live && flev <= nlay) {
+                                oldf = __ldcg(fxp(2 + ost, flev));
+                                if (r.idrv == 1) oldd = __ldcg(fxp(4 + ost, flev));
+                            }
+                        }
+                    }
+                    if (lev >= 1 && gact) {
+                        const int l0 = lev - 1;
+                        const bool cldlyr = (CLD != CLD_NONE) && (cfl[q] >> 31) != 0;
+#pragma unroll
+                        for (int k = 0; k < GPT; ++k) {
+                            const double atrans = sa[q][k], bbugas = sb[q][k];
+                            if (CLD != CLD_NONE && cldlyr) {
+                                const double* sB = stB + ((size_t)l0 * 4 * GPT + 4 * k) * 32;
+                                const double atot = __ldcg(sB);
+                                const double bbutot = __ldcg(sB + 32);
+                                const double ef = __ldcg(sB + 64);
+                                const double cf = __ldcg(sB + 96);
+                                const double gassrc = bbugas * atrans;
+                                radlu[k] = radlu[k] - radlu[k] * (atrans + ef * (1. - atrans)) + gassrc + cf * (bbutot * atot - gassrc);
+                                if (r.idrv == 1)
+                                    d_radlu[k] = d_radlu[k] * cf * (1.0 - atot) + d_radlu[k] * (1.0 - cf) * (1.0 - atrans);
+                            } else {
+                                radlu[k] = radlu[k] + (bbugas - radlu[k]) * atrans;
+                                if (r.idrv == 1) d_radlu[k] = d_radlu[k] * (1.0 - atrans);
+                            }
+                            if (CLD != CLD_NONE) {
+                                radclru[k] = radclru[k] + (bbugas - radclru[k]) * atrans;
+                                if (r.idrv == 1) d_radclru[k] = d_radclru[k] * (1.0 - atrans);
+                            }
+                        }
+                    }
+                    const bool mine = og == (q % LPR);
+                    const bool flush = (q % LPR) == LPR - 1 || lev == nlay;
+                    const bool st = live && flev <= nlay && og <= (q % LPR);
+                    double vt = radlu[0], vc = radclru[0];
+                    if constexpr (GPT == 2) { vt = vt + radlu[1]; vc = vc + radclru[1]; }
+                    const double sum = unit_sum<LPU, NSD>(vt, vc, j);
+                    if (mine) acc = sum;
+                    if (flush && st) {
+                        const double add = (acc * 0.5) * delw;
+                        if constexpr (FIRST) __stcg(fxp(2 + ost, flev), 0.0 + add); else __stcg(fxp(2 + ost, flev), oldf + add);
                     }
                     if (r.idrv == 1) {
-                        xreduce<NGP>(qd, g);
-                        if (live && plev <= nlay) {
-                            double* f = fx + (long)(4 + pst) * fxs + plev;
-                            const double add = (qd[0] * 0.5) * delw * C.fluxfac;
-                            if constexpr (B == 1) __stcg(f, 0.0 + add); else __stcg(f, __ldcg(f) + add);
+                        double dt = d_radlu[0], dc = d_radclru[0];
+                        if constexpr (GPT == 2) { dt = dt + d_radlu[1]; dc = dc + d_radclru[1]; }
+                        const double sumd = unit_sum<LPU, NSD>(dt, dc, j);
+                        if (mine) accd = sumd;
+                        if (flush && st) {
+                            const double add = (accd * 0.5) * delw * C.fluxfac;
+                            if constexpr (FIRST) __stcg(fxp(4 + ost, flev), 0.0 + add); else __stcg(fxp(4 + ost, flev), oldd + add);
                         }
                     }
                 }

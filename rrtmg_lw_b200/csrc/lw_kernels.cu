@@ -330,20 +330,25 @@ __global__ void __launch_bounds__(128) finalizeT_kernel(ColIn in, ColOut out, Sc
     const int nlay = r.nlay;
     const bool sep = cloudy && s.ctop[i] > 0;
     const long fxs = s.pitch * (long)s.LP1;
-    const double* fx = s.fluxT + (long)i * s.LP1;
+    const double* fx = s.fluxT + (long)i * s.LP1;          // wide bands, level fastest
+    const long fcs = (long)(nlay + 1) * s.pitch;
+    const double* fc = s.fluxC + i;                         // narrow bands, column fastest
     double fnet_lo = 0., fnetc_lo = 0., pz_lo = 0.;
     for (int lev = 0; lev <= nlay; ++lev) {
         const long o = ci + out.ld * lev;
-        const double d = fx[lev] * C.fluxfac;
-        const double u = fx[2 * fxs + lev] * C.fluxfac;
+        const long oc = (long)lev * s.pitch;
+        const double d = (fx[lev] + fc[oc]) * C.fluxfac;
+        const double u = (fx[2 * fxs + lev] + fc[2 * fcs + oc]) * C.fluxfac;
         double uc, dc;
-        if (sep) { dc = fx[fxs + lev] * C.fluxfac; uc = fx[3 * fxs + lev] * C.fluxfac; }
-        else { uc = u; dc = d; }
+        if (sep) {
+            dc = (fx[fxs + lev] + fc[fcs + oc]) * C.fluxfac;
+            uc = (fx[3 * fxs + lev] + fc[3 * fcs + oc]) * C.fluxfac;
+        } else { uc = u; dc = d; }
         out.uflx[o] = u; out.dflx[o] = d; out.uflxc[o] = uc; out.dflxc[o] = dc;
         if (r.idrv == 1) {
-            const double du = fx[4 * fxs + lev];
+            const double du = fx[4 * fxs + lev] + fc[4 * fcs + oc];
             out.duflx_dt[o] = du;
-            out.duflxc_dt[o] = sep ? fx[5 * fxs + lev] : du;
+            out.duflxc_dt[o] = sep ? fx[5 * fxs + lev] + fc[5 * fcs + oc] : du;
         }
         const double fnet = u - d, fnetc = uc - dc;
         const double pz = in.plev[ci + in.ld * lev];

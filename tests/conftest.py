@@ -34,6 +34,10 @@ def gpu(kblob):
     assert torch.cuda.is_available(), "gpu tests need a CUDA device; the library has no CPU fallback"
     from rrtmg_lw_b200 import api
     api.rrtmg_lw_ini(1004.0, kblob, 4)
+    # RRTMG_LW_BAND_KERNEL=2|3 runs the whole suite against the other band-kernel mapping
+    bk = os.environ.get("RRTMG_LW_BAND_KERNEL")
+    if bk:
+        api.set_option("band_kernel", int(bk))
     return api
 
 
