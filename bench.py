@@ -180,8 +180,8 @@ def main():
     ap.add_argument("--e2e-cols", type=int, default=131072)
     ap.add_argument("--ref-cols", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--band-kernel", type=int, default=3, choices=[2, 3],
-                    help="3 = one thread per (column, g-point); 2 = one thread per (column, band)")
+    ap.add_argument("--band-kernel", type=int, default=2, choices=[2, 3],
+                    help="2 = one thread per (column, band), all g-points in registers; 3 = g-points across lanes")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)

@@ -133,8 +133,9 @@ long rrtmg_lw_b200_get_table(const char* name, double* out, long cap);
 /* Upper bound of columns processed per internal pass (scratch is sized to it). */
 int rrtmg_lw_b200_set_chunk(int max_columns);
 
-/* Tuning switches (no reference counterpart).  "band_kernel": 3 (default) = one thread per
- * (column, g-point) with the exp/tfn table in shared memory, 2 = one thread per (column, band). */
+/* Tuning switches (no reference counterpart).  "band_kernel": 2 (default) = one thread per
+ * (column, band) with the band's g-points in registers; 3 = g-points spread over the lanes of a
+ * unit with the exp/tfn table in shared memory (lw_gband.cuh). */
 int rrtmg_lw_b200_set_option(const char* name, int value);
 /* Number of kernels launched by this library since the last call with reset != 0. */
 long rrtmg_lw_b200_launch_count(int reset);

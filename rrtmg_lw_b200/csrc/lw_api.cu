@@ -36,7 +36,7 @@ struct Ctx {
     double* stage = nullptr;
     size_t stage_doubles = 0;
     int chunk = 32768;
-    int band_kernel = 3;  // 3 = g-lane kernel (lw_gband.cuh), 2 = column-lane kernel (lw_band.cuh)
+    int band_kernel = 2;  // 2 = column-lane kernel (lw_band.cuh, fastest measured), 3 = g-lane kernel (lw_gband.cuh)
     int sms = 0;
     long launches = 0;
     bool dbg = false;

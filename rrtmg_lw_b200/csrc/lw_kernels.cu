@@ -238,6 +238,205 @@ __global__ void __launch_bounds__(128) mcica_kiss_kernel(ColIn in, Scratch s, Ru
     s.ctop[i] = ctop;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Sub-column-parallel KISS generator.  The reference draws a column's numbers as ONE stream
+// (sub-column outer, layer inner, mcica:523-543); the four component generators of KISS all have
+// closed-form n-step jumps, so thread (column, sub-column) starts its own copy of the stream at
+// draw  permuteseed + isubcol * draws_per_subcolumn :
+//   s1  x -> 69069 x + 1327217885 (mod 2^32)            affine map, n-fold composition
+//   s2  32-bit xorshift (13, 17, 5)                      linear over GF(2): a 32x32 bit matrix power
+//   s3  multiply-with-carry, a = 18000 (low/high half)   x -> a x mod (a 2^16 - 1)
+//   s4  multiply-with-carry, a = 30903                   x -> a x mod (a 2^16 - 1)
+// The host tabulates the 140 jumps once per (permuteseed, draws_per_subcolumn) (KissJump); the
+// numbers drawn are bit-identical to the sequential stream.  One CTA = one column, one warp = 32
+// sub-columns, so a layer's 32 cloud bits are one __ballot_sync.
+struct KissJump {
+    unsigned a1[NGPT], c1[NGPT];   // s1_n = a1 * s1_0 + c1
+    unsigned p3[NGPT], p4[NGPT];   // a^(n-1) mod m (applied after one explicit step; n = 0 -> unused)
+    unsigned n[NGPT];              // the jump distance itself
+    unsigned m2[NGPT][32];         // columns of the xorshift matrix power
+};
+constexpr unsigned KISS_M3 = 18000u * 65536u - 1u, KISS_M4 = 30903u * 65536u - 1u;
+
+__global__ void __launch_bounds__(160) mcica_kiss_par_kernel(ColIn in, Scratch s, RunCfg r, const KissJump* __restrict__ J) {
+    extern __shared__ unsigned mk_words[];  // nlay x 5 mask words, then 1 word: cloud top
+    const int i = blockIdx.x;
+    const long ci = r.c0 + i;
+    const int nlay = r.nlay;
+    const long P = s.pitch;
+    const int icld = r.icld;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sc = w * 32 + lane;
+    const bool act = sc < NGPT;
+    const double cldmin = 1.0e-20;
+    const double p1 = in.play[ci] * 1.e2, p2 = in.play[ci + in.ld] * 1.e2;
+    if (p1 < p2) {  // uniform over the CTA
+        if (threadIdx.x == 0) { raise(s, 4, ci, 1); s.ctop[i] = 0; }
+        return;
+    }
+    if (threadIdx.x == 0) mk_words[nlay * 5] = 0u;
+    Kiss k;
+    if (act) {
+        const double p3 = in.play[ci + 2 * in.ld] * 1.e2, p4 = in.play[ci + 3 * in.ld] * 1.e2;
+        const unsigned z1 = (unsigned)(int)((p1 - (double)(int)p1) * 1000000000.0);
+        const unsigned z2 = (unsigned)(int)((p2 - (double)(int)p2) * 1000000000.0);
+        const unsigned z3 = (unsigned)(int)((p3 - (double)(int)p3) * 1000000000.0);
+        const unsigned z4 = (unsigned)(int)((p4 - (double)(int)p4) * 1000000000.0);
+        k.s1 = J->a1[sc] * z1 + J->c1[sc];
+        unsigned y = 0;
+#pragma unroll 8
+        for (int b = 0; b < 32; ++b) y ^= ((z2 >> b) & 1u) ? J->m2[sc][b] : 0u;
+        k.s2 = y;
+        if (J->n[sc] == 0u) {
+            k.s3 = z3; k.s4 = z4;
+        } else {
+            unsigned t3 = 18000u * (z3 & 65535u) + (z3 >> 16);
+            unsigned t4 = 30903u * (z4 & 65535u) + (z4 >> 16);
+            if (t3 != KISS_M3) t3 = (unsigned)(((unsigned long long)J->p3[sc] * t3) % KISS_M3);
+            if (t4 != KISS_M4) t4 = (unsigned)(((unsigned long long)J->p4[sc] * t4) % KISS_M4);
+            k.s3 = t3; k.s4 = t4;
+        }
+    } else {
+        k.s1 = k.s2 = k.s3 = k.s4 = 0u;
+    }
+    double prev = 0.;
+    double rmax = 0.;
+    if (icld == 3 && act) rmax = k.next();
+    double cfm = 0.;
+    for (int l = 0; l < nlay; ++l) {
+        double cf = in.cldfrac[ci + in.ld * l];
+        if (cf < cldmin) cf = 0.;
+        double x;
+        if (icld == 3) {
+            x = rmax;
+        } else {
+            x = k.next();
+            if (icld >= 4) {
+                const double x2 = k.next();
+                if (l > 0 && x2 < in.alpha[ci + in.ld * l]) x = prev;
+            } else if (icld == 2 && l > 0) {
+                if (prev > 1. - cfm) x = prev; else x = x * (1. - cfm);
+            }
+        }
+        prev = x;
+        cfm = cf;
+        const unsigned word = __ballot_sync(0xffffffffu, act && (x >= 1. - cf));
+        if (lane == 0) mk_words[l * 5 + w] = word;
+    }
+    __syncthreads();
+    // per-layer cloud flag (icldlyr), column cloud top, cldprmc input validation, mask write-out
+    for (int l = threadIdx.x; l < nlay; l += blockDim.x) {
+        unsigned any = 0;
+#pragma unroll
+        for (int q = 0; q < 5; ++q) any |= mk_words[l * 5 + q];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) s.mask[((long)l * 5 + q) * P + i] = mk_words[l * 5 + q];
+        s.mask[((long)l * 5 + 4) * P + i] = mk_words[l * 5 + 4] | (any ? 0x80000000u : 0u);
+        if (any) {
+            atomicMax(&mk_words[nlay * 5], (unsigned)(l + 1));
+            const long a = ci + in.ld * l;
+            const double ciwp = in.ciwp[a], clwp = in.clwp[a];
+            bool taubig = false;
+            if (in.tauc) for (int b = 0; b < 16; ++b) taubig |= in.tauc[b + 16 * a] >= cldmin;
+            if ((ciwp + clwp) >= cldmin || taubig) {
+                if (r.inflag == 1) raise(s, 1, ci, l + 1);
+                if (r.inflag == 2) {
+                    if (ciwp != 0.0) {
+                        const double rad = in.rei[a];
+                        if ((r.iceflag == 0 && rad < 10.0) || (r.iceflag == 1 && (rad < 13.0 || rad > 130.)) ||
+                            (r.iceflag == 2 && (rad < 5.0 || rad > 131.0)) || (r.iceflag == 3 && (rad < 5.0 || rad > 140.0)))
+                            raise(s, 2, ci, l + 1);
+                    }
+                    if (clwp != 0.0 && r.liqflag == 1) {
+                        const double rad = in.rel[a];
+                        if (rad < 2.5 || rad > 60.) raise(s, 3, ci, l + 1);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s.ctop[i] = (int)mk_words[nlay * 5];
+}
+
+// host side of the jumps ---------------------------------------------------------------------
+namespace {
+struct KissMap {               // n-step map of the four component generators
+    unsigned a1, c1;           // affine map of s1
+    unsigned m2[32];           // matrix columns of s2
+    unsigned long long p3, p4; // multipliers of s3, s4 (mod m)
+};
+unsigned xs_step(unsigned v) { v ^= v << 13; v ^= v >> 17; v ^= v << 5; return v; }
+unsigned m2_apply(const unsigned* m, unsigned x) {
+    unsigned y = 0;
+    for (int b = 0; b < 32; ++b) if ((x >> b) & 1u) y ^= m[b];
+    return y;
+}
+KissMap kiss_identity() {
+    KissMap k; k.a1 = 1u; k.c1 = 0u; k.p3 = 1; k.p4 = 1;
+    for (int b = 0; b < 32; ++b) k.m2[b] = 1u << b;
+    return k;
+}
+KissMap kiss_one() {
+    KissMap k; k.a1 = 69069u; k.c1 = 1327217885u; k.p3 = 18000; k.p4 = 30903;
+    for (int b = 0; b < 32; ++b) k.m2[b] = xs_step(1u << b);
+    return k;
+}
+// first y, then x
+KissMap kiss_compose(const KissMap& x, const KissMap& y) {
+    KissMap k;
+    k.a1 = x.a1 * y.a1; k.c1 = x.a1 * y.c1 + x.c1;
+    for (int b = 0; b < 32; ++b) k.m2[b] = m2_apply(x.m2, y.m2[b]);
+    k.p3 = (x.p3 * y.p3) % KISS_M3; k.p4 = (x.p4 * y.p4) % KISS_M4;
+    return k;
+}
+KissMap kiss_power(unsigned long long n) {
+    KissMap res = kiss_identity(), base = kiss_one();
+    while (n) {
+        if (n & 1ull) res = kiss_compose(base, res);
+        base = kiss_compose(base, base);
+        n >>= 1;
+    }
+    return res;
+}
+struct KissJumpCache {
+    KissJump* dev = nullptr;
+    long key_seed = -1, key_draws = -1;
+} g_kj;
+}  // namespace
+
+// fills (and caches) the device jump table for jumps permuteseed + isubcol * draws, isubcol = 0..139
+static const KissJump* kiss_jump_table(int permuteseed, long draws, cudaStream_t st) {
+    if (!g_kj.dev) {
+        if (cudaMalloc((void**)&g_kj.dev, sizeof(KissJump)) != cudaSuccess) return nullptr;
+    }
+    if (g_kj.key_seed == permuteseed && g_kj.key_draws == draws) return g_kj.dev;
+    static KissJump h;  // host staging (pageable; the copy below is synchronous with respect to the host buffer)
+    const unsigned long long n0 = permuteseed > 0 ? (unsigned long long)permuteseed : 0ull;
+    // multipliers are tabulated for n - 1 steps (the kernel takes the first MWC step explicitly, which
+    // maps any 32-bit seed into the range where the modular form is exact)
+    const KissMap stepD = kiss_power((unsigned long long)draws);
+    KissMap cur = kiss_power(n0);
+    const KissMap inv_guard = kiss_identity();
+    (void)inv_guard;
+    for (int sc = 0; sc < NGPT; ++sc) {
+        const unsigned long long n = n0 + (unsigned long long)sc * (unsigned long long)draws;
+        h.a1[sc] = cur.a1; h.c1[sc] = cur.c1;
+        for (int b = 0; b < 32; ++b) h.m2[sc][b] = cur.m2[b];
+        h.n[sc] = n > 0xffffffffull ? 0xffffffffu : (unsigned)n;
+        if (n == 0) { h.p3[sc] = 1u; h.p4[sc] = 1u; }
+        else {
+            const KissMap m1 = kiss_power(n - 1);
+            h.p3[sc] = (unsigned)m1.p3; h.p4[sc] = (unsigned)m1.p4;
+        }
+        cur = kiss_compose(stepD, cur);
+    }
+    if (cudaMemcpyAsync(g_kj.dev, &h, sizeof(KissJump), cudaMemcpyHostToDevice, st) != cudaSuccess) return nullptr;
+    cudaStreamSynchronize(st);
+    g_kj.key_seed = permuteseed; g_kj.key_draws = draws;
+    return g_kj.dev;
+}
+
 // Cloud flags for the strict rrtmg_lw() entry: one warp scans the 140 sub-column fractions of a
 // (column, layer); icldlyr = any(cldfmc == 1) (rtrnmc.f90:316-329); validates like cldprmc.
 __global__ void __launch_bounds__(128) cldflags_kernel(ColIn in, Scratch s, RunCfg r) {
@@ -446,7 +645,11 @@ void launch_prep(const ColIn& in, const Scratch& s, const RunCfg& r, cudaStream_
     prep_kernel<<<nblk(r.ncol, 128), 128, 0, st>>>(in, s, r);
 }
 void launch_mcica_kiss(const ColIn& in, const Scratch& s, const RunCfg& r, cudaStream_t st) {
-    mcica_kiss_kernel<<<nblk(r.ncol, 128), 128, 0, st>>>(in, s, r);
+    const long draws = r.icld == 3 ? 1 : (r.icld >= 4 ? 2L * r.nlay : (long)r.nlay);
+    const KissJump* J = kiss_jump_table(r.permuteseed, draws, st);
+    if (!J) { mcica_kiss_kernel<<<nblk(r.ncol, 128), 128, 0, st>>>(in, s, r); return; }
+    const size_t smem = ((size_t)r.nlay * 5 + 1) * sizeof(unsigned);
+    mcica_kiss_par_kernel<<<r.ncol, 160, smem, st>>>(in, s, r, J);
 }
 void launch_cldflags(const ColIn& in, const Scratch& s, const RunCfg& r, cudaStream_t st) {
     zero_int_kernel<<<nblk(r.ncol, 256), 256, 0, st>>>(s.ctop, r.ncol);

@@ -266,3 +266,25 @@ def test_full_size_column_independence(gpu, oracle):
         tol = HR_TOL if k.startswith("hr") else FLUX_TOL
         err = float(np.abs(got[k][:, idx.to("cuda:0")].cpu().numpy() - ref[k]).max())
         assert err <= tol, (k, err)
+
+
+@pytest.mark.parametrize("kernel", [2, 3])
+def test_both_band_kernel_mappings_match_oracle(gpu, oracle, kernel):
+    """The two band-kernel mappings (set_option("band_kernel", 2|3)) reproduce the oracle: clear sky
+    with idrv = 1 and a McICA cloudy batch with aerosol."""
+    try:
+        gpu.set_option("band_kernel", kernel)
+        b = synth.make_batch(384, 72, aerosol=True)
+        ref = oracle.rrtmg_lw(b, idrv=1, nthreads=8)
+        got = driver.run_clear_or_strict(b, idrv=1, device="cuda:0")
+        gpu.sync()
+        _check(got, ref, 1, what="kernel %d clear" % kernel)
+        b = synth.make_batch(384, 72, cloudy=True, aerosol=True)
+        mc = oracle.mcica_subcol_lw(b, 2, permuteseed=1, irng=0)
+        ref = oracle.rrtmg_lw(b, icld=2, idrv=1, inflglw=2, iceflglw=3, liqflglw=1, mc=mc, nthreads=8)
+        got = driver.run_fused(b, icld=2, idrv=1, device="cuda:0")
+        gpu.sync()
+        _check(got, ref, 1, what="kernel %d cloudy" % kernel)
+    finally:
+        import os
+        gpu.set_option("band_kernel", int(os.environ.get("RRTMG_LW_BAND_KERNEL", "2")))
