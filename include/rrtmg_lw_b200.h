@@ -135,7 +135,9 @@ int rrtmg_lw_b200_set_chunk(int max_columns);
 
 /* Tuning switches (no reference counterpart).  "band_kernel": 2 (default) = one thread per
  * (column, band) with the band's g-points in registers; 3 = g-points spread over the lanes of a
- * unit with the exp/tfn table in shared memory (lw_gband.cuh). */
+ * unit with the exp/tfn table in shared memory (lw_gband.cuh).  "host_chunk": columns per staged
+ * pass of a host-pointer call (default 32768); passes alternate between two staging arenas so the
+ * H2D copy of pass k+1 and the D2H copy of pass k-1 overlap the kernels of pass k. */
 int rrtmg_lw_b200_set_option(const char* name, int value);
 /* Number of kernels launched by this library since the last call with reset != 0. */
 long rrtmg_lw_b200_launch_count(int reset);

@@ -36,6 +36,9 @@ struct Ctx {
     double* stage = nullptr;
     size_t stage_doubles = 0;
     int chunk = 32768;
+    int host_chunk = 32768;   // columns per staged pass of a host-pointer call (H2D / compute / D2H overlap)
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t e_in[2] = {nullptr, nullptr}, e_done[2] = {nullptr, nullptr}, e_out[2] = {nullptr, nullptr};
     int band_kernel = 2;  // 2 = column-lane kernel (lw_band.cuh, fastest measured), 3 = g-lane kernel (lw_gband.cuh)
     int sms = 0;
     long launches = 0;
@@ -245,6 +248,80 @@ struct Stager {
     }
 };
 
+int ensure_pipeline() {
+    if (G.s_in) return 0;
+    CK(cudaStreamCreateWithFlags(&G.s_in, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&G.s_out, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+        CK(cudaEventCreateWithFlags(&G.e_in[k], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&G.e_done[k], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&G.e_out[k], cudaEventDisableTiming));
+    }
+    return 0;
+}
+
+struct HostOut {
+    double *uflx, *dflx, *hr, *uflxc, *dflxc, *hrc, *duflx_dt, *duflxc_dt;
+};
+
+// Host-pointer calls: the column range is cut into passes of G.host_chunk columns that alternate between
+// two staging arenas; pass k+1 is copied in (stream s_in) while pass k computes (the caller's stream) and
+// pass k-1 is copied out (stream s_out), so the PCIe transfers of a large call overlap the kernels.
+// stage_in(sg, in, c0, nc) carves the device copies of one pass and enqueues their H2D copies.
+template <class StageIn>
+int host_pipeline(Mode mode, int ncol, int ld, int nlay, int icld, int idrv, int inflag, int iceflag, int liqflag,
+                  int permuteseed, int irng, size_t per_col, StageIn stage_in, const HostOut& ho, cudaStream_t st) {
+    int rc = ensure_pipeline();
+    if (rc) return rc;
+    int hc = G.host_chunk < G.chunk ? G.host_chunk : G.chunk;
+    const int chunk = hc < ncol ? hc : ncol;
+    const long P = ((chunk + 31) / 32) * 32;
+    const size_t half = per_col * P + 64;
+    rc = ensure_stage(2 * half);
+    if (rc) return rc;
+    const int saved_chunk = G.chunk;
+    int k = 0;
+    for (long c0 = 0; c0 < ncol; c0 += chunk, ++k) {
+        const int a = k & 1;
+        const int nc = (int)((ncol - c0) < chunk ? (ncol - c0) : chunk);
+        if (k >= 2) CK(cudaStreamWaitEvent(G.s_in, G.e_out[a], 0));  // arena a: outputs of pass k-2 have left
+        Stager sg{G.stage + (size_t)a * half, 0, P, G.s_in};
+        ColIn in{};
+        rc = stage_in(sg, in, c0, nc);
+        if (rc) return rc;
+        in.ld = P; in.nlay = nlay;
+        ColOut out{};
+        out.ld = P;
+        out.uflx = sg.carve((size_t)P * (nlay + 1)); out.dflx = sg.carve((size_t)P * (nlay + 1));
+        out.uflxc = sg.carve((size_t)P * (nlay + 1)); out.dflxc = sg.carve((size_t)P * (nlay + 1));
+        out.duflx_dt = sg.carve((size_t)P * (nlay + 1)); out.duflxc_dt = sg.carve((size_t)P * (nlay + 1));
+        out.hr = sg.carve((size_t)P * nlay); out.hrc = sg.carve((size_t)P * nlay);
+        CK(cudaEventRecord(G.e_in[a], G.s_in));
+        CK(cudaStreamWaitEvent(st, G.e_in[a], 0));
+        const long dbg_save = G.dbg_col;
+        if (G.dbg) G.dbg_col = dbg_save - c0;  // chunk-relative for the staged pass
+        G.chunk = chunk;
+        rc = run_device(mode, nc, nlay, icld, idrv, inflag, iceflag, liqflag, permuteseed, irng, in, out, st);
+        G.chunk = saved_chunk;
+        G.dbg_col = dbg_save;
+        if (rc) return rc;
+        CK(cudaEventRecord(G.e_done[a], st));
+        CK(cudaStreamWaitEvent(G.s_out, G.e_done[a], 0));
+        sg.st = G.s_out;
+        if (sg.out(ho.uflx, out.uflx, 1, ld, c0, nc, nlay + 1) || sg.out(ho.dflx, out.dflx, 1, ld, c0, nc, nlay + 1) ||
+            sg.out(ho.uflxc, out.uflxc, 1, ld, c0, nc, nlay + 1) || sg.out(ho.dflxc, out.dflxc, 1, ld, c0, nc, nlay + 1) ||
+            sg.out(ho.hr, out.hr, 1, ld, c0, nc, nlay) || sg.out(ho.hrc, out.hrc, 1, ld, c0, nc, nlay))
+            return RRTMG_LW_ERR_CUDA;
+        if (idrv == 1 && (sg.out(ho.duflx_dt, out.duflx_dt, 1, ld, c0, nc, nlay + 1) ||
+                          sg.out(ho.duflxc_dt, out.duflxc_dt, 1, ld, c0, nc, nlay + 1)))
+            return RRTMG_LW_ERR_CUDA;
+        CK(cudaEventRecord(G.e_out[a], G.s_out));
+    }
+    CK(cudaStreamSynchronize(G.s_out));
+    CK(cudaStreamSynchronize(st));
+    return decode_status(nullptr, nullptr);
+}
+
 bool check_common(int ncol, int ld, int nlay) { return ncol >= 1 && ld >= ncol && nlay >= 1 && nlay <= LW_MAXLAY; }
 
 }  // namespace
@@ -412,18 +489,10 @@ extern "C" int rrtmg_lw_b200_rrtmg_lw(int ncol, int ld, int nlay, int* icld, int
         ColOut out{uflx, dflx, hr, uflxc, dflxc, hrc, duflx_dt, duflxc_dt, ld};
         return run_device(MODE_STRICT, ncol, nlay, *icld, idrv, inflglw, iceflglw, liqflglw, 0, 0, in, out, st);
     }
-    // host pointers: stage chunk by chunk
-    const int chunk = G.chunk < ncol ? G.chunk : ncol;
-    const long P = ((chunk + 31) / 32) * 32;
+    // host pointers: staged, pipelined passes
     const size_t per_col = (size_t)12 * nlay + 2 * (nlay + 1) + 1 + 16 + 16 * (size_t)nlay +
                            (cloudy ? (size_t)4 * 140 * nlay + 2 * nlay : 0) + 6 * (size_t)(nlay + 1) + 2 * (size_t)nlay;
-    int rc = ensure_stage(per_col * P + 64);
-    if (rc) return rc;
-    const int saved_chunk = G.chunk;
-    for (long c0 = 0; c0 < ncol; c0 += chunk) {
-        const int nc = (int)((ncol - c0) < chunk ? (ncol - c0) : chunk);
-        Stager sg{G.stage, 0, P, st};
-        ColIn in{};
+    auto stage_in = [&](Stager& sg, ColIn& in, long c0, int nc) -> int {
         double* d;
 #define IN2(field, src, rows) if (sg.in(src, &d, 1, ld, c0, nc, rows)) return RRTMG_LW_ERR_CUDA; in.field = d;
         IN2(play, play, nlay) IN2(plev, plev, nlay + 1) IN2(tlay, tlay, nlay) IN2(tlev, tlev, nlay + 1) IN2(tsfc, tsfc, 1)
@@ -437,30 +506,10 @@ extern "C" int rrtmg_lw_b200_rrtmg_lw(int ncol, int ld, int nlay, int* icld, int
             IN2(reicmcl, reicmcl, nlay) IN2(relqmcl, relqmcl, nlay)
         }
 #undef IN2
-        in.ld = P; in.nlay = nlay;
-        ColOut out{};
-        out.ld = P;
-        out.uflx = sg.carve((size_t)P * (nlay + 1)); out.dflx = sg.carve((size_t)P * (nlay + 1));
-        out.uflxc = sg.carve((size_t)P * (nlay + 1)); out.dflxc = sg.carve((size_t)P * (nlay + 1));
-        out.duflx_dt = sg.carve((size_t)P * (nlay + 1)); out.duflxc_dt = sg.carve((size_t)P * (nlay + 1));
-        out.hr = sg.carve((size_t)P * nlay); out.hrc = sg.carve((size_t)P * nlay);
-        const long dbg_save = G.dbg_col;
-        if (G.dbg) G.dbg_col = dbg_save - c0;  // chunk-relative for the staged call
-        G.chunk = chunk;
-        rc = run_device(MODE_STRICT, nc, nlay, *icld, idrv, inflglw, iceflglw, liqflglw, 0, 0, in, out, st);
-        G.chunk = saved_chunk;
-        G.dbg_col = dbg_save;
-        if (rc) return rc;
-        if (sg.out(uflx, out.uflx, 1, ld, c0, nc, nlay + 1) || sg.out(dflx, out.dflx, 1, ld, c0, nc, nlay + 1) ||
-            sg.out(uflxc, out.uflxc, 1, ld, c0, nc, nlay + 1) || sg.out(dflxc, out.dflxc, 1, ld, c0, nc, nlay + 1) ||
-            sg.out(hr, out.hr, 1, ld, c0, nc, nlay) || sg.out(hrc, out.hrc, 1, ld, c0, nc, nlay))
-            return RRTMG_LW_ERR_CUDA;
-        if (idrv == 1 && (sg.out(duflx_dt, out.duflx_dt, 1, ld, c0, nc, nlay + 1) ||
-                          sg.out(duflxc_dt, out.duflxc_dt, 1, ld, c0, nc, nlay + 1)))
-            return RRTMG_LW_ERR_CUDA;
-        CK(cudaStreamSynchronize(st));
-    }
-    return decode_status(nullptr, nullptr);
+        return 0;
+    };
+    const HostOut ho{uflx, dflx, hr, uflxc, dflxc, hrc, duflx_dt, duflxc_dt};
+    return host_pipeline(MODE_STRICT, ncol, ld, nlay, *icld, idrv, inflglw, iceflglw, liqflglw, 0, 0, per_col, stage_in, ho, st);
 }
 
 extern "C" int rrtmg_lw_b200_rrtmg_lw_mcica(int ncol, int ld, int nlay, int icld_overlap, int idrv, int permuteseed,
@@ -501,17 +550,9 @@ extern "C" int rrtmg_lw_b200_rrtmg_lw_mcica(int ncol, int ld, int nlay, int icld
         return run_device(MODE_FUSED, ncol, nlay, icld_overlap, idrv, inflglw, iceflglw, liqflglw, permuteseed, irng, in,
                           out, st);
     }
-    const int chunk = G.chunk < ncol ? G.chunk : ncol;
-    const long P = ((chunk + 31) / 32) * 32;
     const size_t per_col = (size_t)12 * nlay + 2 * (nlay + 1) + 1 + 16 + 16 * (size_t)nlay +
                            (cloudy ? (size_t)6 * nlay + 16 * (size_t)nlay : 0) + 6 * (size_t)(nlay + 1) + 2 * (size_t)nlay;
-    int rc = ensure_stage(per_col * P + 64);
-    if (rc) return rc;
-    const int saved_chunk = G.chunk;
-    for (long c0 = 0; c0 < ncol; c0 += chunk) {
-        const int nc = (int)((ncol - c0) < chunk ? (ncol - c0) : chunk);
-        Stager sg{G.stage, 0, P, st};
-        ColIn in{};
+    auto stage_in = [&](Stager& sg, ColIn& in, long c0, int nc) -> int {
         double* d;
 #define IN2(field, src, rows) if (sg.in(src, &d, 1, ld, c0, nc, rows)) return RRTMG_LW_ERR_CUDA; in.field = d;
         IN2(play, play, nlay) IN2(plev, plev, nlay + 1) IN2(tlay, tlay, nlay) IN2(tlev, tlev, nlay + 1) IN2(tsfc, tsfc, 1)
@@ -525,30 +566,11 @@ extern "C" int rrtmg_lw_b200_rrtmg_lw_mcica(int ncol, int ld, int nlay, int icld
             in.tauc = d;
         }
 #undef IN2
-        in.ld = P; in.nlay = nlay;
-        ColOut out{};
-        out.ld = P;
-        out.uflx = sg.carve((size_t)P * (nlay + 1)); out.dflx = sg.carve((size_t)P * (nlay + 1));
-        out.uflxc = sg.carve((size_t)P * (nlay + 1)); out.dflxc = sg.carve((size_t)P * (nlay + 1));
-        out.duflx_dt = sg.carve((size_t)P * (nlay + 1)); out.duflxc_dt = sg.carve((size_t)P * (nlay + 1));
-        out.hr = sg.carve((size_t)P * nlay); out.hrc = sg.carve((size_t)P * nlay);
-        const long dbg_save = G.dbg_col;
-        if (G.dbg) G.dbg_col = dbg_save - c0;
-        G.chunk = chunk;
-        rc = run_device(MODE_FUSED, nc, nlay, icld_overlap, idrv, inflglw, iceflglw, liqflglw, permuteseed, irng, in, out, st);
-        G.chunk = saved_chunk;
-        G.dbg_col = dbg_save;
-        if (rc) return rc;
-        if (sg.out(uflx, out.uflx, 1, ld, c0, nc, nlay + 1) || sg.out(dflx, out.dflx, 1, ld, c0, nc, nlay + 1) ||
-            sg.out(uflxc, out.uflxc, 1, ld, c0, nc, nlay + 1) || sg.out(dflxc, out.dflxc, 1, ld, c0, nc, nlay + 1) ||
-            sg.out(hr, out.hr, 1, ld, c0, nc, nlay) || sg.out(hrc, out.hrc, 1, ld, c0, nc, nlay))
-            return RRTMG_LW_ERR_CUDA;
-        if (idrv == 1 && (sg.out(duflx_dt, out.duflx_dt, 1, ld, c0, nc, nlay + 1) ||
-                          sg.out(duflxc_dt, out.duflxc_dt, 1, ld, c0, nc, nlay + 1)))
-            return RRTMG_LW_ERR_CUDA;
-        CK(cudaStreamSynchronize(st));
-    }
-    return decode_status(nullptr, nullptr);
+        return 0;
+    };
+    const HostOut ho{uflx, dflx, hr, uflxc, dflxc, hrc, duflx_dt, duflxc_dt};
+    return host_pipeline(MODE_FUSED, ncol, ld, nlay, icld_overlap, idrv, inflglw, iceflglw, liqflglw, permuteseed, irng,
+                         per_col, stage_in, ho, st);
 }
 
 extern "C" int rrtmg_lw_b200_mcica_subcol_lw(int iplon, int ncol, int ld, int nlay, int icld, int permuteseed, int* irng,
@@ -731,6 +753,11 @@ extern "C" int rrtmg_lw_b200_set_option(const char* name, int value) {
         G.band_kernel = value;
         return RRTMG_LW_OK;
     }
+    if (std::strcmp(name, "host_chunk") == 0) {
+        if (value < 32) return RRTMG_LW_ERR_ARG;
+        G.host_chunk = value;
+        return RRTMG_LW_OK;
+    }
     return RRTMG_LW_ERR_ARG;
 }
 
@@ -788,5 +815,10 @@ extern "C" void rrtmg_lw_b200_finalize(void) {
     }
     if (G.d_gtab) cudaFree(G.d_gtab);
     G.d_gtab = nullptr;
+    if (G.s_in) {
+        cudaStreamDestroy(G.s_in); cudaStreamDestroy(G.s_out);
+        for (int k = 0; k < 2; ++k) { cudaEventDestroy(G.e_in[k]); cudaEventDestroy(G.e_done[k]); cudaEventDestroy(G.e_out[k]); }
+        G.s_in = G.s_out = nullptr;
+    }
     G.inited = false;
 }
