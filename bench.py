@@ -269,7 +269,9 @@ def main():
         bytes_per_col = (37 * NLAY + 19 + 6 * NLAY + 4) * 8.0   # API words in + out, SURVEY 8(d)
         cols_per_s_band = ncol / (ms_band * 1e-3)
         roof = {
-            "bound": "fp64", "kernel": "band_kernel<1..16,CLD_MASK,0> (16 launches per pass)",
+            "bound": "fp64",
+            "kernel": ("band_kernel<1..16,CLD_MASK,0>" if args.band_kernel == 2 else "gband_kernel<1..16,CLD_MASK>") +
+                      " (16 launches per pass of %d columns)" % args.chunk,
             "achieved": flops_per_col * cols_per_s_band / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
             "frac": flops_per_col * cols_per_s_band / 1e12 / fp64_peak,
             "peak_source": "DFMA microbenchmark run in this process (rrtmg_lw_b200_fp64_peak)",
@@ -279,11 +281,16 @@ def main():
                     "frac": bytes_per_col * cols_per_s_band / 1e9 / hbm_peak, "bytes_per_column": bytes_per_col,
                     "peak_source": hbm_src},
         }
+        # DRAM bytes of the same 16 launches from the committed ncu capture (profiles/traffic.json: bytes per
+        # column of dram__bytes_read.sum + dram__bytes_write.sum over bands 1..16), scaled to this step
         prof = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(prof):
             try:
-                roof["traffic"] = json.load(open(prof)).get("dram_bytes_per_step")
-            except (OSError, ValueError):
+                tj = json.load(open(prof))
+                if tj.get("band_kernel") == args.band_kernel:
+                    roof["traffic"] = tj["dram_bytes_per_column"] * ncol
+                    roof["traffic_note"] = tj.get("note")
+            except (OSError, ValueError, KeyError):
                 pass
         res = {
             "metric": "columns/sec", "value": value, "unit": "columns/s", "n_gpus": world, "steps": args.steps,
@@ -291,7 +298,7 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "columns_per_gpu": ncol, "layers": NLAY, "chunk_columns": args.chunk,
                        "entry": "rrtmg_lw_b200_rrtmg_lw_mcica (device pointers)", "l2": "inputs (>=20 GB) larger than L2",
-                       "fma": "off (-fmad=false)"},
+                       "fma": "off (-fmad=false)", "band_kernel": args.band_kernel},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof,
         }
 

@@ -139,6 +139,11 @@ int rrtmg_lw_b200_set_chunk(int max_columns);
  * pass of a host-pointer call (default 32768); passes alternate between two staging arenas so the
  * H2D copy of pass k+1 and the D2H copy of pass k-1 overlap the kernels of pass k. */
 int rrtmg_lw_b200_set_option(const char* name, int value);
+
+/* Host-only self test of the n-step jumps of the KISS generator used by the sub-column-parallel
+ * McICA kernel (src/mcica_subcol_gen_lw.f90:731-741 stepped n times == one jump); returns the number
+ * of mismatches (0 = ok).  Needs no CUDA device. */
+int rrtmg_lw_b200_kiss_jump_selftest(void);
 /* Number of kernels launched by this library since the last call with reset != 0. */
 long rrtmg_lw_b200_launch_count(int reset);
 /* CUDA-event time (ms) spent in the band kernels / all kernels of the last HOST- or DEVICE-mode

@@ -801,6 +801,8 @@ extern "C" int rrtmg_lw_b200_fp64_peak(double* tflops) {
     return measure_fp64_peak(tflops, 5) ? RRTMG_LW_ERR_CUDA : RRTMG_LW_OK;
 }
 
+extern "C" int rrtmg_lw_b200_kiss_jump_selftest(void) { return kiss_jump_selftest(); }
+
 extern "C" const char* rrtmg_lw_b200_version(void) { return "rrtmg_lw_b200 0.1 (sm_100a)"; }
 
 extern "C" void rrtmg_lw_b200_finalize(void) {

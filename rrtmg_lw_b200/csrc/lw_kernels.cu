@@ -405,6 +405,39 @@ struct KissJumpCache {
 } g_kj;
 }  // namespace
 
+// Host-only check of the jump algebra against plain stepping: returns the number of mismatching
+// generator states over a few (distance, seed) pairs (0 = all n-step jumps reproduce n single steps).
+int kiss_jump_selftest() {
+    const unsigned long long dist[] = {0ull, 1ull, 2ull, 71ull, 72ull, 144ull, 1000ull, 10079ull, 20161ull, 123457ull};
+    const unsigned seeds[][4] = {{123456789u, 362436069u, 521288629u, 916191069u}, {0u, 0u, 0u, 0u},
+                                 {999999999u, 1u, 65535u, 65536u}, {250000000u, 777777777u, 1179647998u, 2025259006u}};
+    int bad = 0;
+    for (unsigned long long n : dist) {
+        const KissMap m = kiss_power(n);
+        const KissMap m1 = kiss_power(n > 0 ? n - 1 : 0);
+        for (const auto& z : seeds) {
+            unsigned s1 = z[0], s2 = z[1], s3 = z[2], s4 = z[3];
+            for (unsigned long long k = 0; k < n; ++k) {
+                s1 = 69069u * s1 + 1327217885u;
+                s2 = xs_step(s2);
+                s3 = 18000u * (s3 & 65535u) + (s3 >> 16);
+                s4 = 30903u * (s4 & 65535u) + (s4 >> 16);
+            }
+            const unsigned j1 = m.a1 * z[0] + m.c1;
+            const unsigned j2 = m2_apply(m.m2, z[1]);
+            unsigned j3 = z[2], j4 = z[3];
+            if (n > 0) {
+                j3 = 18000u * (z[2] & 65535u) + (z[2] >> 16);
+                j4 = 30903u * (z[3] & 65535u) + (z[3] >> 16);
+                if (j3 != KISS_M3) j3 = (unsigned)((m1.p3 * j3) % KISS_M3);
+                if (j4 != KISS_M4) j4 = (unsigned)((m1.p4 * j4) % KISS_M4);
+            }
+            bad += (j1 != s1) + (j2 != s2) + (j3 != s3) + (j4 != s4);
+        }
+    }
+    return bad;
+}
+
 // fills (and caches) the device jump table for jumps permuteseed + isubcol * draws, isubcol = 0..139
 static const KissJump* kiss_jump_table(int permuteseed, long draws, cudaStream_t st) {
     if (!g_kj.dev) {

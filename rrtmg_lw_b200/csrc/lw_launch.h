@@ -22,6 +22,7 @@ void launch_get_alpha(int ncol, long ld, int nlay, int icld, int idcor, double d
 void launch_materialize(const ColIn&, const Scratch&, const RunCfg&, double* cldfmcl, double* ciwpmcl, double* clwpmcl,
                         double* reicmcl, double* relqmcl, double* taucmcl, cudaStream_t);
 int measure_fp64_peak(double* tflops, int reps);
+int kiss_jump_selftest();
 cudaError_t upload_constants_kernels(const ConstTab&, const DevPtrs&, const double (*refrat)[5]);
 
 // band kernels: each TU handles a subset of bands; returns false when the band is not its own

@@ -99,3 +99,10 @@ def test_product_does_not_reference_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")) or f == "Makefile":
                 t = open(os.path.join(dp, f)).read()
                 assert "oracle" not in t.lower().replace("oracle/_ref", ""), os.path.join(dp, f)
+
+
+def test_kiss_jump_ahead_matches_stepping():
+    """The closed-form n-step jumps behind the sub-column-parallel KISS kernel equal n single steps of
+    kissvec (src/mcica_subcol_gen_lw.f90:731-741) for all four component generators (host-only check)."""
+    from rrtmg_lw_b200 import api
+    assert api.lib().rrtmg_lw_b200_kiss_jump_selftest() == 0
