@@ -200,6 +200,9 @@ def main():
     torch.cuda.set_device(local)
     dev = "cuda:%d" % local
     if world > 1:
+        # keep stdout to the one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION) goes to stdout
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device(dev))
     blob = kdata.synthetic_blob()
     api.rrtmg_lw_ini(1004.0, blob, 4)
