@@ -150,6 +150,8 @@ long rrtmg_lw_b200_launch_count(int reset);
  * call when timing capture is enabled with rrtmg_lw_b200_set_timing(1). */
 int rrtmg_lw_b200_set_timing(int enable);
 int rrtmg_lw_b200_last_timing(float* ms_band_kernels, float* ms_all_kernels);
+/* Same capture, per band: ms16[b-1] = CUDA-event time of band b's kernel summed over the passes. */
+int rrtmg_lw_b200_last_band_timing(float* ms16);
 
 /* Measured FP64 FMA throughput of the current device in TFLOP/s (an FMA = 2 flops); the FP64
  * roofline denominator used by bench.py. */

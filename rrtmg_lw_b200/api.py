@@ -204,6 +204,13 @@ def last_timing():
     return a.value, b.value
 
 
+def last_band_timing():
+    """CUDA-event milliseconds of each band's kernel in the last call made with timing enabled."""
+    a = (C.c_float * 16)()
+    lib().rrtmg_lw_b200_last_band_timing(a)
+    return [float(x) for x in a]
+
+
 def debug_capture(col):
     """Capture the stage dump of global column ``col`` (0-based) on the next call; None disables."""
     lib().rrtmg_lw_b200_debug_capture(0 if col is None else int(col) + 1)

@@ -24,6 +24,7 @@ struct Ctx {
     bool inited = false;
     HostTables H;
     double* d_arena = nullptr;
+    double* d_arena_p = nullptr;
     GTab* d_gtab = nullptr;
     double *d_totplnk = nullptr, *d_totplnkderiv = nullptr, *d_exptfn = nullptr, *d_tau = nullptr;
     double *d_absice2 = nullptr, *d_absice3 = nullptr, *d_absliq1 = nullptr;
@@ -47,7 +48,9 @@ struct Ctx {
     int dbg_nlay = 0;
     bool timing = false;
     float ms_band = 0.f, ms_all = 0.f;
+    float ms_bands[NBND] = {};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t evb[NBND + 1] = {};
     std::mutex mu;
 };
 Ctx G;
@@ -177,8 +180,11 @@ int run_device(Mode mode, int ncol, int nlay, int icld, int idrv, int inflag, in
     if (G.timing) {
         for (auto& e : G.ev)
             if (!e) CK(cudaEventCreate(&e));
+        for (auto& e : G.evb)
+            if (!e) CK(cudaEventCreate(&e));
         G.ms_band = 0.f;
         G.ms_all = 0.f;
+        for (auto& m : G.ms_bands) m = 0.f;
     }
     for (long c0 = 0; c0 < ncol; c0 += chunk) {
         RunCfg r{};
@@ -204,9 +210,11 @@ int run_device(Mode mode, int ncol, int nlay, int icld, int idrv, int inflag, in
             }
         } else {
             for (int b = 1; b <= NBND; ++b) {
+                if (G.timing) CK(cudaEventRecord(G.evb[b - 1], st));
                 if (!launch_band(b, cld, idrv, in, out, S, r, st)) return RRTMG_LW_ERR_ARG;
                 G.launches++;
             }
+            if (G.timing) CK(cudaEventRecord(G.evb[NBND], st));
         }
         if (G.timing) CK(cudaEventRecord(G.ev[2], st));
         if (G.band_kernel == 3) launch_finalizeT(in, out, S, r, cld != CLD_NONE, st);
@@ -220,6 +228,12 @@ int run_device(Mode mode, int ncol, int nlay, int icld, int idrv, int inflag, in
             CK(cudaEventElapsedTime(&b, G.ev[0], G.ev[3]));
             G.ms_band += a;
             G.ms_all += b;
+            if (G.band_kernel != 3)
+                for (int k = 0; k < NBND; ++k) {
+                    float m = 0.f;
+                    CK(cudaEventElapsedTime(&m, G.evb[k], G.evb[k + 1]));
+                    G.ms_bands[k] += m;
+                }
         }
         CK(cudaGetLastError());
     }
@@ -384,6 +398,7 @@ extern "C" int rrtmg_lw_b200_ini(double cpdair, const double* kdata, long nkdata
         return 0;
     };
     if (up(&G.d_arena, H.arena)) return RRTMG_LW_ERR_CUDA;
+    if (up(&G.d_arena_p, H.arena_p)) return RRTMG_LW_ERR_CUDA;
     if (up(&G.d_totplnk, H.totplnk)) return RRTMG_LW_ERR_CUDA;
     if (up(&G.d_totplnkderiv, H.totplnkderiv)) return RRTMG_LW_ERR_CUDA;
     if (up(&G.d_tau, H.tau_tbl)) return RRTMG_LW_ERR_CUDA;
@@ -429,6 +444,13 @@ extern "C" int rrtmg_lw_b200_ini(double cpdair, const double* kdata, long nkdata
         T.ka = P(0); T.kb = P(1); T.selfref = P(2); T.forref = P(3); T.fracrefa = P(4); T.fracrefb = P(5);
         for (int m = 0; m < 5; ++m) T.m[m] = P(6 + m);
         T.v[0] = P(11); T.v[1] = P(12);
+        auto Q = [&](int slot) -> const double* {
+            return H.offp[b][slot] == (size_t)-1 ? nullptr : G.d_arena_p + H.offp[b][slot];
+        };
+        BandTab& U = H.ct.bandp[b];
+        U.ka = Q(0); U.kb = Q(1); U.selfref = Q(2); U.forref = Q(3); U.fracrefa = Q(4); U.fracrefb = Q(5);
+        for (int m = 0; m < 5; ++m) U.m[m] = Q(6 + m);
+        U.v[0] = Q(11); U.v[1] = Q(12);
     }
     DevPtrs dp;
     dp.g = G.d_gtab; dp.totplnk = G.d_totplnk; dp.totplnkderiv = G.d_totplnkderiv;
@@ -781,6 +803,13 @@ extern "C" int rrtmg_lw_b200_last_timing(float* ms_band, float* ms_all) {
     return RRTMG_LW_OK;
 }
 
+extern "C" int rrtmg_lw_b200_last_band_timing(float* ms16) {
+    std::lock_guard<std::mutex> lk(G.mu);
+    if (!ms16) return RRTMG_LW_ERR_ARG;
+    for (int k = 0; k < NBND; ++k) ms16[k] = G.ms_bands[k];
+    return RRTMG_LW_OK;
+}
+
 extern "C" const char* rrtmg_lw_b200_strerror(int code) {
     switch (code) {
         case RRTMG_LW_OK: return "ok";
@@ -810,7 +839,7 @@ extern "C" void rrtmg_lw_b200_finalize(void) {
     free_scratch();
     if (G.stage) cudaFree(G.stage);
     G.stage = nullptr; G.stage_doubles = 0;
-    for (double** p : {&G.d_arena, &G.d_totplnk, &G.d_totplnkderiv, &G.d_exptfn, &G.d_tau, &G.d_absice2, &G.d_absice3,
+    for (double** p : {&G.d_arena, &G.d_arena_p, &G.d_totplnk, &G.d_totplnkderiv, &G.d_exptfn, &G.d_tau, &G.d_absice2, &G.d_absice3,
                        &G.d_absliq1}) {
         if (*p) cudaFree(*p);
         *p = nullptr;

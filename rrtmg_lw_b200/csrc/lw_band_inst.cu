@@ -1,5 +1,7 @@
 // lw_band_inst.cu -- instantiations of the band kernel; compiled once per -DLW_TU=n so the 16
 // bands x cloud modes x idrv variants build in parallel.
+#include <cstdlib>
+
 #include "lw_band.cuh"
 #include "lw_launch.h"
 
@@ -31,7 +33,9 @@ static void launch_b(int cld, int idrv, const ColIn& in, const ColOut& out, cons
                      cudaStream_t st) {
     const int threads = BAND_THREADS;
     const int blocks = (r.ncol + threads - 1) / threads;
-    const size_t smem = Ring<B>::BYTES;
+    // RRTMG_LW_SMEM_PAD (bytes, dev experiments): extra dynamic shared memory per CTA, i.e. fewer resident CTAs
+    static const size_t pad = std::getenv("RRTMG_LW_SMEM_PAD") ? (size_t)std::atol(std::getenv("RRTMG_LW_SMEM_PAD")) : 0;
+    const size_t smem = Ring<B>::BYTES + pad;
 #define LW_GO(CLD, IDRV)                                                                                  \
     do {                                                                                                  \
         static bool attr_set = false;                                                                     \

@@ -131,8 +131,9 @@ void build_host_tables(double cpdair, const double* st, const double* kdata, int
 
     // ---- reduce every table 16 -> NG and lay it out g-fastest in one arena
     for (int b = 0; b < NBND; ++b)
-        for (int s = 0; s < 13; ++s) H.off[b][s] = std::numeric_limits<size_t>::max();
+        for (int s = 0; s < 13; ++s) H.off[b][s] = H.offp[b][s] = std::numeric_limits<size_t>::max();
     H.arena.clear();
+    H.arena_p.clear();
     H.named.clear();
     int nminor[NBND] = {0}, nvec[NBND] = {0};
     const double* src = kdata;
@@ -143,6 +144,10 @@ void build_host_tables(double cpdair, const double* st, const double* kdata, int
         if (H.arena.size() & 1) H.arena.push_back(0.0);
         const size_t base = H.arena.size();
         H.arena.resize(base + (size_t)lead * ng, 0.0);
+        const int ngp = NGPAD[b];
+        while (H.arena_p.size() & 15) H.arena_p.push_back(0.0);  // every table starts a 128-byte line
+        const size_t basep = H.arena_p.size();
+        H.arena_p.resize(basep + (size_t)lead * ngp, 0.0);
         std::vector<double> ref((size_t)lead * ng, 0.0);  // reference element order, for get_table
         for (int i = 0; i < lead; ++i) {
             int g16 = 0;
@@ -153,6 +158,7 @@ void build_host_tables(double cpdair, const double* st, const double* kdata, int
                     acc = d.weighted ? acc + x * H.rwgt[b * 16 + g16] : acc + x;
                 }
                 H.arena[base + (size_t)i * ng + ig] = acc;
+                H.arena_p[basep + (size_t)i * ngp + ig] = acc;
                 if (d.gfirst) ref[ig + (size_t)ng * i] = acc; else ref[i + (size_t)lead * ig] = acc;
             }
         }
@@ -168,9 +174,11 @@ void build_host_tables(double cpdair, const double* st, const double* kdata, int
         else if (nm.find("_m") != std::string::npos) slot = 6 + nminor[b]++;
         else slot = 11 + nvec[b]++;
         H.off[b][slot] = base;
+        H.offp[b][slot] = basep;
         H.named.emplace_back(std::to_string(d.band) + ":" + reduced_name(nm), std::move(ref));
     }
     if (H.arena.size() & 1) H.arena.push_back(0.0);
+    while (H.arena_p.size() & 3) H.arena_p.push_back(0.0);
 }
 
 }  // namespace lw

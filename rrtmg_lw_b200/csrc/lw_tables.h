@@ -19,6 +19,9 @@ constexpr int NTBL = 10000;
 // g-points per band / first g-point (0-based) of each band: ngc, ngs of src/rrtmg_lw_init.f90:325-326
 constexpr int NGC[NBND] = {10, 12, 16, 14, 16, 8, 12, 8, 12, 6, 8, 8, 4, 2, 2, 2};
 constexpr int GOFF[NBND] = {0, 10, 22, 38, 52, 68, 76, 88, 96, 108, 114, 122, 130, 134, 136, 138};
+// row stride of the band kernel's copy of the k-tables: NG rounded up to 4 g-points, so that a row
+// is a whole number of 32-byte sectors and four g-points are one aligned 256-bit load (the pad is 0)
+constexpr int NGPAD[NBND] = {12, 12, 16, 16, 16, 8, 12, 8, 12, 8, 8, 8, 4, 4, 4, 4};
 constexpr int NSPA[NBND] = {1, 1, 9, 9, 9, 1, 9, 1, 9, 1, 1, 9, 9, 1, 9, 9};
 constexpr int NSPB[NBND] = {1, 1, 5, 5, 5, 0, 1, 1, 1, 1, 1, 0, 0, 1, 0, 0};
 
@@ -43,7 +46,8 @@ struct BandTab {
 
 // Scalars and small tables that live in __constant__ memory.
 struct ConstTab {
-    BandTab band[NBND];
+    BandTab band[NBND];    // rows of NG doubles (g-lane kernel)
+    BandTab bandp[NBND];   // rows of NGPAD doubles, 32-byte aligned (column-lane kernel)
     double delwave[NBND];
     double a0[NBND], a1[NBND], a2[NBND];  // diffusivity-angle fit, src/rrtmg_lw_rtrnmc.f90:258-269
     double pref[59], preflog[59], tref[59];
@@ -75,6 +79,8 @@ struct HostTables {
     ConstTab ct;                       // band pointers filled after upload
     std::vector<double> arena;         // device-layout k tables
     size_t off[NBND][13];              // arena offsets: ka,kb,self,for,fra,frb,m0..m4,v0,v1 (SIZE_MAX = absent)
+    std::vector<double> arena_p;       // same tables with rows padded to NGPAD, every table start 32-byte aligned
+    size_t offp[NBND][13];
     std::vector<double> totplnk, totplnkderiv;  // (181,16) reference order
     std::vector<double> exp_tbl, tfn_tbl, tau_tbl;
     std::vector<double> absice2, absice3, absliq1;
