@@ -83,7 +83,12 @@ int rrtmg_lw_b200_rrtmg_lw(int ncol, int ld, int nlay, int* icld, int idrv,
                            int memspace, void* stream);
 
 /* Replaces mcica_subcol_lw (src/mcica_subcol_gen_lw.f90:183-291); irng is inout (:442).
- * iplon is accepted and ignored, as in the reference.  icld in [0,5]; alpha read for icld 4/5. */
+ * iplon is accepted and ignored, as in the reference.  icld in [0,5]; alpha read for icld 4/5.
+ * irng = 0: KISS, one stream per column seeded from the column's four lowest pressures (needs nlay >= 4).
+ * irng = 1: Mersenne Twister (src/mcica_random_numbers.f90), ONE stream per call in the order
+ *           (sub-column, column, layer) seeded with permuteseed -- reproduced exactly, including for calls
+ *           that the library processes in several column passes; a compatibility path (one CTA advances
+ *           the generator), use irng = 0 for throughput. */
 int rrtmg_lw_b200_mcica_subcol_lw(int iplon, int ncol, int ld, int nlay, int icld, int permuteseed, int* irng,
                                   const double* play, const double* cldfrac, const double* ciwp,
                                   const double* clwp, const double* rei, const double* rel, const double* tauc,

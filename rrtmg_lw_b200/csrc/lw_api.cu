@@ -47,6 +47,8 @@ struct Ctx {
     long dbg_col = -1;  // requested by debug_capture: always column given at debug_stages time? (we capture col 0..)
     int dbg_nlay = 0;
     bool timing = false;
+    // Mersenne-Twister stream bookkeeping of a staged host call: columns of the whole call / first column of the pass
+    long mt_total = 0, mt_base = 0;
     float ms_band = 0.f, ms_all = 0.f;
     float ms_bands[NBND] = {};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -172,7 +174,6 @@ int run_device(Mode mode, int ncol, int nlay, int icld, int idrv, int inflag, in
                int irng, ColIn in, ColOut out, cudaStream_t st) {
     if (nlay < 4 && mode == MODE_FUSED && icld > 0 && irng == 0) return RRTMG_LW_ERR_ARG;  // KISS seeds need 4 layers
     if (nlay < 1 || nlay > LW_MAXLAY) return RRTMG_LW_ERR_ARG;
-    if (mode == MODE_FUSED && icld > 0 && irng != 0) return RRTMG_LW_ERR_ARG;  // MT stream: see mcica_subcol_lw
     const int chunk = G.chunk;
     int rc = ensure_scratch(ncol < chunk ? ncol : chunk, nlay);
     if (rc) return rc;
@@ -199,7 +200,16 @@ int run_device(Mode mode, int ncol, int nlay, int icld, int idrv, int inflag, in
         if (S.dbg_col >= 0) G.dbg_nlay = nlay;
         if (G.timing) CK(cudaEventRecord(G.ev[0], st));
         launch_prep(in, S, r, st); G.launches++;
-        if (cld == CLD_MASK) { launch_mcica_kiss(in, S, r, st); G.launches++; }
+        if (cld == CLD_MASK) {
+            if (irng == 0) {
+                launch_mcica_kiss(in, S, r, st); G.launches++;
+            } else {
+                // one global stream over (sub-column, column, layer): position of this chunk inside the whole call
+                const int nl = launch_mcica_mt(in, S, r, G.mt_total ? G.mt_total : ncol, G.mt_base + c0, st);
+                if (nl < 0) return RRTMG_LW_ERR_CUDA;
+                G.launches += nl;
+            }
+        }
         if (cld == CLD_ARRAYS) { launch_cldflags(in, S, r, st); G.launches += 2; }
         if (G.band_kernel == 3) { launch_transposes(S, r, cld != CLD_NONE, st); G.launches += cld != CLD_NONE ? 3 : 2; }
         if (G.timing) CK(cudaEventRecord(G.ev[1], st));
@@ -315,7 +325,9 @@ int host_pipeline(Mode mode, int ncol, int ld, int nlay, int icld, int idrv, int
         const long dbg_save = G.dbg_col;
         if (G.dbg) G.dbg_col = dbg_save - c0;  // chunk-relative for the staged pass
         G.chunk = chunk;
+        G.mt_total = ncol; G.mt_base = c0;
         rc = run_device(mode, nc, nlay, icld, idrv, inflag, iceflag, liqflag, permuteseed, irng, in, out, st);
+        G.mt_total = 0; G.mt_base = 0;
         G.chunk = saved_chunk;
         G.dbg_col = dbg_save;
         if (rc) return rc;
@@ -606,13 +618,12 @@ extern "C" int rrtmg_lw_b200_mcica_subcol_lw(int iplon, int ncol, int ld, int nl
     if (!G.inited) return RRTMG_LW_ERR_NOT_INIT;
     if (icld == 0) return RRTMG_LW_OK;  // mcica:257
     if (icld < 0 || icld > 5) return RRTMG_LW_ERR_FLAG;
-    if (!irng || !check_common(ncol, ld, nlay) || nlay < 4) return RRTMG_LW_ERR_ARG;
+    if (!irng || !check_common(ncol, ld, nlay) || (nlay < 4 && *irng == 0)) return RRTMG_LW_ERR_ARG;
     if (!play || !cldfrac || !ciwp || !clwp || !rei || !rel || !tauc || !cldfmcl || !ciwpmcl || !clwpmcl || !reicmcl ||
         !relqmcl || !taucmcl)
         return RRTMG_LW_ERR_ARG;
     if (icld >= 4 && !alpha) return RRTMG_LW_ERR_ARG;
     if (*irng != 0) *irng = 1;
-    if (*irng == 1) return RRTMG_LW_ERR_ARG;  // Mersenne-Twister stream: not built yet
     cudaStream_t st = (cudaStream_t)stream;
     const int chunk = G.chunk < ncol ? G.chunk : ncol;
     int rc = ensure_scratch(chunk, nlay);
@@ -625,16 +636,23 @@ extern "C" int rrtmg_lw_b200_mcica_subcol_lw(int iplon, int ncol, int ld, int nl
     for (long c0 = 0; c0 < ncol; c0 += chunk) {
         RunCfg r{};
         r.ncol = (int)((ncol - c0) < chunk ? (ncol - c0) : chunk);
-        r.nlay = nlay; r.icld = icld; r.irng = 0; r.permuteseed = permuteseed;
+        r.nlay = nlay; r.icld = icld; r.irng = *irng; r.permuteseed = permuteseed;
         ColIn in{};
         in.nlay = nlay;
+        auto generate = [&]() -> int {
+            if (*irng == 0) { launch_mcica_kiss(in, G.S, r, st); G.launches++; return 0; }
+            const int nl = launch_mcica_mt(in, G.S, r, ncol, c0, st);
+            if (nl < 0) return RRTMG_LW_ERR_CUDA;
+            G.launches += nl;
+            return 0;
+        };
         if (memspace == RRTMG_LW_DEVICE) {
             r.c0 = c0;
             in.play = play; in.cldfrac = cldfrac; in.ciwp = ciwp; in.clwp = clwp; in.rei = rei; in.rel = rel;
             in.tauc = tauc; in.alpha = alpha; in.ld = ld;
-            launch_mcica_kiss(in, G.S, r, st);
+            if (generate()) return RRTMG_LW_ERR_CUDA;
             launch_materialize(in, G.S, r, cldfmcl, ciwpmcl, clwpmcl, reicmcl, relqmcl, taucmcl, st);
-            G.launches += 2;
+            G.launches++;
         } else {
             r.c0 = 0;
             Stager sg{G.stage, 0, P, st};
@@ -649,9 +667,9 @@ extern "C" int rrtmg_lw_b200_mcica_subcol_lw(int iplon, int ncol, int ld, int nl
             double* o_cld = sg.carve((size_t)140 * P * nlay); double* o_ciwp = sg.carve((size_t)140 * P * nlay);
             double* o_clwp = sg.carve((size_t)140 * P * nlay); double* o_tauc = sg.carve((size_t)140 * P * nlay);
             double* o_rei = sg.carve((size_t)P * nlay); double* o_rel = sg.carve((size_t)P * nlay);
-            launch_mcica_kiss(in, G.S, r, st);
+            if (generate()) return RRTMG_LW_ERR_CUDA;
             launch_materialize(in, G.S, r, o_cld, o_ciwp, o_clwp, o_rei, o_rel, o_tauc, st);
-            G.launches += 2;
+            G.launches++;
             if (sg.out(cldfmcl, o_cld, 140, ld, c0, r.ncol, nlay) || sg.out(ciwpmcl, o_ciwp, 140, ld, c0, r.ncol, nlay) ||
                 sg.out(clwpmcl, o_clwp, 140, ld, c0, r.ncol, nlay) || sg.out(taucmcl, o_tauc, 140, ld, c0, r.ncol, nlay) ||
                 sg.out(reicmcl, o_rei, 1, ld, c0, r.ncol, nlay) || sg.out(relqmcl, o_rel, 1, ld, c0, r.ncol, nlay))
@@ -837,6 +855,7 @@ extern "C" const char* rrtmg_lw_b200_version(void) { return "rrtmg_lw_b200 0.1 (
 extern "C" void rrtmg_lw_b200_finalize(void) {
     std::lock_guard<std::mutex> lk(G.mu);
     free_scratch();
+    free_mt_buffers();
     if (G.stage) cudaFree(G.stage);
     G.stage = nullptr; G.stage_doubles = 0;
     for (double** p : {&G.d_arena, &G.d_arena_p, &G.d_totplnk, &G.d_totplnkderiv, &G.d_exptfn, &G.d_tau, &G.d_absice2, &G.d_absice3,

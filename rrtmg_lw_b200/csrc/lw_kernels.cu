@@ -18,6 +18,8 @@ __device__ __forceinline__ void raise(const Scratch& s, int code, long col, int 
     atomicCAS(s.status, 0ull, v);
 }
 
+static inline int nblk(long n, int b) { return (int)((n + b - 1) / b); }
+
 // ---------------------------------------------------------------------------------------------
 // inatm (src/rrtmg_lw_rad.f90:755-870) + setcoef (src/rrtmg_lw_setcoef.f90:271-432) for one column
 // per thread.  The two whole-column sums (amttl, wvttl -> pwvcm) run in layer order, as in the
@@ -151,6 +153,43 @@ struct Kiss {
     }
 };
 
+// per-layer cloud flag (icldlyr, bit 31 of mask word 4), column cloud top, and the validation of the cloud-optics
+// inputs the way cldprmc would STOP (cldprmc.f90:191-253), for column i whose 140 mask bits per layer are in place
+__device__ void finish_column(const ColIn& in, const Scratch& s, const RunCfg& r, int i) {
+    const long ci = r.c0 + i;
+    const int nlay = r.nlay;
+    const long P = s.pitch;
+    const double cldmin = 1.0e-20;
+    int ctop = 0;
+    for (int l = 0; l < nlay; ++l) {
+        unsigned any = 0;
+        for (int w = 0; w < 5; ++w) any |= s.mask[((long)l * 5 + w) * P + i];
+        if (any) {
+            s.mask[((long)l * 5 + 4) * P + i] |= 0x80000000u;
+            ctop = l + 1;
+            const long a = ci + in.ld * l;
+            const double ciwp = in.ciwp[a], clwp = in.clwp[a];
+            bool taubig = false;
+            if (in.tauc) for (int b = 0; b < 16; ++b) taubig |= in.tauc[b + 16 * a] >= cldmin;
+            if ((ciwp + clwp) >= cldmin || taubig) {
+                if (r.inflag == 1) raise(s, 1, ci, l + 1);
+                if (r.inflag == 2) {
+                    if (ciwp != 0.0) {
+                        const double rad = in.rei[a];
+                        if ((r.iceflag == 0 && rad < 10.0) || (r.iceflag == 1 && (rad < 13.0 || rad > 130.)) ||
+                            (r.iceflag == 2 && (rad < 5.0 || rad > 131.0)) || (r.iceflag == 3 && (rad < 5.0 || rad > 140.0)))
+                            raise(s, 2, ci, l + 1);
+                    }
+                    if (clwp != 0.0 && r.liqflag == 1) {
+                        const double rad = in.rel[a];
+                        if (rad < 2.5 || rad > 60.) raise(s, 3, ci, l + 1);
+                    }
+                }
+            }
+        }
+    }
+    s.ctop[i] = ctop;}
+
 // One thread = one column: draws its 140 x nlay (or 2 x that) numbers in the reference's order
 // (sub-column outer, layer inner), applies the overlap recurrence on the fly and packs the cloud
 // mask as 140 bits per layer.  generate_stochastic_clouds, mcica:442-679; icld 4/5 per the column
@@ -206,36 +245,164 @@ __global__ void __launch_bounds__(128) mcica_kiss_kernel(ColIn in, Scratch s, Ru
         if ((sc & 31) == 31 || sc == NGPT - 1)
             for (int l = 0; l < nlay; ++l) s.mask[((long)l * 5 + (sc >> 5)) * P + i] = mloc[l];
     }
-    // per-layer cloud flag (icldlyr), column cloud top, and cldprmc input validation
-    int ctop = 0;
-    for (int l = 0; l < nlay; ++l) {
-        unsigned any = 0;
-        for (int w = 0; w < 5; ++w) any |= s.mask[((long)l * 5 + w) * P + i];
-        if (any) {
-            s.mask[((long)l * 5 + 4) * P + i] |= 0x80000000u;
-            ctop = l + 1;
-            const long a = ci + in.ld * l;
-            const double ciwp = in.ciwp[a], clwp = in.clwp[a];
-            bool taubig = false;
-            if (in.tauc) for (int b = 0; b < 16; ++b) taubig |= in.tauc[b + 16 * a] >= cldmin;
-            if ((ciwp + clwp) >= cldmin || taubig) {
-                if (r.inflag == 1) raise(s, 1, ci, l + 1);
-                if (r.inflag == 2) {
-                    if (ciwp != 0.0) {
-                        const double rad = in.rei[a];
-                        if ((r.iceflag == 0 && rad < 10.0) || (r.iceflag == 1 && (rad < 13.0 || rad > 130.)) ||
-                            (r.iceflag == 2 && (rad < 5.0 || rad > 131.0)) || (r.iceflag == 3 && (rad < 5.0 || rad > 140.0)))
-                            raise(s, 2, ci, l + 1);
-                    }
-                    if (clwp != 0.0 && r.liqflag == 1) {
-                        const double rad = in.rel[a];
-                        if (rad < 2.5 || rad > 60.) raise(s, 3, ci, l + 1);
-                    }
-                }
+    finish_column(in, s, r, i);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Mersenne-Twister path (irng = 1).  The reference draws ONE global stream in the order
+// (sub-column, column, layer) [two draws per point for icld 4/5, one per (sub-column, column) for icld 3]
+// from new_RandomNumberSequence(seed = permuteseed) (mcica:478, 523-530, 586-595; MT19937 itself
+// src/mcica_random_numbers.f90:116-185).  Here one CTA regenerates the 624-word state in three
+// data-parallel phases and emits the tempered words of one sub-column's run of a column chunk at a time
+// (the words between two runs of a chunk are stepped over, not stored); a column-parallel kernel then
+// applies the overlap recurrence and sets that sub-column's bit in the packed cloud mask.  This is the
+// reference-faithful compatibility path, not a throughput path.
+struct MtState {
+    unsigned mt[624];
+    int cur;
+};
+__global__ void mt_seed_kernel(MtState* st, unsigned seed) {  // initialize_scalar, random_numbers:169-185
+    unsigned x = seed;
+    st->mt[0] = x;
+    for (int i = 1; i < 624; ++i) { x = 1812433253u * (x ^ (x >> 30)) + (unsigned)i; st->mt[i] = x; }
+    st->cur = 624;
+}
+__device__ __forceinline__ unsigned mt_twist(unsigned u, unsigned v) {
+    const unsigned mix = (u & 0x80000000u) | (v & 0x7fffffffu);
+    return (mix >> 1) ^ ((v & 1u) ? 0x9908b0dfu : 0u);
+}
+__global__ void __launch_bounds__(256) mt_fill_kernel(MtState* st, unsigned* __restrict__ out, long skip, long emit) {
+    __shared__ unsigned mt[624];
+    const int t = threadIdx.x;
+    for (int k = t; k < 624; k += 256) mt[k] = st->mt[k];
+    int cur = st->cur;
+    __syncthreads();
+    long pos = -skip;  // index of the next word relative to out[0]
+    while (pos < emit) {
+        if (cur >= 624) {  // nextState, random_numbers:134-152
+            unsigned v = 0;
+            if (t < 227) v = mt[t + 397] ^ mt_twist(mt[t], mt[t + 1]);
+            __syncthreads();
+            if (t < 227) mt[t] = v;
+            __syncthreads();
+            if (t < 227) v = mt[t] ^ mt_twist(mt[t + 227], mt[t + 228]);
+            __syncthreads();
+            if (t < 227) mt[t + 227] = v;
+            __syncthreads();
+            if (t < 169) v = mt[t + 227] ^ mt_twist(mt[t + 454], mt[t + 455]);
+            __syncthreads();
+            if (t < 169) mt[t + 454] = v;
+            __syncthreads();
+            if (t == 0) mt[623] = mt[396] ^ mt_twist(mt[623], mt[0]);
+            __syncthreads();
+            cur = 0;
+        }
+        const long left = emit - pos;
+        const int n = (624 - cur) < left ? (624 - cur) : (int)left;
+        for (int k = t; k < n; k += 256) {
+            const long o = pos + k;
+            if (o >= 0) {  // temper, random_numbers:154-165
+                unsigned y = mt[cur + k];
+                y ^= y >> 11;
+                y ^= (y << 7) & 0x9d2c5680u;
+                y ^= (y << 15) & 0xefc60000u;
+                out[o] = y ^ (y >> 18);
             }
         }
+        pos += n;
+        cur += n;
+        __syncthreads();
     }
-    s.ctop[i] = ctop;
+    for (int k = t; k < 624; k += 256) st->mt[k] = mt[k];
+    if (t == 0) st->cur = cur;
+}
+// getRandomReal, random_numbers:276-295: for a negative INT32 the sum localInt + 2.0**32 is evaluated in the
+// default real kind (float under plain gfortran), then divided by the kind-rb 2**32 - 1
+__device__ __forceinline__ double mt_real(unsigned w) {
+    const int li = (int)w;
+    const double denom = 4294967296.0 - 1.0;
+    if (li < 0) {
+        if (C.drk == 4) return (double)((float)li + 4294967296.0f) / denom;
+        return ((double)li + 4294967296.0) / denom;
+    }
+    return (double)li / denom;
+}
+// one thread = one column of the chunk, sub-column sc: its draws are buf[(i * nlay + l) * d (+1)]
+__global__ void __launch_bounds__(128) mcica_mt_apply_kernel(ColIn in, Scratch s, RunCfg r, const unsigned* __restrict__ buf, int sc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= r.ncol) return;
+    const long ci = r.c0 + i;
+    const int nlay = r.nlay, icld = r.icld;
+    const long P = s.pitch;
+    const double cldmin = 1.0e-20;
+    const unsigned bit = 1u << (sc & 31);
+    const bool fresh = (sc & 31) == 0;
+    const int d = icld >= 4 ? 2 : 1;
+    const unsigned* q = icld == 3 ? buf + i : buf + (long)i * nlay * d;
+    double prev = 0., cfm = 0.;
+    const double rmax = icld == 3 ? mt_real(q[0]) : 0.;
+    for (int l = 0; l < nlay; ++l) {
+        double cf = in.cldfrac[ci + in.ld * l];
+        if (cf < cldmin) cf = 0.;
+        double x;
+        if (icld == 3) {
+            x = rmax;
+        } else {
+            x = mt_real(q[l * d]);
+            if (icld >= 4) {
+                const double x2 = mt_real(q[l * d + 1]);
+                if (l > 0 && x2 < in.alpha[ci + in.ld * l]) x = prev;
+            } else if (icld == 2 && l > 0) {
+                if (prev > 1. - cfm) x = prev; else x = x * (1. - cfm);
+            }
+        }
+        prev = x;
+        cfm = cf;
+        unsigned* mw = s.mask + ((long)l * 5 + (sc >> 5)) * P + i;
+        unsigned m = fresh ? 0u : *mw;
+        if (x >= 1. - cf) m |= bit;
+        *mw = m;
+    }
+}
+__global__ void __launch_bounds__(128) mcica_finish_kernel(ColIn in, Scratch s, RunCfg r) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < r.ncol) finish_column(in, s, r, i);
+}
+
+static MtState* g_mt_state = nullptr;
+static unsigned* g_mt_buf = nullptr;
+static size_t g_mt_buf_words = 0;
+
+void free_mt_buffers() {
+    if (g_mt_state) cudaFree(g_mt_state);
+    if (g_mt_buf) cudaFree(g_mt_buf);
+    g_mt_state = nullptr; g_mt_buf = nullptr; g_mt_buf_words = 0;
+}
+
+// Masks of chunk columns [mt_c0, mt_c0 + r.ncol) of a call over mt_ncol columns; returns the number of kernel
+// launches, or -1 when a buffer cannot be allocated.
+int launch_mcica_mt(const ColIn& in, const Scratch& s, const RunCfg& r, long mt_ncol, long mt_c0, cudaStream_t st) {
+    const long per_col = r.icld == 3 ? 1 : (r.icld >= 4 ? 2L * r.nlay : (long)r.nlay);  // draws per (sub-column, column)
+    const size_t need = (size_t)per_col * r.ncol;
+    if (!g_mt_state && cudaMalloc((void**)&g_mt_state, sizeof(MtState)) != cudaSuccess) return -1;
+    if (need > g_mt_buf_words) {
+        cudaStreamSynchronize(st);
+        if (g_mt_buf) cudaFree(g_mt_buf);
+        g_mt_buf = nullptr; g_mt_buf_words = 0;
+        if (cudaMalloc((void**)&g_mt_buf, need * sizeof(unsigned)) != cudaSuccess) return -1;
+        g_mt_buf_words = need;
+    }
+    mt_seed_kernel<<<1, 1, 0, st>>>(g_mt_state, (unsigned)r.permuteseed);
+    int launches = 1;
+    for (int sc = 0; sc < NGPT; ++sc) {
+        // the chunk's run of sub-column sc starts (sc * mt_ncol + mt_c0) * per_col words into the stream
+        const long skip = sc == 0 ? mt_c0 * per_col : (mt_ncol - r.ncol) * per_col;
+        mt_fill_kernel<<<1, 256, 0, st>>>(g_mt_state, g_mt_buf, skip, (long)need);
+        mcica_mt_apply_kernel<<<nblk(r.ncol, 128), 128, 0, st>>>(in, s, r, g_mt_buf, sc);
+        launches += 2;
+    }
+    mcica_finish_kernel<<<nblk(r.ncol, 128), 128, 0, st>>>(in, s, r);
+    return launches + 1;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -672,7 +839,6 @@ __global__ void materialize_kernel(ColIn in, Scratch s, RunCfg r, double* cldfmc
 }
 
 // ---------------------------------------------------------------------------------------------
-static inline int nblk(long n, int b) { return (int)((n + b - 1) / b); }
 
 void launch_prep(const ColIn& in, const Scratch& s, const RunCfg& r, cudaStream_t st) {
     prep_kernel<<<nblk(r.ncol, 128), 128, 0, st>>>(in, s, r);

@@ -14,6 +14,10 @@ struct DevPtrs;
 
 void launch_prep(const ColIn&, const Scratch&, const RunCfg&, cudaStream_t);
 void launch_mcica_kiss(const ColIn&, const Scratch&, const RunCfg&, cudaStream_t);
+// Mersenne-Twister generator (irng = 1): masks of a chunk whose first column is global column mt_c0 of a call over
+// mt_ncol columns; returns the kernels launched or -1 (allocation failure)
+int launch_mcica_mt(const ColIn&, const Scratch&, const RunCfg&, long mt_ncol, long mt_c0, cudaStream_t);
+void free_mt_buffers();
 void launch_cldflags(const ColIn&, const Scratch&, const RunCfg&, cudaStream_t);
 void launch_finalize(const ColIn&, const ColOut&, const Scratch&, const RunCfg&, int cloudy, cudaStream_t);
 void launch_get_alpha(int ncol, long ld, int nlay, int icld, int idcor, double decorr_con, const double* dz,

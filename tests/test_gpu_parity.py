@@ -288,3 +288,45 @@ def test_both_band_kernel_mappings_match_oracle(gpu, oracle, kernel):
     finally:
         import os
         gpu.set_option("band_kernel", int(os.environ.get("RRTMG_LW_BAND_KERNEL", "2")))
+
+
+@pytest.mark.parametrize("icld", [1, 2, 3, 4, 5])
+def test_mersenne_twister_stream_masks_bit_exact(gpu, oracle, icld):
+    """irng = 1: ONE global MT19937 stream over (sub-column, column, layer)
+    (src/mcica_subcol_gen_lw.f90:523-530, 586-595; getRandomReal semantics of
+    src/mcica_random_numbers.f90:276-295).  Device pointers, host pointers, and a column chunk
+    smaller than the call (the words between a chunk's runs are stepped over) all reproduce the oracle."""
+    b = synth.make_batch(300, 72, cloudy=True)
+    al = oracle.get_alpha(b, icld, idcor=1, juldat=200) if icld >= 4 else None
+    ref = oracle.mcica_subcol_lw(b, icld, permuteseed=11, irng=1, alpha=al)
+    assert ref["cldfmcl"].sum() > 0
+    got = driver.run_mcica_subcol(b, icld, permuteseed=11, irng=1, alpha=al, device="cuda:0")
+    assert got["irng"] == 1
+    for k in ("cldfmcl", "ciwpmcl", "clwpmcl", "taucmcl", "reicmcl", "relqmcl"):
+        assert np.array_equal(_np(got[k]), ref[k]), (icld, k)
+    try:
+        gpu.set_chunk(96)   # 300 columns = 4 passes; every pass regenerates the stream up to its runs
+        got = driver.run_mcica_subcol(b, icld, permuteseed=11, irng=1, alpha=al, device="cuda:0")
+        assert np.array_equal(_np(got["cldfmcl"]), ref["cldfmcl"]), (icld, "chunked device")
+        got = driver.run_mcica_subcol(b, icld, permuteseed=11, irng=1, alpha=al)
+        assert np.array_equal(got["cldfmcl"], ref["cldfmcl"]), (icld, "chunked host")
+    finally:
+        gpu.set_chunk(32768)
+
+
+def test_mersenne_twister_fused_matches_oracle(gpu, oracle):
+    """mcica_subcol_lw(irng=1) -> rrtmg_lw in one pass, device and staged host calls (host passes of 128
+    columns keep their place in the global stream)."""
+    b = synth.make_batch(320, 72, cloudy=True, aerosol=True)
+    mc = oracle.mcica_subcol_lw(b, 2, permuteseed=3, irng=1)
+    ref = oracle.rrtmg_lw(b, icld=2, idrv=1, inflglw=2, iceflglw=3, liqflglw=1, mc=mc, nthreads=8)
+    assert ref["rc"] == 0
+    got = driver.run_fused(b, icld=2, idrv=1, permuteseed=3, irng=1, device="cuda:0")
+    gpu.sync()
+    _check(got, ref, 1, what="MT fused device")
+    try:
+        gpu.set_option("host_chunk", 128)
+        got = driver.run_fused(b, icld=2, idrv=1, permuteseed=3, irng=1)
+        _check(got, ref, 1, what="MT fused host, 3 staged passes")
+    finally:
+        gpu.set_option("host_chunk", 32768)
