@@ -255,6 +255,7 @@ def main():
     step()
     torch.cuda.synchronize()
     ms_band, ms_all = api.last_timing()
+    ms_bands = api.last_band_timing()
     api.set_timing(False)
 
     res = None
@@ -279,6 +280,7 @@ def main():
             "frac": flops_per_col * cols_per_s_band / 1e12 / fp64_peak,
             "peak_source": "DFMA microbenchmark run in this process (rrtmg_lw_b200_fp64_peak)",
             "flops_per_column": flops_per_col, "band_kernels_ms_per_step": ms_band, "all_kernels_ms_per_step": ms_all,
+            "per_band_ms_per_step": [round(x, 3) for x in ms_bands],
             "traffic": None,
             "hbm": {"achieved": bytes_per_col * cols_per_s_band / 1e9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": bytes_per_col * cols_per_s_band / 1e9 / hbm_peak, "bytes_per_column": bytes_per_col,
