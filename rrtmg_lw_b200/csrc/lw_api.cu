@@ -25,6 +25,9 @@ struct Ctx {
     HostTables H;
     double* d_arena = nullptr;
     double* d_arena_p = nullptr;
+    // FP32 mode: float copies of every table the band kernels read
+    std::vector<float*> f32_allocs;
+    int precision = 64;
     GTab* d_gtab = nullptr;
     double *d_totplnk = nullptr, *d_totplnkderiv = nullptr, *d_exptfn = nullptr, *d_tau = nullptr;
     double *d_absice2 = nullptr, *d_absice3 = nullptr, *d_absliq1 = nullptr;
@@ -102,6 +105,11 @@ int ensure_scratch(long cols, int nlay) {
     if (A(&S.ctop, (size_t)P)) return RRTMG_LW_ERR_CUDA;
     if (A(&S.state, (size_t)5 * 16 * plane)) return RRTMG_LW_ERR_CUDA;
     if (A(&S.abscld, plane)) return RRTMG_LW_ERR_CUDA;
+    // FP32 mode: the float kernels reuse the same memory through float views; caller-array copies are extra
+    S.fldf = reinterpret_cast<float*>(S.fld);
+    S.statef = reinterpret_cast<float*>(S.state);
+    S.abscldf = reinterpret_cast<float*>(S.abscld);
+    if (A(&S.inf, (size_t)(40 * (size_t)(nlay + 1) + 32) * P)) return RRTMG_LW_ERR_CUDA;
     if (A(&S.status, (size_t)1)) return RRTMG_LW_ERR_CUDA;
     // g-lane path: layer-fastest copies, level-fastest band fluxes, per-resident-warp state slots
     S.LP = ((nlay + 15) / 16) * 16;
@@ -160,6 +168,13 @@ bool launch_band(int band, int cld, int idrv, const ColIn& in, const ColOut& out
            launch_band_tu4(band, cld, idrv, in, out, s, r, st) || launch_band_tu5(band, cld, idrv, in, out, s, r, st);
 }
 
+bool launch_band32(int band, int cld, int idrv, const ColInF& in, const ColOut& out, const Scratch& s, const RunCfg& r,
+                   cudaStream_t st) {
+    return launch_band32_tu0(band, cld, idrv, in, out, s, r, st) || launch_band32_tu1(band, cld, idrv, in, out, s, r, st) ||
+           launch_band32_tu2(band, cld, idrv, in, out, s, r, st) || launch_band32_tu3(band, cld, idrv, in, out, s, r, st) ||
+           launch_band32_tu4(band, cld, idrv, in, out, s, r, st) || launch_band32_tu5(band, cld, idrv, in, out, s, r, st);
+}
+
 bool launch_gband(int band, int cld, int grid, const ColIn& in, const Scratch& s, const RunCfg& r, cudaStream_t st) {
     return launch_gband_tu0(band, cld, grid, in, s, r, st) || launch_gband_tu1(band, cld, grid, in, s, r, st) ||
            launch_gband_tu2(band, cld, grid, in, s, r, st) || launch_gband_tu3(band, cld, grid, in, s, r, st) ||
@@ -195,6 +210,10 @@ int run_device(Mode mode, int ncol, int nlay, int icld, int idrv, int inflag, in
         r.idrv = idrv;
         r.inflag = inflag; r.iceflag = iceflag; r.liqflag = liqflag;
         r.icld = icld; r.irng = irng; r.permuteseed = permuteseed;
+        // optional FP32 mode: float band kernels for clear sky and the fused McICA entry (the strict entry with
+        // per-g cloud arrays and the g-lane kernel stay FP64)
+        const bool fp32 = G.precision == 32 && cld != CLD_ARRAYS && G.band_kernel != 3;
+        r.fp32 = fp32 ? 1 : 0;
         Scratch S = G.S;
         S.dbg_col = (G.dbg && G.dbg_col >= c0 && G.dbg_col < c0 + r.ncol) ? (int)(G.dbg_col - c0) : -1;
         if (S.dbg_col >= 0) G.dbg_nlay = nlay;
@@ -219,9 +238,12 @@ int run_device(Mode mode, int ncol, int nlay, int icld, int idrv, int inflag, in
                 G.launches++;
             }
         } else {
+            ColInF inf{};
+            if (fp32) { G.launches += launch_cvt_inputs(in, S, r, cld != CLD_NONE, inflag, &inf, st); }
             for (int b = 1; b <= NBND; ++b) {
                 if (G.timing) CK(cudaEventRecord(G.evb[b - 1], st));
-                if (!launch_band(b, cld, idrv, in, out, S, r, st)) return RRTMG_LW_ERR_ARG;
+                if (fp32 ? !launch_band32(b, cld, idrv, inf, out, S, r, st) : !launch_band(b, cld, idrv, in, out, S, r, st))
+                    return RRTMG_LW_ERR_ARG;
                 G.launches++;
             }
             if (G.timing) CK(cudaEventRecord(G.evb[NBND], st));
@@ -468,13 +490,59 @@ extern "C" int rrtmg_lw_b200_ini(double cpdair, const double* kdata, long nkdata
     dp.g = G.d_gtab; dp.totplnk = G.d_totplnk; dp.totplnkderiv = G.d_totplnkderiv;
     dp.exptfn = reinterpret_cast<const double2*>(G.d_exptfn); dp.tau_tbl = G.d_tau;
     dp.absice2 = G.d_absice2; dp.absice3 = G.d_absice3; dp.absliq1 = G.d_absliq1;
+    // ---- float copies for the optional FP32 mode (set_option("precision", 32))
+    for (float* p : G.f32_allocs) cudaFree(p);
+    G.f32_allocs.clear();
+    auto upf = [&](const double* h, size_t n, const float** d) -> int {
+        std::vector<float> f(n);
+        for (size_t k = 0; k < n; ++k) f[k] = (float)h[k];
+        float* p = nullptr;
+        CK(cudaMalloc((void**)&p, n * sizeof(float)));
+        CK(cudaMemcpy(p, f.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+        G.f32_allocs.push_back(p);
+        *d = p;
+        return 0;
+    };
+    const float* f_arena = nullptr;
+    const float* f_et = nullptr;
+    const float* f_gt = nullptr;
+    if (upf(H.arena_p.data(), H.arena_p.size(), &f_arena) || upf(H.totplnk.data(), H.totplnk.size(), &dp.totplnk_f) ||
+        upf(H.totplnkderiv.data(), H.totplnkderiv.size(), &dp.totplnkderiv_f) ||
+        upf(H.tau_tbl.data(), H.tau_tbl.size(), &dp.tau_tbl_f) || upf(H.absice2.data(), H.absice2.size(), &dp.absice2_f) ||
+        upf(H.absice3.data(), H.absice3.size(), &dp.absice3_f) || upf(H.absliq1.data(), H.absliq1.size(), &dp.absliq1_f) ||
+        upf(et.data(), et.size(), &f_et) ||
+        upf(reinterpret_cast<const double*>(&gt), sizeof(GTab) / sizeof(double), &f_gt))
+        return RRTMG_LW_ERR_CUDA;
+    static_assert(sizeof(GTabF) / sizeof(float) == sizeof(GTab) / sizeof(double), "GTabF mirrors GTab");
+    dp.exptfn_f = reinterpret_cast<const float2*>(f_et);
+    dp.gf = reinterpret_cast<const GTabF*>(f_gt);
+    ConstTabF cf{};
+    for (int b = 0; b < NBND; ++b) {
+        auto Q = [&](int slot) -> const float* {
+            return H.offp[b][slot] == (size_t)-1 ? nullptr : f_arena + H.offp[b][slot];
+        };
+        BandTabF& U = cf.bandp[b];
+        U.ka = Q(0); U.kb = Q(1); U.selfref = Q(2); U.forref = Q(3); U.fracrefa = Q(4); U.fracrefb = Q(5);
+        for (int m = 0; m < 5; ++m) U.m[m] = Q(6 + m);
+        U.v[0] = Q(11); U.v[1] = Q(12);
+        cf.band[b] = U;
+        cf.delwave[b] = (float)H.ct.delwave[b];
+        cf.a0[b] = (float)H.ct.a0[b]; cf.a1[b] = (float)H.ct.a1[b]; cf.a2[b] = (float)H.ct.a2[b];
+    }
+    cf.fluxfac = (float)H.ct.fluxfac; cf.oneminus = (float)H.ct.oneminus; cf.bpade = (float)H.ct.bpade;
+    cf.e20_b3up = (float)H.ct.e20_b3up; cf.e20_b7 = (float)H.ct.e20_b7;
+    for (int k = 0; k < 7; ++k) cf.b4scale[k] = (float)H.ct.b4scale[k];
+    cf.co2ref_b13 = (float)H.ct.co2ref_b13;
+    for (int k = 0; k < 2; ++k) cf.absice0[k] = (float)H.ct.absice0[k];
+    for (int k = 0; k < 10; ++k) cf.absice1[k] = (float)H.ct.absice1[k];
+    cf.absliq0 = (float)H.ct.absliq0;
     CK(upload_constants_kernels(H.ct, dp, rr));
-    CK(upload_constants_tu0(H.ct, dp, rr));
-    CK(upload_constants_tu1(H.ct, dp, rr));
-    CK(upload_constants_tu2(H.ct, dp, rr));
-    CK(upload_constants_tu3(H.ct, dp, rr));
-    CK(upload_constants_tu4(H.ct, dp, rr));
-    CK(upload_constants_tu5(H.ct, dp, rr));
+    CK(upload_constants_tu0(H.ct, dp, rr, &cf));
+    CK(upload_constants_tu1(H.ct, dp, rr, &cf));
+    CK(upload_constants_tu2(H.ct, dp, rr, &cf));
+    CK(upload_constants_tu3(H.ct, dp, rr, &cf));
+    CK(upload_constants_tu4(H.ct, dp, rr, &cf));
+    CK(upload_constants_tu5(H.ct, dp, rr, &cf));
     CK(upload_constants_gtu0(H.ct, dp, rr));
     CK(upload_constants_gtu1(H.ct, dp, rr));
     CK(upload_constants_gtu2(H.ct, dp, rr));
@@ -793,6 +861,12 @@ extern "C" int rrtmg_lw_b200_set_option(const char* name, int value) {
         G.band_kernel = value;
         return RRTMG_LW_OK;
     }
+    if (std::strcmp(name, "precision") == 0) {
+        // 64 (default) or 32: float band kernels (fluxes within 0.05 W m-2, heating rates within 0.01 K/day of FP64)
+        if (value != 64 && value != 32) return RRTMG_LW_ERR_ARG;
+        G.precision = value;
+        return RRTMG_LW_OK;
+    }
     if (std::strcmp(name, "host_chunk") == 0) {
         if (value < 32) return RRTMG_LW_ERR_ARG;
         G.host_chunk = value;
@@ -856,6 +930,8 @@ extern "C" void rrtmg_lw_b200_finalize(void) {
     std::lock_guard<std::mutex> lk(G.mu);
     free_scratch();
     free_mt_buffers();
+    for (float* p : G.f32_allocs) cudaFree(p);
+    G.f32_allocs.clear();
     if (G.stage) cudaFree(G.stage);
     G.stage = nullptr; G.stage_doubles = 0;
     for (double** p : {&G.d_arena, &G.d_arena_p, &G.d_totplnk, &G.d_totplnkderiv, &G.d_exptfn, &G.d_tau, &G.d_absice2, &G.d_absice3,

@@ -3,6 +3,7 @@
 #include <cstdlib>
 
 #include "lw_band.cuh"
+#include "_generated/lw_band32.cuh"
 #include "lw_launch.h"
 
 #ifndef LW_TU
@@ -51,6 +52,37 @@ static void launch_b(int cld, int idrv, const ColIn& in, const ColOut& out, cons
 #undef LW_GO
 }
 
+// FP32 mode (generated float kernels, lw::p32): clear sky and the fused McICA entry
+template <int B>
+static void launch_b32(int cld, int idrv, const ColInF& in, const ColOut& out, const Scratch& s, const RunCfg& r,
+                       cudaStream_t st) {
+    const int threads = BAND_THREADS;
+    const int blocks = (r.ncol + threads - 1) / threads;
+    const size_t smem = p32::Ring<B>::BYTES;
+#define LW_GO(CLD, IDRV)                                                                                  \
+    do {                                                                                                  \
+        static bool attr_set = false;                                                                     \
+        if (!attr_set) {                                                                                  \
+            cudaFuncSetAttribute(p32::band_kernel<B, CLD, IDRV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            attr_set = true;                                                                              \
+        }                                                                                                 \
+        p32::band_kernel<B, CLD, IDRV><<<blocks, threads, smem, st>>>(in, out, s, r);                     \
+    } while (0)
+    if (cld == CLD_NONE) { if (idrv) LW_GO(CLD_NONE, 1); else LW_GO(CLD_NONE, 0); }
+    else { if (idrv) LW_GO(CLD_MASK, 1); else LW_GO(CLD_MASK, 0); }
+#undef LW_GO
+}
+
+bool LW_CAT(launch_band32_tu, LW_TU)(int band, int cld, int idrv, const ColInF& in, const ColOut& out, const Scratch& s,
+                                     const RunCfg& r, cudaStream_t st) {
+    switch (band) {
+#define LW_CASE(b) case b: launch_b32<b>(cld, idrv, in, out, s, r, st); return true;
+        LW_TU_BANDS(LW_CASE)
+#undef LW_CASE
+        default: return false;
+    }
+}
+
 bool LW_CAT(launch_band_tu, LW_TU)(int band, int cld, int idrv, const ColIn& in, const ColOut& out, const Scratch& s,
                                    const RunCfg& r, cudaStream_t st) {
     switch (band) {
@@ -61,8 +93,9 @@ bool LW_CAT(launch_band_tu, LW_TU)(int band, int cld, int idrv, const ColIn& in,
     }
 }
 
-cudaError_t LW_CAT(upload_constants_tu, LW_TU)(const ConstTab& c, const DevPtrs& d, const double (*refrat)[5]) {
-    return upload_constants_here(c, d, refrat);
+cudaError_t LW_CAT(upload_constants_tu, LW_TU)(const ConstTab& c, const DevPtrs& d, const double (*refrat)[5],
+                                               const ConstTabF* cf) {
+    return upload_constants_here(c, d, refrat, cf);
 }
 
 }  // namespace lw

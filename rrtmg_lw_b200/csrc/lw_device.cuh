@@ -20,6 +20,16 @@ struct ColIn {
     int nlay;
 };
 
+// FP32 mode: float copies (made by the conversion pass of the prep stage, pitch-strided like the scratch) of the
+// caller arrays the band kernels read; same member names as ColIn.
+struct ColInF {
+    const float *play, *tlay, *tlev, *tsfc, *emis, *tauaer;
+    const float *cldfmcl, *taucmcl, *ciwpmcl, *clwpmcl, *reicmcl, *relqmcl;  // unused (strict entry stays FP64)
+    const float *ciwp, *clwp, *rei, *rel, *tauc;
+    long ld;
+    int nlay;
+};
+
 struct ColOut {
     double *uflx, *dflx, *hr, *uflxc, *dflxc, *hrc, *duflx_dt, *duflxc_dt;
     long ld;
@@ -46,6 +56,11 @@ struct Scratch {
     int* ctop;          // pitch : highest layer (1-based) with icldlyr = 1, 0 = cloud-free column
     double* state;      // 5 x 16 x nlay x pitch : atrans, bbugas, atot, bbutot, efclfrac per (g, layer)
     double* abscld;     // nlay x pitch : 1 - exp(-odcld) of the current band (CLD_MASK)
+    // FP32 mode (set_option("precision", 32)): float views / copies used by the generated float band kernels
+    float* fldf;        // NFIELD x nlay x pitch (written by the prep kernel instead of fld)
+    float* statef;      // aliases state
+    float* abscldf;     // aliases abscld
+    float* inf;         // float copies of caller arrays, see lw_api.cu: carve_fp32_inputs
     unsigned long long* status;  // sticky error word: code<<56 | (col+1)<<24 | lay
     long pitch;         // columns per row of every scratch array (multiple of 32)
     // ---- g-lane band kernel (lw_gband.cuh): layer-fastest copies and per-warp state slots
@@ -74,6 +89,7 @@ struct RunCfg {
     int idrv;
     int inflag, iceflag, liqflag;
     int icld, irng, permuteseed;
+    int fp32;        // 1 = the prep kernel writes float fields (Scratch::fldf) for the FP32-mode band kernels
 };
 
 }  // namespace lw

@@ -55,11 +55,15 @@ __global__ void __launch_bounds__(128) prep_kernel(ColIn in, Scratch s, RunCfg r
                      w7 = coldry * o2;
         amttl = amttl + coldry + w1;
         wvttl = wvttl + w1;
-        double* F = s.fld + idx;
-        F[F_WX1 * plane] = coldry * in.ccl4[a] * 1.e-20;
-        F[F_WX2 * plane] = coldry * in.cfc11[a] * 1.e-20;
-        F[F_WX3 * plane] = coldry * in.cfc12[a] * 1.e-20;
-        F[F_WX4 * plane] = coldry * in.cfc22[a] * 1.e-20;
+        // FP32 mode: the float band kernels read float fields from the same memory
+        auto put = [&](int f, double v) {
+            if (r.fp32) s.fldf[(long)f * plane + idx] = (float)v;
+            else s.fld[(long)f * plane + idx] = v;
+        };
+        put(F_WX1, coldry * in.ccl4[a] * 1.e-20);
+        put(F_WX2, coldry * in.cfc11[a] * 1.e-20);
+        put(F_WX3, coldry * in.cfc12[a] * 1.e-20);
+        put(F_WX4, coldry * in.cfc22[a] * 1.e-20);
 
         // setcoef
         const double plog = log(pavel);
@@ -105,25 +109,25 @@ __global__ void __launch_bounds__(128) prep_kernel(ColIn in, Scratch s, RunCfg r
         if (coln2o == 0.) coln2o = 1.e-32 * coldry;
         if (colch4 == 0.) colch4 = 1.e-32 * coldry;
         const double compfp = 1. - fp;
-        F[F_FAC10 * plane] = compfp * ft;
-        F[F_FAC00 * plane] = compfp * (1. - ft);
-        F[F_FAC11 * plane] = fp * ft1;
-        F[F_FAC01 * plane] = fp * (1. - ft1);
-        F[F_COLH2O * plane] = colh2o;
-        F[F_COLCO2 * plane] = colco2;
-        F[F_COLO3 * plane] = colo3;
-        F[F_COLN2O * plane] = coln2o;
-        F[F_COLCH4 * plane] = colch4;
-        F[F_COLO2 * plane] = colo2;
-        F[F_COLBRD * plane] = 1.e-20 * wbrodl;
-        F[F_COLDRY * plane] = coldry;
-        F[F_SELFFAC * plane] = colh2o * selffac;
-        F[F_SELFFRAC * plane] = selffrac;
-        F[F_FORFAC * plane] = colh2o * forfac;
-        F[F_FORFRAC * plane] = forfrac;
-        F[F_MINORFRAC * plane] = minorfrac;
-        F[F_SCALEMINOR * plane] = scaleminor;
-        F[F_SCALEMINORN2 * plane] = scaleminorn2;
+        put(F_FAC10, compfp * ft);
+        put(F_FAC00, compfp * (1. - ft));
+        put(F_FAC11, fp * ft1);
+        put(F_FAC01, fp * (1. - ft1));
+        put(F_COLH2O, colh2o);
+        put(F_COLCO2, colco2);
+        put(F_COLO3, colo3);
+        put(F_COLN2O, coln2o);
+        put(F_COLCH4, colch4);
+        put(F_COLO2, colo2);
+        put(F_COLBRD, 1.e-20 * wbrodl);
+        put(F_COLDRY, coldry);
+        put(F_SELFFAC, colh2o * selffac);
+        put(F_SELFFRAC, selffrac);
+        put(F_FORFAC, colh2o * forfac);
+        put(F_FORFRAC, forfrac);
+        put(F_MINORFRAC, minorfrac);
+        put(F_SCALEMINOR, scaleminor);
+        put(F_SCALEMINORN2, scaleminorn2);
         s.ipack[idx] = jp | (jt << 6) | (jt1 << 9) | (indself << 12) | (indfor << 16) | (indminor << 18);
         if (dbg) {
             int* q = s.dbg_ints + 6 * l;
@@ -850,6 +854,49 @@ void launch_mcica_kiss(const ColIn& in, const Scratch& s, const RunCfg& r, cudaS
     const size_t smem = ((size_t)r.nlay * 5 + 1) * sizeof(unsigned);
     mcica_kiss_par_kernel<<<r.ncol, 160, smem, st>>>(in, s, r, J);
 }
+// dst[e + w*(i + ldd*k)] = (float) src[e + w*(c0 + i + lds*k)]   for e < w, i < ncol, k < nrows
+__global__ void cvt_kernel(const double* __restrict__ src, float* __restrict__ dst, int w, long lds, long ldd, long c0,
+                           int ncol, long nrows) {
+    const long n = (long)w * ncol;
+    for (long k = blockIdx.y; k < nrows; k += gridDim.y)
+        for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < n; t += (long)gridDim.x * blockDim.x)
+            dst[t + (long)w * ldd * k] = (float)src[t + (long)w * (c0 + lds * k)];
+}
+
+int launch_cvt_inputs(const ColIn& in, const Scratch& s, const RunCfg& r, int cloudy, int inflag, ColInF* out,
+                      cudaStream_t st) {
+    const long P = s.pitch;
+    const int nlay = r.nlay;
+    float* p = s.inf;
+    int launches = 0;
+    auto cvt = [&](const double* src, int w, long nrows) -> const float* {
+        float* d = p;
+        p += (size_t)w * P * nrows;
+        dim3 g((unsigned)nblk((long)w * r.ncol, 256), (unsigned)(nrows < 65535 ? nrows : 65535));
+        cvt_kernel<<<g, 256, 0, st>>>(src, d, w, in.ld, P, r.c0, r.ncol, nrows);
+        ++launches;
+        return d - (long)w * r.c0;  // the band kernels index with c0 + i
+    };
+    ColInF f{};
+    f.ld = P; f.nlay = nlay;
+    f.play = cvt(in.play, 1, nlay);
+    f.tlay = cvt(in.tlay, 1, nlay);
+    f.tlev = cvt(in.tlev, 1, nlay + 1);
+    f.tsfc = cvt(in.tsfc, 1, 1);
+    f.emis = cvt(in.emis, 1, 16);
+    f.tauaer = cvt(in.tauaer, 1, (long)nlay * 16);
+    if (cloudy) {
+        f.ciwp = cvt(in.ciwp, 1, nlay); f.clwp = cvt(in.clwp, 1, nlay);
+        f.rei = cvt(in.rei, 1, nlay); f.rel = cvt(in.rel, 1, nlay);
+        // tauc only enters the arithmetic when the cloud optical depth is prescribed (inflag 0); with inflag 2 it only
+        // takes part in the "is there any cloud" test, which the float copy answers identically
+        f.tauc = in.tauc ? cvt(in.tauc, 16, nlay) : nullptr;
+        (void)inflag;
+    }
+    *out = f;
+    return launches;
+}
+
 void launch_cldflags(const ColIn& in, const Scratch& s, const RunCfg& r, cudaStream_t st) {
     zero_int_kernel<<<nblk(r.ncol, 256), 256, 0, st>>>(s.ctop, r.ncol);
     cldflags_kernel<<<nblk((long)r.ncol * r.nlay * 32, 128), 128, 0, st>>>(in, s, r);

@@ -18,6 +18,9 @@ void launch_mcica_kiss(const ColIn&, const Scratch&, const RunCfg&, cudaStream_t
 // mt_ncol columns; returns the kernels launched or -1 (allocation failure)
 int launch_mcica_mt(const ColIn&, const Scratch&, const RunCfg&, long mt_ncol, long mt_c0, cudaStream_t);
 void free_mt_buffers();
+// FP32 mode: float copies of the caller arrays the band kernels read, into Scratch::inf; fills *out with pointers
+// biased by the chunk's first column (the kernels index caller arrays with c0 + i); returns kernels launched
+int launch_cvt_inputs(const ColIn&, const Scratch&, const RunCfg&, int cloudy, int inflag, ColInF* out, cudaStream_t);
 void launch_cldflags(const ColIn&, const Scratch&, const RunCfg&, cudaStream_t);
 void launch_finalize(const ColIn&, const ColOut&, const Scratch&, const RunCfg&, int cloudy, cudaStream_t);
 void launch_get_alpha(int ncol, long ld, int nlay, int icld, int idcor, double decorr_con, const double* dz,
@@ -33,7 +36,9 @@ cudaError_t upload_constants_kernels(const ConstTab&, const DevPtrs&, const doub
 #define LW_DECL_TU(n)                                                                                         \
     bool launch_band_tu##n(int band, int cld, int idrv, const ColIn&, const ColOut&, const Scratch&, const RunCfg&, \
                            cudaStream_t);                                                                     \
-    cudaError_t upload_constants_tu##n(const ConstTab&, const DevPtrs&, const double (*refrat)[5]);
+    bool launch_band32_tu##n(int band, int cld, int idrv, const ColInF&, const ColOut&, const Scratch&, const RunCfg&, \
+                             cudaStream_t);                                                                   \
+    cudaError_t upload_constants_tu##n(const ConstTab&, const DevPtrs&, const double (*refrat)[5], const ConstTabF*);
 LW_DECL_TU(0) LW_DECL_TU(1) LW_DECL_TU(2) LW_DECL_TU(3) LW_DECL_TU(4) LW_DECL_TU(5)
 #undef LW_DECL_TU
 

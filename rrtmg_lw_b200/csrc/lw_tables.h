@@ -33,16 +33,19 @@ constexpr int NSPB[NBND] = {1, 1, 5, 5, 5, 0, 1, 1, 1, 1, 1, 0, 0, 1, 0, 0};
 //   band 8: m0 ka_mco2 m1 ka_mn2o m2 ka_mo3 m3 kb_mco2 m4 kb_mn2o v0 cfc12 v1 cfc22adj
 //   band 9: m0 ka_mn2o(9,19) m1 kb_mn2o   band 11: m0 ka_mo2 m1 kb_mo2
 //   band 13: m0 ka_mco2(9,19) m1 ka_mco(9,19) m2 kb_mo3   band 15: m0 ka_mn2(9,19)
-struct BandTab {
-    const double* ka;    // (65*nspa, NG)
-    const double* kb;    // (235*max(nspb,1), NG) or null
-    const double* selfref;  // (10, NG)
-    const double* forref;   // (4, NG)
-    const double* fracrefa; // (9 or 1, NG)
-    const double* fracrefb; // (5 or 1, NG) or null
-    const double* m[5];
-    const double* v[2];
+template <class T>
+struct BandTabT {
+    const T* ka;    // (65*nspa, NG)
+    const T* kb;    // (235*max(nspb,1), NG) or null
+    const T* selfref;  // (10, NG)
+    const T* forref;   // (4, NG)
+    const T* fracrefa; // (9 or 1, NG)
+    const T* fracrefb; // (5 or 1, NG) or null
+    const T* m[5];
+    const T* v[2];
 };
+using BandTab = BandTabT<double>;
+using BandTabF = BandTabT<float>;   // optional FP32 mode: float copy of the padded arena
 
 // Scalars and small tables that live in __constant__ memory.
 struct ConstTab {
@@ -60,6 +63,20 @@ struct ConstTab {
     double co2ref_b13;             // 3.55e-4 at taumol.f90:2498
     double absice0[2], absice1[10], abscld1, absliq0;
     int drk;
+};
+
+// Float copies of what the FP32-mode band kernels read from constant memory (same member names as ConstTab, so
+// the generated FP32 kernel source only swaps the object).
+struct ConstTabF {
+    BandTabF band[NBND];   // = bandp (the FP32 kernels only use padded rows)
+    BandTabF bandp[NBND];
+    float delwave[NBND];
+    float a0[NBND], a1[NBND], a2[NBND];
+    float fluxfac, oneminus, bpade;
+    float e20_b3up, e20_b7;
+    float b4scale[7];
+    float co2ref_b13;
+    float absice0[2], absice1[10], absliq0;
 };
 
 struct DeviceTables {

@@ -330,3 +330,34 @@ def test_mersenne_twister_fused_matches_oracle(gpu, oracle):
         _check(got, ref, 1, what="MT fused host, 3 staged passes")
     finally:
         gpu.set_option("host_chunk", 32768)
+
+
+def test_fp32_mode_within_north_star_tolerance(gpu, oracle):
+    """Optional FP32 mode (set_option("precision", 32)): the float band kernels (same source as the FP64 ones,
+    tools/gen_fp32.py) must stay within 0.05 W m-2 / 0.01 K day-1 of the FP64 oracle (BASELINE.json north_star);
+    setcoef indices and McICA masks are produced by the unchanged FP64 / integer kernels."""
+    try:
+        gpu.set_option("precision", 32)
+        worst = {}
+        for name, b, kw in (
+            ("clear", synth.make_batch(1024, 72, aerosol=True), None),
+            ("cloudy", synth.make_batch(1024, 72, cloudy=True, aerosol=True), dict(icld=2)),
+            ("cloudy137", synth.make_batch(256, 137, cloudy=True), dict(icld=1)),
+        ):
+            if kw is None:
+                ref = oracle.rrtmg_lw(b, idrv=1, nthreads=8)
+                got = driver.run_clear_or_strict(b, idrv=1, device="cuda:0")
+            else:
+                mc = oracle.mcica_subcol_lw(b, kw["icld"], permuteseed=1, irng=0)
+                ref = oracle.rrtmg_lw(b, icld=kw["icld"], idrv=1, inflglw=2, iceflglw=3, liqflglw=1, mc=mc, nthreads=8)
+                got = driver.run_fused(b, icld=kw["icld"], idrv=1, device="cuda:0")
+            gpu.sync()
+            assert ref["rc"] == 0
+            for k in KEYS + ("duflx_dt", "duflxc_dt"):
+                err = float(np.abs(_np(got[k]) - ref[k]).max())
+                worst[(name, k)] = err
+                tol = 0.01 if k.startswith("hr") else 0.05
+                assert err <= tol, (name, k, err)
+        print("fp32 worst errors:", {k: "%.2e" % v for k, v in worst.items()})
+    finally:
+        gpu.set_option("precision", 64)
