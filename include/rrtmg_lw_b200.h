@@ -142,7 +142,10 @@ int rrtmg_lw_b200_set_chunk(int max_columns);
  * (column, band) with the band's g-points in registers; 3 = g-points spread over the lanes of a
  * unit with the exp/tfn table in shared memory (lw_gband.cuh).  "host_chunk": columns per staged
  * pass of a host-pointer call (default 32768); passes alternate between two staging arenas so the
- * H2D copy of pass k+1 and the D2H copy of pass k-1 overlap the kernels of pass k. */
+ * H2D copy of pass k+1 and the D2H copy of pass k-1 overlap the kernels of pass k.  "precision": 64 (default) or 32 = the optional
+ * FP32 mode of BASELINE.json's north star: float band kernels (taumol, cldprmc, rtrnmc) with double flux
+ * accumulators for clear sky and the fused McICA entry, within 0.05 W m-2 / 0.01 K day-1 of the FP64 results;
+ * setcoef indices and McICA masks are unchanged. */
 int rrtmg_lw_b200_set_option(const char* name, int value);
 
 /* Host-only self test of the n-step jumps of the KISS generator used by the sub-column-parallel
