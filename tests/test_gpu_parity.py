@@ -358,6 +358,16 @@ def test_fp32_mode_within_north_star_tolerance(gpu, oracle):
                 worst[(name, k)] = err
                 tol = 0.01 if k.startswith("hr") else 0.05
                 assert err <= tol, (name, k, err)
+        # host pointers (staged passes) and the Mersenne-Twister stream go through the same float kernels
+        b = synth.make_batch(320, 72, cloudy=True, aerosol=True)
+        mc = oracle.mcica_subcol_lw(b, 2, permuteseed=3, irng=1)
+        ref = oracle.rrtmg_lw(b, icld=2, idrv=0, inflglw=2, iceflglw=3, liqflglw=1, mc=mc, nthreads=8)
+        gpu.set_option("host_chunk", 128)
+        got = driver.run_fused(b, icld=2, idrv=0, permuteseed=3, irng=1)
+        for k in KEYS:
+            err = float(np.abs(_np(got[k]) - ref[k]).max())
+            assert err <= (0.01 if k.startswith("hr") else 0.05), ("host+MT", k, err)
         print("fp32 worst errors:", {k: "%.2e" % v for k, v in worst.items()})
     finally:
         gpu.set_option("precision", 64)
+        gpu.set_option("host_chunk", 32768)
