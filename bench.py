@@ -177,7 +177,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ncol", type=int, default=1048576, help="columns per GPU")
     ap.add_argument("--chunk", type=int, default=262144, help="columns per internal pass")
-    ap.add_argument("--e2e-cols", type=int, default=131072)
+    ap.add_argument("--e2e-cols", type=int, default=262144,
+                    help="columns per end-to-end step (pinned host buffers, 33 KB per column)")
     ap.add_argument("--ref-cols", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", type=int, default=64, choices=[64, 32],
@@ -201,10 +202,12 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = "cuda:%d" % local
+    # keep stdout to the ONE JSON line: anything a library prints to fd 1 meanwhile (e.g. NCCL's version banner)
+    # goes to stderr; fd 1 is restored just before the result line is printed
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # keep stdout to the one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION) goes to stdout
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device(dev))
     blob = kdata.synthetic_blob()
     api.rrtmg_lw_ini(1004.0, blob, 4)
@@ -314,18 +317,30 @@ def main():
 
     # ---- e2e: same metric through the C ABI with HOST (pinned) buffers, H2D + D2H inside the timed region
     ne = min(args.e2e_cols, ncol)
-    hb = {}
     names = ["play", "plev", "tlay", "tlev", "tsfc", "h2ovmr", "o3vmr", "co2vmr", "ch4vmr", "n2ovmr", "o2vmr",
              "cfc11vmr", "cfc12vmr", "cfc22vmr", "ccl4vmr", "emis", "cldfrac", "ciwp", "clwp", "rei", "rel", "tauaer"]
-    for k in names:
-        src = getattr(b, k)
-        sl = src[..., :ne].contiguous()
-        pin = torch.empty(sl.shape, dtype=sl.dtype, pin_memory=True)
-        pin.copy_(sl)
-        hb[k] = pin.numpy()
-    tauc_h = torch.zeros((NLAY, ne, 16), dtype=torch.float64, pin_memory=True).numpy()
-    ho = {k: torch.empty((n, ne), dtype=torch.float64, pin_memory=True).numpy()
-          for k, n in (("uflx", NLAY + 1), ("dflx", NLAY + 1), ("uflxc", NLAY + 1), ("dflxc", NLAY + 1), ("hr", NLAY), ("hrc", NLAY))}
+
+    def pinned_buffers(n):
+        hb_ = {}
+        for k in names:
+            sl = getattr(b, k)[..., :n].contiguous()
+            pin = torch.empty(sl.shape, dtype=sl.dtype, pin_memory=True)
+            pin.copy_(sl)
+            hb_[k] = pin.numpy()
+        tc_ = torch.zeros((NLAY, n, 16), dtype=torch.float64, pin_memory=True).numpy()
+        ho_ = {k: torch.empty((m, n), dtype=torch.float64, pin_memory=True).numpy()
+               for k, m in (("uflx", NLAY + 1), ("dflx", NLAY + 1), ("uflxc", NLAY + 1), ("dflxc", NLAY + 1),
+                            ("hr", NLAY), ("hrc", NLAY))}
+        return hb_, tc_, ho_
+
+    while True:
+        try:
+            hb, tauc_h, ho = pinned_buffers(ne)
+            break
+        except RuntimeError:  # not enough page-locked memory on this host: halve the end-to-end batch
+            if ne <= 8192:
+                raise
+            ne //= 2
     h2d = sum(v.nbytes for v in hb.values()) + tauc_h.nbytes
     d2h = sum(v.nbytes for v in ho.values())
 
@@ -364,8 +379,13 @@ def main():
                                    "sample": "%d columns x %d layers (McICA generation + rrtmg_lw), blocks of 128 over %d "
                                              "threads; C++ restatement of the reference, g++ -O2 -ffp-contract=off "
                                              "(no Fortran compiler in the image)" % (nc, NLAY, cores)}
-        print(json.dumps(res))
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
+    if rank == 0:
+        print(json.dumps(res), flush=True)
     if world > 1:
+        os.dup2(2, 1)
         dist.barrier()
         dist.destroy_process_group()
 
