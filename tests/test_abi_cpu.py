@@ -106,3 +106,25 @@ def test_kiss_jump_ahead_matches_stepping():
     kissvec (src/mcica_subcol_gen_lw.f90:731-741) for all four component generators (host-only check)."""
     from rrtmg_lw_b200 import api
     assert api.lib().rrtmg_lw_b200_kiss_jump_selftest() == 0
+
+
+def test_fp32_variant_is_generated_from_the_same_source():
+    """The optional FP32 mode compiles the SAME band-kernel source as float (tools/gen_fp32.py): the generated
+    header must hold no double-typed kernel arithmetic outside the accumulator alias, and the one the library was
+    built from must be what the generator makes of the current source."""
+    import re
+    import subprocess
+    import sys
+    import tempfile
+    src = os.path.join(ROOT, "rrtmg_lw_b200", "csrc", "lw_band.cuh")
+    gen = os.path.join(ROOT, "rrtmg_lw_b200", "csrc", "_generated", "lw_band32.cuh")
+    with tempfile.TemporaryDirectory() as d:
+        out = os.path.join(d, "lw_band32.cuh")
+        subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "gen_fp32.py"), src, out])
+        body = open(out).read()
+    if os.path.exists(gen):  # built tree: the header the library was compiled from is the current one
+        assert body == open(gen).read(), "stale generated header"
+    assert "namespace p32" in body and "#define LW_F32 1" in body
+    code = "\n".join(l.split("//")[0] for l in body.split("\n"))
+    assert not re.search(r"\bdouble2?\b", code), "double-typed code left in the float variant"
+    assert "acc_t" in code and "ld.global.nc.v4.f32" in body
