@@ -367,7 +367,17 @@ def test_fp32_mode_within_north_star_tolerance(gpu, oracle):
         for k in KEYS:
             err = float(np.abs(_np(got[k]) - ref[k]).max())
             assert err <= (0.01 if k.startswith("hr") else 0.05), ("host+MT", k, err)
+        # column passes inside one device-pointer call (first column of a pass != 0) do not change the result
+        gpu.set_option("host_chunk", 32768)
+        one = driver.run_fused(b, icld=2, idrv=0, device="cuda:0")
+        gpu.sync()
+        gpu.set_chunk(96)
+        many = driver.run_fused(b, icld=2, idrv=0, device="cuda:0")
+        gpu.sync()
+        for k in KEYS:
+            assert np.array_equal(_np(one[k]), _np(many[k])), ("fp32 chunking", k)
         print("fp32 worst errors:", {k: "%.2e" % v for k, v in worst.items()})
     finally:
         gpu.set_option("precision", 64)
         gpu.set_option("host_chunk", 32768)
+        gpu.set_chunk(32768)
