@@ -381,3 +381,35 @@ def test_fp32_mode_within_north_star_tolerance(gpu, oracle):
         gpu.set_option("precision", 64)
         gpu.set_option("host_chunk", 32768)
         gpu.set_chunk(32768)
+
+
+@pytest.mark.parametrize("ncol,nlay", [(1, 72), (33, 51), (129, 4), (7, 200)])
+def test_ragged_and_extreme_sizes(gpu, oracle, ncol, nlay):
+    """One column, column counts that leave partial warps / CTAs, the 4-layer minimum of the KISS seeds and
+    a deep 200-layer grid (parrrtm mxlay = 603): fused McICA entry with aerosol and dF/dTs, device and host."""
+    b = synth.make_batch(ncol, nlay, cloudy=True, aerosol=True)
+    mc = oracle.mcica_subcol_lw(b, 2, permuteseed=1, irng=0)
+    ref = oracle.rrtmg_lw(b, icld=2, idrv=1, inflglw=2, iceflglw=3, liqflglw=1, mc=mc, nthreads=4)
+    assert ref["rc"] == 0
+    got = driver.run_fused(b, icld=2, idrv=1, device="cuda:0")
+    gpu.sync()
+    _check(got, ref, 1, what="device %dx%d" % (ncol, nlay))
+    got = driver.run_fused(b, icld=2, idrv=1)
+    _check(got, ref, 1, what="host %dx%d" % (ncol, nlay))
+    gm = driver.run_mcica_subcol(b, 2, device="cuda:0")
+    assert np.array_equal(_np(gm["cldfmcl"]), mc["cldfmcl"])
+
+
+def test_empty_and_invalid_calls_are_refused(gpu):
+    """ncol = 0, ld < ncol, nlay = 0 or above the compiled maximum: RRTMG_LW_ERR_ARG, nothing is launched."""
+    from rrtmg_lw_b200 import api
+    b = synth.make_batch(8, 72, cloudy=True)
+    c = driver._conv(b, None)
+    at = driver.atm_args(b, c)
+    cl = [c(x) for x in (b.cldfrac, b.ciwp, b.clwp, b.rei, b.rel, b.tauc)]
+    o = driver._outputs(72, 8)
+    outs = [o[k] for k in ("uflx", "dflx", "hr", "uflxc", "dflxc", "hrc")]
+    for ncol, nlay in ((0, 72), (8, 0), (8, 100000)):
+        with pytest.raises(api.RrtmgLwError) as e:
+            api.rrtmg_lw_mcica(ncol, nlay, 2, 0, 1, 0, *at, 2, 3, 1, *cl, None, c(b.tauaer), *outs, None, None)
+        assert e.value.code == 7
