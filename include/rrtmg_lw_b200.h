@@ -135,7 +135,8 @@ int rrtmg_lw_b200_debug_stages(int icol, int* ints6, double* facs, double* taug,
  * count (0 = unknown name); copies min(count, cap) doubles when out != NULL. */
 long rrtmg_lw_b200_get_table(const char* name, double* out, long cap);
 
-/* Upper bound of columns processed per internal pass (scratch is sized to it). */
+/* Upper bound of columns processed per internal pass of a device-pointer call (default 262144; scratch is
+ * sized to min(ncol, max_columns), about 70 KB per column). */
 int rrtmg_lw_b200_set_chunk(int max_columns);
 
 /* Tuning switches (no reference counterpart).  "band_kernel": 2 (default) = one thread per

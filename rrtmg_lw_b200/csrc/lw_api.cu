@@ -39,7 +39,7 @@ struct Ctx {
     // host-mode staging arena
     double* stage = nullptr;
     size_t stage_doubles = 0;
-    int chunk = 32768;
+    int chunk = 262144;       // columns per internal pass of a device-pointer call (scratch is sized to min(ncol, chunk))
     int host_chunk = 32768;   // columns per staged pass of a host-pointer call (H2D / compute / D2H overlap)
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t e_in[2] = {nullptr, nullptr}, e_done[2] = {nullptr, nullptr}, e_out[2] = {nullptr, nullptr};
@@ -693,7 +693,10 @@ extern "C" int rrtmg_lw_b200_mcica_subcol_lw(int iplon, int ncol, int ld, int nl
     if (icld >= 4 && !alpha) return RRTMG_LW_ERR_ARG;
     if (*irng != 0) *irng = 1;
     cudaStream_t st = (cudaStream_t)stream;
-    const int chunk = G.chunk < ncol ? G.chunk : ncol;
+    // host pointers: the staged pass holds the four (140, ncol, nlay) output arrays, so it follows host_chunk
+    int cap = G.chunk;
+    if (memspace == RRTMG_LW_HOST && G.host_chunk < cap) cap = G.host_chunk;
+    const int chunk = cap < ncol ? cap : ncol;
     int rc = ensure_scratch(chunk, nlay);
     if (rc) return rc;
     const long P = ((chunk + 31) / 32) * 32;

@@ -165,7 +165,7 @@ def test_chunking_and_leading_dimension_invariance(gpu, oracle):
         c = driver.run_fused(b, icld=2, device="cuda:0")
         h = driver.run_fused(b, icld=2)
     finally:
-        gpu.set_chunk(32768)
+        gpu.set_chunk(262144)
     for k in KEYS:
         assert torch.equal(a[k], c[k]), k
         assert np.array_equal(_np(a[k]), h[k]), k
@@ -311,7 +311,7 @@ def test_mersenne_twister_stream_masks_bit_exact(gpu, oracle, icld):
         got = driver.run_mcica_subcol(b, icld, permuteseed=11, irng=1, alpha=al)
         assert np.array_equal(got["cldfmcl"], ref["cldfmcl"]), (icld, "chunked host")
     finally:
-        gpu.set_chunk(32768)
+        gpu.set_chunk(262144)
 
 
 def test_mersenne_twister_fused_matches_oracle(gpu, oracle):
@@ -380,7 +380,7 @@ def test_fp32_mode_within_north_star_tolerance(gpu, oracle):
     finally:
         gpu.set_option("precision", 64)
         gpu.set_option("host_chunk", 32768)
-        gpu.set_chunk(32768)
+        gpu.set_chunk(262144)
 
 
 @pytest.mark.parametrize("ncol,nlay", [(1, 72), (33, 51), (129, 4), (7, 200)])
