@@ -17,6 +17,14 @@ for kv in os.environ.get("EXP_OPTS", "").split(","):
         k, v = kv.split("=")
         api.set_option(k, int(v))
 b = bench.make_device_batch(ncol, dev, 0)
+if os.environ.get("EXP_SAME_ATM"):
+    # upper bound of any table-locality optimisation: every column gets column 0's atmosphere (pressure,
+    # temperature, gases), so all lanes of a warp gather the same k-table rows; cloud inputs stay per column
+    for k in ("play", "plev", "tlay", "tlev", "h2ovmr", "o3vmr", "co2vmr", "ch4vmr", "n2ovmr", "o2vmr",
+              "cfc11vmr", "cfc12vmr", "cfc22vmr", "ccl4vmr"):
+        t = getattr(b, k)
+        t.copy_(t[:, :1].expand_as(t))
+    b.tsfc.copy_(b.tsfc[:1].expand_as(b.tsfc))
 out = driver._outputs(72, ncol, like=b.play)
 conv = driver._conv(b, dev)
 at = driver.atm_args(b, conv)
