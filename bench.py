@@ -86,6 +86,23 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def pin_to_gpu_numa_node(index):
+    """Run this rank's host thread (and first-touch its pinned staging buffers) on the CPUs that are local to its
+    GPU, so the end-to-end copies of several ranks do not cross the socket interconnect.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:  # no NVML / no permission: keep the inherited affinity
+        pass
+
+
 def cpu_sample_run(ncol, nthreads, seed_off=0, block=128):
     """The oracle (CPU restatement) on `ncol` cloudy columns: McICA generation + rrtmg_lw in column
     blocks spread over `nthreads` host threads.  Returns seconds."""
@@ -200,6 +217,8 @@ def main():
     from rrtmg_lw_b200 import api, driver, kdata
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    all_cpus = os.sched_getaffinity(0)
+    pin_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
     dev = "cuda:%d" % local
     # keep stdout to the ONE JSON line: anything a library prints to fd 1 meanwhile (e.g. NCCL's version banner)
@@ -369,6 +388,7 @@ def main():
         res["checks"] = {"toa_up_mean": float(out["uflx"][-1].mean()), "sfc_down_mean": float(out["dflx"][0].mean()),
                          "host_equals_device": bool(np.array_equal(ho["uflx"], out["uflx"][:, :ne].cpu().numpy()))}
         if world == 1 and not args.no_cpu_baseline:
+            os.sched_setaffinity(0, all_cpus)  # the CPU baseline uses every host core again
             from oracle import orc
             orc.ini(blob, 1004.0, 4)
             cores = os.cpu_count() or 1
