@@ -87,7 +87,7 @@ int ensure_scratch(long cols, int nlay) {
     const unsigned long long* old_status = G.S.status;
     (void)old_status;
     free_scratch();
-    const long P = ((cols + 31) / 32) * 32;
+    const long P = ((cols + 127) / 128) * 128;  // whole 128-column blocks (RunCfg::fld_block layouts)
     Scratch& S = G.S;
     S = Scratch{};
     S.pitch = P;
@@ -214,6 +214,7 @@ int run_device(Mode mode, int ncol, int nlay, int icld, int idrv, int inflag, in
         // per-g cloud arrays and the g-lane kernel stay FP64)
         const bool fp32 = G.precision == 32 && cld != CLD_ARRAYS && G.band_kernel != 3;
         r.fp32 = fp32 ? 1 : 0;
+        r.fld_block = G.band_kernel == 3 ? 0 : 1;
         Scratch S = G.S;
         S.dbg_col = (G.dbg && G.dbg_col >= c0 && G.dbg_col < c0 + r.ncol) ? (int)(G.dbg_col - c0) : -1;
         if (S.dbg_col >= 0) G.dbg_nlay = nlay;

@@ -90,6 +90,9 @@ struct RunCfg {
     int inflag, iceflag, liqflag;
     int icld, irng, permuteseed;
     int fp32;        // 1 = the prep kernel writes float fields (Scratch::fldf) for the FP32-mode band kernels
+    int fld_block;   // layout of Scratch::fld: 0 = [field][layer][column] (g-lane kernel), 1 = blocks of 128 columns,
+                     // [column / 128][layer][field][column % 128] (column-lane kernel: a CTA's fields of one layer are
+                     // one contiguous run, addressed as one base + compile-time offsets); pitch is a multiple of 128
 };
 
 }  // namespace lw

@@ -57,8 +57,9 @@ __global__ void __launch_bounds__(128) prep_kernel(ColIn in, Scratch s, RunCfg r
         wvttl = wvttl + w1;
         // FP32 mode: the float band kernels read float fields from the same memory
         auto put = [&](int f, double v) {
-            if (r.fp32) s.fldf[(long)f * plane + idx] = (float)v;
-            else s.fld[(long)f * plane + idx] = v;
+            const long o = r.fld_block ? ((((long)(i >> 7) * nlay + l) * NFIELD + f) * 128 + (i & 127)) : ((long)f * plane + idx);
+            if (r.fp32) s.fldf[o] = (float)v;
+            else s.fld[o] = v;
         };
         put(F_WX1, coldry * in.ccl4[a] * 1.e-20);
         put(F_WX2, coldry * in.cfc11[a] * 1.e-20);
