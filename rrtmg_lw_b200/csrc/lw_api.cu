@@ -105,6 +105,7 @@ int ensure_scratch(long cols, int nlay) {
     if (A(&S.ctop, (size_t)P)) return RRTMG_LW_ERR_CUDA;
     if (A(&S.state, (size_t)5 * 16 * plane)) return RRTMG_LW_ERR_CUDA;
     if (A(&S.abscld, plane)) return RRTMG_LW_ERR_CUDA;
+    if (A(&S.fluxB, (size_t)6 * (nlay + 1) * P)) return RRTMG_LW_ERR_CUDA;
     // FP32 mode: the float kernels reuse the same memory through float views; caller-array copies are extra
     S.fldf = reinterpret_cast<float*>(S.fld);
     S.statef = reinterpret_cast<float*>(S.state);

@@ -56,6 +56,8 @@ struct Scratch {
     int* ctop;          // pitch : highest layer (1-based) with icldlyr = 1, 0 = cloud-free column
     double* state;      // 5 x 16 x nlay x pitch : atrans, bbugas, atot, bbutot, efclfrac per (g, layer)
     double* abscld;     // nlay x pitch : 1 - exp(-odcld) of the current band (CLD_MASK)
+    double* fluxB;      // [pitch / 128][nlay + 1][6][128] running band sums of dflx, dflxc, uflx, uflxc, duflx_dt,
+                        // duflxc_dt (column-lane kernel; the finalize kernel writes the caller's arrays from them)
     // FP32 mode (set_option("precision", 32)): float views / copies used by the generated float band kernels
     float* fldf;        // NFIELD x nlay x pitch (written by the prep kernel instead of fld)
     float* statef;      // aliases state

@@ -705,16 +705,23 @@ __global__ void __launch_bounds__(128) finalize_kernel(ColIn in, ColOut out, Scr
     const long ci = r.c0 + i;
     const int nlay = r.nlay;
     const bool sep = cloudy && s.ctop[i] > 0;
+    // band sums of the column-lane kernels: [column / 128][level][6][column % 128] (lw_band.cuh)
+    const double* fb = s.fluxB + ((long)(i >> 7) * (nlay + 1) * 6) * 128 + (i & 127);
     double fnet_lo = 0., fnetc_lo = 0., pz_lo = 0.;
     for (int lev = 0; lev <= nlay; ++lev) {
         const long o = ci + out.ld * lev;
-        const double u = out.uflx[o] * C.fluxfac;
-        const double d = out.dflx[o] * C.fluxfac;
+        const double* f = fb + (long)lev * 6 * 128;
+        const double u = f[256] * C.fluxfac;
+        const double d = f[0] * C.fluxfac;
         double uc, dc;
-        if (sep) { uc = out.uflxc[o] * C.fluxfac; dc = out.dflxc[o] * C.fluxfac; }
+        if (sep) { uc = f[384] * C.fluxfac; dc = f[128] * C.fluxfac; }
         else { uc = u; dc = d; }
         out.uflx[o] = u; out.dflx[o] = d; out.uflxc[o] = uc; out.dflxc[o] = dc;
-        if (r.idrv == 1 && !sep) out.duflxc_dt[o] = out.duflx_dt[o];
+        if (r.idrv == 1) {
+            const double du = f[512];
+            out.duflx_dt[o] = du;
+            out.duflxc_dt[o] = sep ? f[640] : du;
+        }
         const double fnet = u - d, fnetc = uc - dc;
         const double pz = in.plev[ci + in.ld * lev];
         if (lev > 0) {
