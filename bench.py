@@ -145,7 +145,7 @@ def run_reference(args, rank):
     for s in range(args.steps):
         t += cpu_sample_run(ncol, cores, seed_off=10 + s)
     val = ncol * args.steps / t
-    sample = "%d columns x %d layers per step, blocks of 128 columns over %d threads, oracle C++ port -O2 -ffp-contract=off" % (ncol, NLAY, cores)
+    sample = "%d columns x %d layers per step, blocks of 128 columns over %d threads, oracle C++ port -O3 -ffp-contract=off" % (ncol, NLAY, cores)
     print(json.dumps({
         "impl": "reference", "metric": "columns/sec", "value": val, "unit": "columns/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
@@ -397,7 +397,7 @@ def main():
             tc = cpu_sample_run(nc, cores, seed_off=3)
             res["cpu_baseline"] = {"value": nc / tc, "unit": "columns/s", "cores": cores, "kind": "port",
                                    "sample": "%d columns x %d layers (McICA generation + rrtmg_lw), blocks of 128 over %d "
-                                             "threads; C++ restatement of the reference, g++ -O2 -ffp-contract=off "
+                                             "threads; C++ restatement of the reference, g++ -O3 -ffp-contract=off "
                                              "(no Fortran compiler in the image)" % (nc, NLAY, cores)}
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
