@@ -193,7 +193,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ncol", type=int, default=1048576, help="columns per GPU")
-    ap.add_argument("--chunk", type=int, default=262144, help="columns per internal pass")
+    ap.add_argument("--chunk", type=int, default=1048576,
+                    help="columns per internal pass (scratch is ~70 KB per column of the pass; the default runs the "
+                         "1 M-column batch in one pass: 73 GB of scratch beside 25 GB of inputs and outputs)")
     ap.add_argument("--e2e-cols", type=int, default=262144,
                     help="columns per end-to-end step (pinned host buffers, 33 KB per column)")
     ap.add_argument("--ref-cols", type=int, default=0)
