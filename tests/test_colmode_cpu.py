@@ -1,0 +1,174 @@
+"""Example-suite harness (rrtmg_lw_b200/colmode.py) on the CPU: the parsers against the
+reference's own example files (fixture tests/golden/std_atm_cases.json made by tools/make_golden_cases.py;
+re-parsed from /root/reference when that exists), the writer against the shipped OUTPUT_RRTM text, and
+the driver loop (McICA averaging, idrv dtbound adjustment) run over the oracle and pinned on the
+data-independent numbers of the goldens (surface upward flux, incl. the idrv = 1 adjusted value)."""
+import dataclasses
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from colmode_checker import OracleBackend  # noqa: E402
+from rrtmg_lw_b200 import colmode  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_EX = "/root/reference/run_examples_std_atm"
+have_ref = pytest.mark.skipif(not os.path.isdir(REF_EX), reason="reference tree not mounted")
+
+
+@pytest.fixture(scope="module")
+def suite():
+    return json.load(open(os.path.join(ROOT, "tests", "golden", "std_atm_cases.json")))
+
+
+def _supported(suite):
+    return {n: d for n, d in suite.items() if d["case"] is not None}
+
+
+def test_suite_inventory(suite):
+    """14 runs in script.run_std_atm; 13 parse (iatm = 0), ICRCCM_sonde is the rrtatm case (N4)."""
+    assert len(suite) == 14
+    assert [n for n, d in suite.items() if d["case"] is None] == ["ICRCCM_sonde"]
+    flags = {n: (d["case"]["icld"], d["case"]["imca"], d["case"]["idrv"], d["case"]["iaer"], d["case"]["ixsect"])
+             for n, d in _supported(suite).items()}
+    assert flags["MLS-clr"] == (0, 0, 0, 0, 0)
+    assert flags["MLS-clr-idrv1"] == (0, 0, 1, 0, 0) and suite["MLS-clr-idrv1"]["case"]["dtbound"] == 5.0
+    assert flags["MLS-clr-aer12"] == (0, 0, 0, 10, 0)
+    assert flags["MLS-clr-xsec"] == (0, 0, 0, 0, 1)
+    assert flags["MLS-cld5-imca0-icld2"] == (2, 0, 0, 0, 0)
+    assert flags["MLS-cld7-imca1-icld5-idcor1"] == (5, 1, 0, 0, 0)
+    c = suite["MLS-cld7-imca1-icld5-idcor1"]["case"]
+    assert (c["idcor"], c["juldat"], c["lat"]) == (1, 1, 45.0)
+    c = suite["MLS-cld7-imca1-icld4-idcor0"]["case"]
+    assert c["idcor"] == 0 and c["decorr_con"] > 0
+    assert (c["inflag"], c["iceflag"], c["liqflag"]) == (2, 3, 1)
+    assert sum(1 for f in c["cldfrac"] if f > 0) == 13 and c["cldfrac"][3] == 0.5 and c["clddat"][11] == [2.0, 1.0, 25.0, 10.0]
+    a = suite["MLS-clr-aer12"]["case"]["tauaer"]
+    assert a[0][0] == 0.0005 and a[0][3] == 0.0015 and sum(1 for r in a if max(r) > 0) == 12
+    x = suite["MLS-clr-xsec"]["case"]
+    assert [colmode.xs_slot(n) for n in x["xsname"]] == [2, 4, 3, 1]   # F11 F22 F12 CCL4 -> cfc11 cfc22 cfc12 ccl4
+    assert x["wx0"][0] == [3.5199330e-10, 1.5e-10, 6.3581760e-10, 1.3975950e-10]
+
+
+def test_matches_first_golden_fixture(suite, std_atm):
+    """Same profiles as the round's first fixture (tools/make_golden.py, an independent parser)."""
+    for n in ("MLS-clr", "MLW-clr", "SAW-clr", "TROP-clr"):
+        a, b = suite[n]["case"], std_atm[n]["input"]
+        for k in ("pavel", "tavel", "pz", "tz", "wbrodl", "tbound", "nlayers"):
+            assert a[k] == b[k], (n, k)
+        assert [w[:7] for w in a["wkl"]] == b["wkl"]
+
+
+@have_ref
+def test_fixture_is_what_the_reference_files_parse_to(suite):
+    rd = lambda f: open(os.path.join(REF_EX, f)).read() if f else None  # noqa: E731
+    for n, d in _supported(suite).items():
+        c = colmode.parse_input_rrtm(*[rd(f) for f in d["files"]])
+        assert dataclasses.asdict(c) == d["case"], n
+    with pytest.raises(NotImplementedError):
+        colmode.parse_input_rrtm(rd("input_rrtm_ICRCCM_sonde"))
+
+
+@have_ref
+def test_writer_reproduces_the_shipped_output_text(suite):
+    """format_output fed with the golden numbers gives the reference's block character for character
+    (formats 9899-9958, src/rrtmg_lw.1col.f90:737-751), for every case of the suite."""
+    for n, d in suite.items():
+        text = open(os.path.join(REF_EX, "output_rrtm_" + n)).read()
+        g = {k: np.array(v) for k, v in d["golden"].items() if k in ("pz", "uflx", "dflx", "fnet", "htr")}
+        mine = colmode.format_output(g).split("\n")
+        theirs = text.split("\n")[:len(mine) - 2]
+        assert [ln.rstrip() for ln in mine[:len(theirs)]] == [ln.rstrip() for ln in theirs], n
+
+
+def test_writer_parser_round_trip():
+    rng = np.random.default_rng(7)
+    pz = np.array([1013.0, 500.0, 99.5, 9.95, 0.995, 0.0995, 0.00995, 0.000995])
+    res = dict(pz=pz, uflx=rng.uniform(0, 500, 8), dflx=rng.uniform(0, 400, 8), htr=rng.uniform(-30, 30, 8))
+    res["fnet"] = res["uflx"] - res["dflx"]
+    res["htr"][3] = -0.25
+    b = colmode.parse_output_rrtm(colmode.format_output(res, iplon=3) + colmode.format_output(res, iplon=4))
+    assert len(b) == 2 and b[0]["atm"] == 3 and (b[0]["wn1"], b[0]["wn2"]) == (10.0, 3250.0)
+    assert list(b[0]["level"]) == list(range(8))
+    np.testing.assert_allclose(b[0]["uflx"], res["uflx"], atol=5.1e-5)
+    np.testing.assert_allclose(b[0]["fnet"], res["fnet"], atol=5.1e-8)
+    np.testing.assert_allclose(b[0]["htr"], res["htr"], atol=5.1e-6)
+    np.testing.assert_allclose(b[0]["pz"], pz, rtol=6e-4)
+
+
+def test_cloud_and_aerosol_readers_on_synthetic_text():
+    cld = "    0    0    0\n    2       1.0       3.5\n   10      0.25       0.5\n%\nignored\n"
+    inflag, iceflag, liqflag, frac, dat = colmode.parse_in_cld(cld, 12)
+    assert (inflag, iceflag, liqflag) == (0, 0, 0) and frac[1] == 1.0 and dat[1][0] == 3.5 and frac[9] == 0.25
+    with pytest.raises(ValueError):
+        colmode.parse_in_cld("    2    3    1\n   13       1.0       3.5\n%\n", 12)
+    row = lambda lay, v: "  %3d" % lay + "".join("%7.4f" % v for _ in range(16))  # noqa: E731
+    aer = "    2\n    2    1\n" + row(1, 0.01) + "\n" + row(2, 0.02) + "\n    1    1\n" + row(5, 0.05) + "\n"
+    tau = colmode.parse_in_aer(aer, 6)
+    assert tau[0][0] == 0.01 and tau[1][15] == 0.02 and tau[4][7] == 0.05 and max(tau[2]) == 0.0
+    with pytest.raises(ValueError, match="MORE THAN ONE AEROSOL"):
+        colmode.parse_in_aer("    2\n    1    1\n" + row(1, 0.01) + "\n    1    1\n" + row(1, 0.02) + "\n", 6)
+    # implied decimals of a field without a decimal point (Fortran F/E edit descriptors)
+    assert colmode._real("  950", 3) == pytest.approx(0.95) and colmode._real("1.5D2") == 150.0 and colmode._real("   ") == 0.0
+
+
+def test_mixing_ratio_and_column_amount_inputs_agree(suite):
+    """readprof's imix switch (1col:1006-1036): amounts > 1 are molecules/cm2 and divide by the dry column."""
+    c = colmode.Case(**suite["MLS-clr"]["case"])
+    b1 = colmode.case_to_batch(c)
+    assert b1.meta["imix"] == 1
+    summol = np.array([sum(w[1:7]) for w in c.wkl])
+    coldry = np.array(c.wbrodl) / (1.0 - summol)
+    c2 = dataclasses.replace(c, wkl=[[x * cd for x in w] for w, cd in zip(c.wkl, coldry)],
+                             wbrodl=list(coldry * (1.0 - summol)))
+    b2 = colmode.case_to_batch(c2)
+    assert b2.meta["imix"] == 0
+    # column amounts carry the water column too: coldry(imix=0) = wbrodl + sum(non-water) by the reference's rule
+    np.testing.assert_allclose(b2.co2vmr.numpy(), b1.co2vmr.numpy(), rtol=1e-12)
+    np.testing.assert_allclose(b2.h2ovmr.numpy(), b1.h2ovmr.numpy(), rtol=1e-12)
+
+
+def test_driver_loop_over_the_oracle_pins_the_goldens_surface_flux(suite, oracle):
+    """Every supported case through run_case with the CPU checker: level pressures equal the golden's, the
+    surface upward flux (Planck tables only; emissivity 1) equals the golden's to 1.5e-3 W m-2 -- for
+    MLS-clr-idrv1 that is the dtbound-adjusted value 453.6771, which pins dplankbnd_dt -- and the
+    downward flux at the top is zero.  k-dependent numbers are not comparable (synthetic k-data)."""
+    be = OracleBackend(oracle)
+    for n, d in _supported(suite).items():
+        c = colmode.Case(**d["case"])
+        if c.imca == 0 and c.icld >= 1:
+            with pytest.raises(NotImplementedError):
+                colmode.run_case(c, be)
+            continue
+        r = colmode.run_case(c, be, nmca=None if n == "MLS-cld7-imca1-icld5-idcor1" else 6)
+        g = d["golden"]
+        assert r["nmca"] == (1 if c.imca == 0 else (200 if n == "MLS-cld7-imca1-icld5-idcor1" else 6))
+        np.testing.assert_allclose(r["pz"], g["pz"], rtol=6e-4)
+        assert abs(r["uflx"][0] - g["uflx"][0]) <= 1.5e-3, (n, r["uflx"][0], g["uflx"][0])
+        assert r["dflx"][-1] == 0.0 and r["htr"][-1] == 0.0
+        np.testing.assert_allclose(r["fnet"], r["uflx"] - r["dflx"], atol=1e-12)
+        blk = colmode.parse_output_rrtm(colmode.format_output(r))[0]
+        np.testing.assert_allclose(blk["uflx"], r["uflx"], atol=5.1e-5)
+
+
+def test_idrv_adjustment_is_the_reference_formula(suite, oracle):
+    """1col:587-610: uflx += duflx_dt * dtbound, fnet and htr recomputed; dflx unchanged; dtbound = 0 is a no-op."""
+    be = OracleBackend(oracle)
+    c = colmode.Case(**suite["MLS-clr-idrv1"]["case"])
+    r5 = colmode.run_case(c, be)
+    r0 = colmode.run_case(dataclasses.replace(c, dtbound=0.0), be)
+    base = colmode.run_case(dataclasses.replace(c, idrv=0), be)
+    np.testing.assert_allclose(r0["uflx"], base["uflx"], atol=1e-9)
+    np.testing.assert_allclose(r0["htr"], base["htr"], atol=1e-9)
+    np.testing.assert_array_equal(r5["dflx"], base["dflx"])
+    o = be.clear(colmode.case_to_batch(c), 1)
+    np.testing.assert_allclose(r5["uflx"], base["uflx"] + 5.0 * o["duflx_dt"].reshape(-1), atol=1e-9)
+    # the finite difference of two runs 5 K apart agrees with the derivative to second order
+    hot = colmode.run_case(dataclasses.replace(c, idrv=0, tbound=c.tbound + 5.0), be)
+    # (the second-order term 6 sigma T^2 dT^2 is 0.74 W m-2 at the surface)
+    assert abs(hot["uflx"][0] - r5["uflx"][0]) < 1.0
+    assert abs(hot["uflx"][-1] - r5["uflx"][-1]) < 1.0
