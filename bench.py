@@ -204,6 +204,9 @@ def main():
                     help="64 = the headline FP64 path; 32 = the optional FP32 mode of the band kernels (secondary line)")
     ap.add_argument("--band-kernel", type=int, default=2, choices=[2, 3],
                     help="2 = one thread per (column, band), all g-points in registers; 3 = g-points across lanes")
+    ap.add_argument("--gather", action="store_true",
+                    help="N > 1 only: also time the step WITH the NCCL gather of the six output arrays into rank 0, "
+                         "pipelined in 4 column chunks (sharding.pipelined_gather); adds a 'gather' object")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
@@ -285,6 +288,53 @@ def main():
     ms_bands = api.last_band_timing()
     api.set_timing(False)
 
+    # ---- optional: the same step followed by the output gather to rank 0, chunk i's NCCL gather
+    # overlapping chunk i+1's kernels; timed like the headline (device events, max over ranks)
+    gather_res = None
+    if world > 1 and args.gather:
+        from rrtmg_lw_b200 import sharding
+        rows = [("uflx", NLAY + 1), ("dflx", NLAY + 1), ("hr", NLAY), ("uflxc", NLAY + 1), ("dflxc", NLAY + 1),
+                ("hrc", NLAY)]
+        co = api.col_offset
+
+        def run_chunk(lo, hi, outs):
+            a = [co(x, lo) for x in at]
+            c_ = [co(x, lo) for x in cl[:5]] + [co(b.tauc, lo, 16)]
+            o = {k: co(out[k], lo) for k, _ in rows}
+            api.rrtmg_lw_mcica(hi - lo, NLAY, 2, 0, 1, 0, *a, 2, 3, 1, *c_, None, co(b.tauaer, lo), o["uflx"], o["dflx"],
+                               o["hr"], o["uflxc"], o["dflxc"], o["hrc"], None, None, ld=ncol)
+            for k, _ in rows:
+                outs[k].copy_(out[k][:, lo:hi])
+
+        def step_gather():
+            return sharding.pipelined_gather(world * ncol, rows, run_chunk, nchunks=4, dst=0, device=dev)
+
+        step()
+        torch.cuda.synchronize()
+        keep_local = {k: out[k].clone() for k, _ in rows} if rank == 0 else None
+        g = step_gather()
+        barrier()
+        same = bool(all(torch.equal(g[k][:, :ncol], keep_local[k]) for k, _ in rows)) if rank == 0 else None
+        del g, keep_local
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kg = max(2, min(args.steps, 5))
+        barrier()
+        g0.record()
+        for _ in range(kg):
+            g = step_gather()
+            del g
+        g1.record()
+        barrier()
+        msg = g0.elapsed_time(g1)
+        tg = torch.tensor([msg], device=dev, dtype=torch.float64)
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        msg = float(tg.item()) / kg
+        gather_res = {"value": world * ncol / (msg * 1e-3), "unit": "columns/s", "ms_per_step": msg, "steps": kg,
+                      "chunks": 4, "dst": 0, "bytes_into_root_per_step": (world - 1) * ncol * (6 * NLAY + 4) * 8,
+                      "root_block_equals_ungathered_step": same,
+                      "note": "step in 4 column chunks; chunk i's ncclGather (NCCL stream) overlaps chunk i+1's kernels; "
+                              "includes packing and the assembly of the (rows, N*ncol) arrays on rank 0"}
+
     res = None
     if rank == 0:
         # ---- roofline of the dominant kernel group (the 16 band kernels of a pass)
@@ -335,6 +385,8 @@ def main():
                                     "optional fp32 mode: float band kernels, double flux accumulators (tolerance 0.05 W m-2 / 0.01 K/day)"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof,
         }
+        if gather_res is not None:
+            res["gather"] = gather_res
 
     # ---- e2e: same metric through the C ABI with HOST (pinned) buffers, H2D + D2H inside the timed region
     ne = min(args.e2e_cols, ncol)

@@ -60,6 +60,27 @@ def _is_torch(a):
     return a is not None and hasattr(a, "data_ptr")
 
 
+class col_offset:
+    """Column ``lo`` onwards of a column-fastest (Fortran layout) device array, for running a column sub-range of a
+    resident batch: pass it where the array goes and give the call ``ld`` = the array's full column extent.
+    ``inner`` = elements per column ahead of the column axis (16 for ``tauc``, 140 for the McICA arrays)."""
+    is_cuda = True
+
+    def __init__(self, t, lo: int, inner: int = 1):
+        assert t.is_cuda and t.is_contiguous() and t.element_size() == 8 and t.dtype.is_floating_point
+        self.base, self.dtype = t, t.dtype
+        self._p = t.data_ptr() + int(lo) * int(inner) * 8
+
+    def data_ptr(self):
+        return self._p
+
+    def element_size(self):
+        return 8
+
+    def is_contiguous(self):
+        return True
+
+
 def _ptr(a):
     if a is None:
         return None

@@ -79,6 +79,72 @@ def gather_outputs(local: dict, ncol_total: int, idrv: int = 0, dst: int | None 
     return out
 
 
+def pipelined_gather(ncol_total: int, rows, run_chunk, nchunks: int = 4, dst: int | None = 0, group=None,
+                     device="cpu", assemble: bool = True):
+    """The rank's column block is run in ``nchunks`` column chunks; the gather of chunk i travels (NCCL's own
+    stream) while chunk i+1 computes on the caller's stream -- SURVEY 8(e): the output gather is comparable to the
+    compute time, so it is overlapped instead of appended.
+
+    ``rows``: list of ``(key, nrows)`` of the output arrays (``uflx`` has nlay+1 rows, ``hr`` nlay, ...).
+    ``run_chunk(lo, hi, outs)`` computes local columns [lo, hi) into ``outs[key]``, contiguous ``(nrows, hi-lo)``
+    tensors on ``device`` -- they are row ranges of the chunk's packed send buffer, so whatever the call writes there is
+    what is sent (a C-ABI call whose inputs are a column sub-range of a resident batch shares one ``ld`` with its
+    outputs: it writes its own ``(nrows, ncol_local)`` arrays through ``api.col_offset`` and copies the chunk in).
+    Returns on ``dst`` (every rank if ``dst`` is None) the dict of full ``(nrows, ncol_total)`` arrays, or with
+    ``assemble=False`` the raw ``[chunk][rank]`` packed buffers plus the geometry ``(per, cw)``; None elsewhere.
+    """
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    per = -(-ncol_total // world)
+    lo_r, hi_r = block_range(ncol_total, world, rank)
+    nloc = hi_r - lo_r
+    cw = -(-per // max(1, nchunks))
+    nchunks = -(-per // cw)
+    R = sum(n for _, n in rows)
+    want = dst is None or rank == dst
+    works, recv, keep = [], [], []
+    for c in range(nchunks):
+        lo = min(c * cw, nloc)
+        hi = min(lo + cw, nloc)
+        full_width = hi - lo == cw
+        pack = (torch.empty if full_width else torch.zeros)((R, cw), dtype=torch.float64, device=device)
+        if hi > lo:
+            tgt = pack if full_width else torch.empty((R, hi - lo), dtype=torch.float64, device=device)
+            outs, r0 = {}, 0
+            for k, n in rows:
+                outs[k] = tgt[r0:r0 + n]
+                r0 += n
+            run_chunk(lo, hi, outs)
+            if not full_width:
+                pack[:, :hi - lo] = tgt
+        if dst is None or not pack.is_cuda:      # gloo: all_gather is universally available
+            bufs = [torch.empty_like(pack) for _ in range(world)]
+            works.append(dist.all_gather(bufs, pack, group=group, async_op=True))
+        else:
+            bufs = [torch.empty_like(pack) for _ in range(world)] if rank == dst else None
+            works.append(dist.gather(pack, bufs, dst=dst, group=group, async_op=True))
+        recv.append(bufs)
+        keep.append(pack)
+    for w in works:
+        w.wait()
+    if not want:
+        return None
+    if not assemble:
+        return dict(packed=recv, per=per, cw=cw, rows=list(rows))
+    full = torch.empty((R, ncol_total), dtype=torch.float64, device=device)
+    for c in range(nchunks):
+        for r in range(world):
+            g0 = r * per + c * cw
+            n = max(0, min(cw, per - c * cw, ncol_total - g0))
+            if n > 0:
+                full[:, g0:g0 + n] = recv[c][r][:, :n]
+    out, r0 = {}, 0
+    for k, n in rows:
+        out[k] = full[r0:r0 + n]
+        r0 += n
+    return out
+
+
 def run_sharded(b: "synth.Batch", run_local, idrv: int = 0, irng: int = 0, gather_to: int | None = None, group=None):
     """Run ``run_local(shard) -> dict`` on this rank's column block and gather the outputs.
 

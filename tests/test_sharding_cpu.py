@@ -67,6 +67,33 @@ def _worker(rank, world, port, ncol, nlay, q):
         assert (only0 is None) == (rank != 0)
         with pytest.raises(ValueError):
             sharding.run_sharded(b, run_local, irng=1)
+        # pipelined variant: the rank's block in 3 column chunks, each chunk's gather issued before the next chunk
+        # is computed (ragged: 37 columns -> blocks 19 + 18, chunks of 7 -> 7 + 7 + 5 | 7 + 7 + 4)
+        shard = sharding.shard_batch(b, world, rank)
+        rows = [(k, nlay if k.startswith("hr") else nlay + 1) for k in sharding.OUT_KEYS]
+        calls = []
+
+        def run_chunk(lo, hi, outs):
+            calls.append((lo, hi))
+            sub = sharding.shard_batch(shard, 1, 0)
+            for k2, v2 in sub.__dict__.items():
+                if torch.is_tensor(v2):
+                    d = sharding._COL_DIM.get(k2, v2.dim() - 1)
+                    setattr(sub, k2, v2.narrow(d, lo, hi - lo).contiguous())
+            sub.ncol = hi - lo
+            r = run_local(sub)
+            for k2 in outs:
+                assert outs[k2].is_contiguous() and outs[k2].shape == r[k2].shape
+                outs[k2].copy_(r[k2])
+
+        for dst_ in (None, 0):
+            piped = sharding.pipelined_gather(ncol, rows, run_chunk, nchunks=3, dst=dst_)
+            assert (piped is None) == (dst_ == 0 and rank != 0)
+            if piped is not None:
+                assert all(torch.equal(piped[k], full[k]) for k in full), "pipelined gather differs"
+        assert calls[:3] == [(0, 7), (7, 14), (14, 19 if rank == 0 else 18)]
+        raw = sharding.pipelined_gather(ncol, rows, run_chunk, nchunks=3, dst=None, assemble=False)
+        assert raw["per"] == 19 and raw["cw"] == 7 and len(raw["packed"]) == 3 and len(raw["packed"][0]) == world
         if rank == 0:
             q.put({k: v.numpy() for k, v in full.items()})
             assert all(torch.equal(only0[k], full[k]) for k in full)
