@@ -11,7 +11,8 @@ provides
   small element-wise jitter so that any index mix-up changes the result,
 * ``load_netcdf``: reader for a real ``rrtmg_lw.nc`` following the variable names and
   hyperslabs of ``src/rrtmg_lw_read_nc.f90`` / ``modules/rrlw_ncpar.f90`` (NetCDF-3 classic
-  through ``scipy.io.netcdf_file``); untested against real data because none is available.
+  through ``scipy.io.netcdf_file``); round-trip tested against ``save_netcdf`` (same names, dimensions and
+  hyperslabs), not against real data because none is available.
 """
 from __future__ import annotations
 
@@ -192,3 +193,63 @@ def load_netcdf(path: str) -> dict:
         out[(band, name)] = np.ascontiguousarray(a, dtype=np.float64)
     f.close()
     return out
+
+
+def save_netcdf(path: str, arrays: dict) -> None:
+    """Write a blob dictionary as an ``rrtmg_lw.nc``-shaped NetCDF-3 classic file: the eight variables of
+    ``src/rrtmg_lw_read_nc.f90`` with the dimensions of ``modules/rrlw_ncpar.f90:31-44`` (Fortran order
+    ``(keylower, Tdiff, plower, GPoint, band, GPointSet)`` etc., i.e. reversed in the file), the slabs each
+    ``lw_kgbNN`` reads filled from ``arrays`` and everything else zero.  Used to exercise ``load_netcdf`` without
+    the reference's data file and to hand k-tables to a reference build that reads NetCDF."""
+    from scipy.io import netcdf_file
+
+    dims = dict(keylower=9, keyupper=5, Tdiff=5, plower=13, pupper=47, Tself=10, Tforeign=4, T=19, band=16, GPoint=16,
+                GPointSet=2, Absorber=12)
+    spec = {   # file (C) order = reversed Fortran order
+        "KeySpeciesAbsorptionCoefficientsLowerAtmos": ("GPointSet", "band", "GPoint", "plower", "Tdiff", "keylower"),
+        "KeySpeciesAbsorptionCoefficientsUpperAtmos": ("GPointSet", "band", "GPoint", "pupper", "Tdiff", "keyupper"),
+        "H20SelfAbsorptionCoefficients": ("GPointSet", "band", "GPoint", "Tself"),
+        "H20ForeignAbsorptionCoefficients": ("GPointSet", "band", "GPoint", "Tforeign"),
+        "PlanckFractionLowerAtmos": ("GPointSet", "band", "keylower", "GPoint"),
+        "PlanckFractionUpperAtmos": ("GPointSet", "band", "keyupper", "GPoint"),
+        "AbsorptionCoefficientsLowerAtmos": ("GPointSet", "band", "Absorber", "GPoint", "T", "keylower"),
+        "AbsorptionCoefficientsUpperAtmos": ("GPointSet", "band", "Absorber", "GPoint", "T", "keyupper"),
+    }
+    data = {k: np.zeros([dims[d] for d in v]) for k, v in spec.items()}
+    kl, ku = data["KeySpeciesAbsorptionCoefficientsLowerAtmos"][0], data["KeySpeciesAbsorptionCoefficientsUpperAtmos"][0]
+    sf, fr = data["H20SelfAbsorptionCoefficients"][0], data["H20ForeignAbsorptionCoefficients"][0]
+    pl, pu = data["PlanckFractionLowerAtmos"][0], data["PlanckFractionUpperAtmos"][0]
+    ml, mu = data["AbsorptionCoefficientsLowerAtmos"][0], data["AbsorptionCoefficientsUpperAtmos"][0]
+    for band, name, lead, gfirst, _ in karrays():
+        b = band - 1
+        a = np.asarray(arrays[(band, name)], dtype=np.float64)
+        if name == "kao":
+            kl[b][:, :, :, :NSPA[b]] = a.reshape((NSPA[b], 5, 13, 16), order="F").transpose(3, 2, 1, 0)
+        elif name == "kbo":
+            nsp = max(NSPB[b], 1)
+            ku[b][:, :, :, :nsp] = a.reshape((nsp, 5, 47, 16), order="F").transpose(3, 2, 1, 0)
+        elif name == "selfrefo":
+            sf[b] = a.T
+        elif name == "forrefo":
+            fr[b] = a.T
+        elif name == "fracrefao":
+            pl[b][:lead] = a.T
+        elif name == "fracrefbo":
+            pu[b][:lead] = a.T
+        else:
+            key = name.split("_", 1)[1] if "_" in name else name
+            ab = _ABSORBER[_MINOR_OF[key]] - 1
+            dst = ml if (name.startswith("kao") or name in _MINOR_OF) else mu
+            if lead == 1:
+                dst[b, ab][:, 0, 0] = a[0]
+            elif lead == 19:
+                dst[b, ab][:, :, 0] = a.T
+            else:
+                dst[b, ab][:, :, :lead // 19] = a.reshape((lead // 19, 19, 16), order="F").transpose(2, 1, 0)
+    f = netcdf_file(path, "w")
+    for d, n in dims.items():
+        f.createDimension(d, n)
+    for k, v in spec.items():
+        var = f.createVariable(k, "d", v)
+        var[:] = data[k]
+    f.close()

@@ -177,3 +177,34 @@ def test_synth_batch_shapes():
     assert float(b.rei.min()) >= 5 and float(b.rei.max()) <= 140 and float(b.rel.min()) >= 2.5
     b2 = synth.make_batch(33, 72, cloudy=True, aerosol=True)
     assert bool((b.h2ovmr == b2.h2ovmr).all())  # deterministic
+
+
+def test_netcdf_ingest_round_trip(tmp_path):
+    """kdata.load_netcdf (the ingest of rrtmg_lw.nc per src/rrtmg_lw_read_nc.f90: variable names, hyperslab
+    starts/counts, absorber order of modules/rrlw_ncpar.f90:15-44) reads back exactly what kdata.save_netcdf lays
+    out with the reference's dimensions -- every one of the k-arrays, bit for bit; band 1's slabs are also checked
+    by hand against the start/count vectors of lw_kgb01 (read_nc.f90:64-105)."""
+    from scipy.io import netcdf_file
+    from rrtmg_lw_b200 import kdata
+    arrs = kdata.synthetic_kdata()
+    p = str(tmp_path / "rrtmg_lw.nc")
+    kdata.save_netcdf(p, arrs)
+    back = kdata.load_netcdf(p)
+    assert set(back) == set(arrs)
+    for k in arrs:
+        assert back[k].shape == arrs[k].shape and np.array_equal(back[k], arrs[k]), k
+    assert np.array_equal(kdata.pack(back), kdata.pack(arrs))
+    f = netcdf_file(p, "r", mmap=False)
+    v = f.variables
+    # Fortran start (1,1,band=1,set=1), count (16,1,1,1) on (GPoint, keylower, band, set) == C [0, 0, 0, :]
+    assert np.array_equal(v["PlanckFractionLowerAtmos"][:][0, 0, 0, :], arrs[(1, "fracrefao")][:, 0])
+    assert v["KeySpeciesAbsorptionCoefficientsLowerAtmos"].shape == (2, 16, 16, 13, 5, 9)
+    assert v["AbsorptionCoefficientsUpperAtmos"].shape == (2, 16, 12, 16, 19, 5)
+    # kao(jt, jp, ig) of band 1 (one key species): count (1, Tdiff, plower, 16, 1, 1)
+    kao = arrs[(1, "kao")].reshape((1, 5, 13, 16), order="F")
+    assert v["KeySpeciesAbsorptionCoefficientsLowerAtmos"][:][0, 0, 7, 11, 3, 0] == kao[0, 3, 11, 7]
+    # kao_mn2(T, ig): absorber 'N2' = index 1, count (1, T, 16, 1, 1, 1)
+    assert np.array_equal(v["AbsorptionCoefficientsLowerAtmos"][:][0, 0, 0, :, :, 0].T, arrs[(1, "kao_mn2")])
+    # selfrefo(Tself, ig): count (Tself, 16, 1, 1)
+    assert np.array_equal(v["H20SelfAbsorptionCoefficients"][:][0, 0].T, arrs[(1, "selfrefo")])
+    f.close()
