@@ -146,7 +146,10 @@ int rrtmg_lw_b200_set_chunk(int max_columns);
  * H2D copy of pass k+1 and the D2H copy of pass k-1 overlap the kernels of pass k.  "precision": 64 (default) or 32 = the optional
  * FP32 mode of BASELINE.json's north star: float band kernels (taumol, cldprmc, rtrnmc) with double flux
  * accumulators for clear sky and the fused McICA entry, within 0.05 W m-2 / 0.01 K day-1 of the FP64 results;
- * setcoef indices and McICA masks are unchanged. */
+ * setcoef indices and McICA masks are unchanged.  "mt_global_ncol" / "mt_col_offset" (irng = 1 only): the columns of
+ * the following calls are columns [offset, offset + ncol) of a batch of mt_global_ncol columns; the single
+ * Mersenne-Twister stream of that batch (src/mcica_subcol_gen_lw.f90:523-530) is stepped over the other blocks'
+ * words, so a column-sharded run reproduces the unsharded one (0 = off: every call is its own stream). */
 int rrtmg_lw_b200_set_option(const char* name, int value);
 
 /* Host-only self test of the n-step jumps of the KISS generator used by the sub-column-parallel

@@ -211,6 +211,16 @@ def set_option(name, value):
         raise RrtmgLwError(rc, "set_option(%s)" % name)
 
 
+def set_mt_block(global_ncol: int, col_offset: int = 0):
+    """``irng = 1`` on a sharded batch: the columns of the following calls are columns
+    ``[col_offset, col_offset + ncol)`` of a batch of ``global_ncol`` columns, and the library steps the single
+    Mersenne-Twister stream of that batch (sub-column, column, layer order,
+    ``src/mcica_subcol_gen_lw.f90:523-530``) over the words of the other blocks, so every rank reproduces exactly
+    what one unsharded call would draw.  ``set_mt_block(0)`` switches it off."""
+    set_option("mt_global_ncol", int(global_ncol))
+    set_option("mt_col_offset", int(col_offset) if global_ncol else 0)
+
+
 def launch_count(reset=False):
     return int(lib().rrtmg_lw_b200_launch_count(1 if reset else 0))
 

@@ -52,6 +52,9 @@ struct Ctx {
     bool timing = false;
     // Mersenne-Twister stream bookkeeping of a staged host call: columns of the whole call / first column of the pass
     long mt_total = 0, mt_base = 0;
+    // set_option("mt_global_ncol" / "mt_col_offset"): the call's columns are columns [offset, offset + ncol) of a
+    // larger batch of mt_global_ncol columns whose single Mersenne-Twister stream is to be reproduced (sharded runs)
+    long mt_opt_total = 0, mt_opt_base = 0;
     float ms_band = 0.f, ms_all = 0.f;
     float ms_bands[NBND] = {};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -226,7 +229,10 @@ int run_device(Mode mode, int ncol, int nlay, int icld, int idrv, int inflag, in
                 launch_mcica_kiss(in, S, r, st); G.launches++;
             } else {
                 // one global stream over (sub-column, column, layer): position of this chunk inside the whole call
-                const int nl = launch_mcica_mt(in, S, r, G.mt_total ? G.mt_total : ncol, G.mt_base + c0, st);
+                const long mt_tot = G.mt_total ? G.mt_total : (G.mt_opt_total ? G.mt_opt_total : (long)ncol);
+                const long mt_b0 = G.mt_total ? G.mt_base : G.mt_opt_base;
+                if (mt_b0 + ncol > mt_tot) return RRTMG_LW_ERR_ARG;
+                const int nl = launch_mcica_mt(in, S, r, mt_tot, mt_b0 + c0, st);
                 if (nl < 0) return RRTMG_LW_ERR_CUDA;
                 G.launches += nl;
             }
@@ -349,7 +355,7 @@ int host_pipeline(Mode mode, int ncol, int ld, int nlay, int icld, int idrv, int
         const long dbg_save = G.dbg_col;
         if (G.dbg) G.dbg_col = dbg_save - c0;  // chunk-relative for the staged pass
         G.chunk = chunk;
-        G.mt_total = ncol; G.mt_base = c0;
+        G.mt_total = G.mt_opt_total ? G.mt_opt_total : (long)ncol; G.mt_base = G.mt_opt_base + c0;
         rc = run_device(mode, nc, nlay, icld, idrv, inflag, iceflag, liqflag, permuteseed, irng, in, out, st);
         G.mt_total = 0; G.mt_base = 0;
         G.chunk = saved_chunk;
@@ -714,7 +720,8 @@ extern "C" int rrtmg_lw_b200_mcica_subcol_lw(int iplon, int ncol, int ld, int nl
         in.nlay = nlay;
         auto generate = [&]() -> int {
             if (*irng == 0) { launch_mcica_kiss(in, G.S, r, st); G.launches++; return 0; }
-            const int nl = launch_mcica_mt(in, G.S, r, ncol, c0, st);
+            if (G.mt_opt_base + ncol > (G.mt_opt_total ? G.mt_opt_total : (long)ncol)) return RRTMG_LW_ERR_ARG;
+            const int nl = launch_mcica_mt(in, G.S, r, G.mt_opt_total ? G.mt_opt_total : (long)ncol, G.mt_opt_base + c0, st);
             if (nl < 0) return RRTMG_LW_ERR_CUDA;
             G.launches += nl;
             return 0;
@@ -870,6 +877,18 @@ extern "C" int rrtmg_lw_b200_set_option(const char* name, int value) {
         // 64 (default) or 32: float band kernels (fluxes within 0.05 W m-2, heating rates within 0.01 K/day of FP64)
         if (value != 64 && value != 32) return RRTMG_LW_ERR_ARG;
         G.precision = value;
+        return RRTMG_LW_OK;
+    }
+    if (std::strcmp(name, "mt_global_ncol") == 0) {
+        // irng = 1 only: the columns of the following calls are a block of a batch of `value` columns (0 = off)
+        if (value < 0) return RRTMG_LW_ERR_ARG;
+        G.mt_opt_total = value;
+        if (value == 0) G.mt_opt_base = 0;
+        return RRTMG_LW_OK;
+    }
+    if (std::strcmp(name, "mt_col_offset") == 0) {
+        if (value < 0) return RRTMG_LW_ERR_ARG;
+        G.mt_opt_base = value;
         return RRTMG_LW_OK;
     }
     if (std::strcmp(name, "host_chunk") == 0) {

@@ -4,7 +4,9 @@ Columns are independent (``src/rrtmg_lw_rad.f90:486``) and the KISS McICA stream
 column (``src/mcica_subcol_gen_lw.f90:467-470``), so the column axis is block-partitioned and the
 data path needs NO collective; the only exchange is the optional gather of the flux / heating-rate
 arrays.  The Mersenne-Twister stream (``irng=1``) is one sequence over (sub-column, column, layer)
-whose values depend on how the batch is split, so it is refused here.
+whose values depend on how the batch is split: it is refused unless the caller hands in
+``mt_block`` (``api.set_mt_block`` on the GPU box), which tells the library where the rank's block sits
+in the global stream so that each rank steps over the other ranks' words.
 
 Pure plumbing: nothing in this module computes radiation.
 """
@@ -145,17 +147,27 @@ def pipelined_gather(ncol_total: int, rows, run_chunk, nchunks: int = 4, dst: in
     return out
 
 
-def run_sharded(b: "synth.Batch", run_local, idrv: int = 0, irng: int = 0, gather_to: int | None = None, group=None):
+def run_sharded(b: "synth.Batch", run_local, idrv: int = 0, irng: int = 0, gather_to: int | None = None, group=None,
+                mt_block=None):
     """Run ``run_local(shard) -> dict`` on this rank's column block and gather the outputs.
 
     ``run_local`` is the caller's per-rank invocation of the CUDA path (``driver.run_fused`` on the
     GPU box); tests substitute a stand-in to exercise the partition/gather logic on CPU.
+    ``mt_block(global_ncol, col_offset)`` (``api.set_mt_block``) is required for ``irng = 1``; it is called with
+    the batch size and the block's first column before ``run_local`` and with ``(0, 0)`` after it.
     """
-    if irng != 0:
+    if irng != 0 and mt_block is None:
         raise ValueError("irng=1 (Mersenne Twister) is one global stream over all columns of a call; "
-                         "its values depend on the partition -- use irng=0 (KISS) on the sharded path")
+                         "its values depend on the partition -- use irng=0 (KISS) on the sharded path, "
+                         "or pass mt_block=api.set_mt_block")
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     shard = shard_batch(b, world, rank)
-    local = run_local(shard)
+    if irng != 0:
+        mt_block(b.ncol, block_range(b.ncol, world, rank)[0])
+    try:
+        local = run_local(shard)
+    finally:
+        if irng != 0:
+            mt_block(0, 0)
     return gather_outputs(local, b.ncol, idrv=idrv, dst=gather_to, group=group)

@@ -332,6 +332,48 @@ def test_mersenne_twister_fused_matches_oracle(gpu, oracle):
         gpu.set_option("host_chunk", 32768)
 
 
+@pytest.mark.parametrize("icld", [2, 5])
+def test_mersenne_twister_blocks_of_a_sharded_batch(gpu, oracle, icld):
+    """with set_mt_block(global_ncol, offset) a call on a column block draws exactly the words the
+    unsharded call would draw for those columns (the other blocks' words are stepped over) -- masks bit-equal to the
+    oracle's one-stream run over the whole batch, fused fluxes within tolerance, for an uneven 3-way split, on device
+    and host pointers, also when the library cuts the block into passes."""
+    from rrtmg_lw_b200 import sharding
+    b = synth.make_batch(301, 72, cloudy=True)
+    al = oracle.get_alpha(b, icld, idcor=1, juldat=200) if icld >= 4 else None
+    mc = oracle.mcica_subcol_lw(b, icld, permuteseed=9, irng=1, alpha=al)
+    ref = oracle.rrtmg_lw(b, icld=icld, idrv=0, inflglw=2, iceflglw=3, liqflglw=1, mc=mc, nthreads=8)
+    assert ref["rc"] == 0
+    try:
+        for world, chunk, device in ((3, 262144, "cuda:0"), (2, 64, "cuda:0"), (3, 262144, None)):
+            gpu.set_chunk(chunk)
+            masks, flux = [], {k: [] for k in KEYS}
+            for rank in range(world):
+                lo, hi = sharding.block_range(b.ncol, world, rank)
+                sh = sharding.shard_batch(b, world, rank)
+                a = None if al is None else np.ascontiguousarray(al[:, lo:hi])
+                gpu.set_mt_block(b.ncol, lo)
+                m = driver.run_mcica_subcol(sh, icld, permuteseed=9, irng=1, alpha=a, device=device)
+                masks.append(_np(m["cldfmcl"]))
+                o = driver.run_fused(sh, icld=icld, permuteseed=9, irng=1, alpha=a, device=device)
+                gpu.sync()
+                for k in KEYS:
+                    flux[k].append(_np(o[k]))
+            assert np.array_equal(np.concatenate(masks, axis=1), mc["cldfmcl"]), (icld, world, chunk, device)
+            _check({k: np.concatenate(v, axis=1) for k, v in flux.items()}, ref, what="MT blocks %s" % ((world, chunk, device),))
+        # a block that does not fit the declared batch is refused
+        gpu.set_mt_block(100, 50)
+        with pytest.raises(Exception):
+            driver.run_fused(sharding.shard_batch(b, 2, 0), icld=icld, permuteseed=9, irng=1,
+                             alpha=None if al is None else np.ascontiguousarray(al[:, :151]), device="cuda:0")
+    finally:
+        gpu.set_mt_block(0)
+        gpu.set_chunk(262144)
+    # switched off: a call is its own stream again
+    got = driver.run_mcica_subcol(b, icld, permuteseed=9, irng=1, alpha=al, device="cuda:0")
+    assert np.array_equal(_np(got["cldfmcl"]), mc["cldfmcl"])
+
+
 def test_fp32_mode_within_north_star_tolerance(gpu, oracle):
     """Optional FP32 mode (set_option("precision", 32)): the float band kernels (same source as the FP64 ones,
     tools/gen_fp32.py) must stay within 0.05 W m-2 / 0.01 K day-1 of the FP64 oracle (BASELINE.json north_star);

@@ -67,6 +67,23 @@ def _worker(rank, world, port, ncol, nlay, q):
         assert (only0 is None) == (rank != 0)
         with pytest.raises(ValueError):
             sharding.run_sharded(b, run_local, irng=1)
+        # irng = 1 with the stream-position hook: called with (batch size, first column of the block), then reset;
+        # the stand-in draws the WHOLE batch's Mersenne-Twister masks with the checker and keeps its block, which is
+        # what the library's stepping over the other blocks' words must reproduce (tests/test_gpu_parity.py)
+        seen = []
+        lo_, hi_ = sharding.block_range(ncol, world, rank)
+        mc_all = orc.mcica_subcol_lw(b, 2, permuteseed=5, irng=1)
+
+        def run_local_mt(shard):
+            assert seen == [(ncol, lo_)]
+            mc = {k: (np.ascontiguousarray(v[:, lo_:hi_]) if isinstance(v, np.ndarray) else v) for k, v in mc_all.items()}
+            r = orc.rrtmg_lw(shard, icld=2, idrv=0, inflglw=2, iceflglw=3, liqflglw=1, mc=mc, nthreads=1)
+            return {k: torch.from_numpy(np.ascontiguousarray(r[k])) for k in sharding.OUT_KEYS}
+
+        full_mt = sharding.run_sharded(b, run_local_mt, irng=1, mt_block=lambda n, o: seen.append((n, o)))
+        assert seen == [(ncol, lo_), (0, 0)]
+        ref_mt = orc.rrtmg_lw(b, icld=2, idrv=0, inflglw=2, iceflglw=3, liqflglw=1, mc=mc_all, nthreads=1)
+        assert all(np.array_equal(full_mt[k].numpy(), ref_mt[k]) for k in sharding.OUT_KEYS)
         # pipelined variant: the rank's block in 3 column chunks, each chunk's gather issued before the next chunk
         # is computed (ragged: 37 columns -> blocks 19 + 18, chunks of 7 -> 7 + 7 + 5 | 7 + 7 + 4)
         shard = sharding.shard_batch(b, world, rank)
