@@ -85,9 +85,26 @@
          import :: c_int, c_ptr
          integer(c_int), value :: code
          end function
+
+         ! run-time switches without a reference counterpart (include/rrtmg_lw_b200.h, INTEGRATION.md section 6)
+         integer(c_int) function c_set_option(name, value) bind(C, name='rrtmg_lw_b200_set_option')
+         import :: c_int, c_char
+         character(kind=c_char), intent(in) :: name(*)
+         integer(c_int), value :: value
+         end function
       end interface
 
       contains
+
+      ! irng = 1 on a column-sharded batch (one MPI rank per GPU): this rank's calls carry columns
+      ! [col_offset+1, col_offset+ncol] of a batch of global_ncol columns; the library steps the batch's single
+      ! Mersenne-Twister stream (src/mcica_subcol_gen_lw.f90:523-530) over the other ranks' words.
+      ! global_ncol = 0 switches it off.
+      subroutine rrtmg_lw_b200_set_mt_block(global_ncol, col_offset)
+      integer, intent(in) :: global_ncol, col_offset
+      call check(c_set_option('mt_global_ncol'//c_null_char, int(global_ncol, c_int)), 'set_option(mt_global_ncol)')
+      call check(c_set_option('mt_col_offset'//c_null_char, int(col_offset, c_int)), 'set_option(mt_col_offset)')
+      end subroutine rrtmg_lw_b200_set_mt_block
 
       ! reference behaviour on these conditions is STOP 'text' (e.g. src/rrtmg_lw_cldprmc.f90:204)
       subroutine check(rc, where)
