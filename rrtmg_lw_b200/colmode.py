@@ -25,7 +25,6 @@ column-mode program (they come from driving the GCM entry, not from this file):
 """
 from __future__ import annotations
 
-import math
 from dataclasses import dataclass, field
 
 import numpy as np
