@@ -137,7 +137,7 @@ def run_reference(args, rank):
     from rrtmg_lw_b200 import kdata
     orc.ini(kdata.synthetic_blob(), 1004.0, 4)
     cores = os.cpu_count() or 1
-    ncol = min(args.ref_cols or 256 * cores, 65536)
+    ncol = min(args.ref_cols or 2048 * cores, 65536)   # ~1 s per step on all cores; a 5+3-step run stays under a minute
     ncol = max(ncol, 512)
     for w in range(max(args.warmup, 1)):
         cpu_sample_run(min(ncol, 64 * cores), cores, seed_off=w)
@@ -446,7 +446,7 @@ def main():
             from oracle import orc
             orc.ini(blob, 1004.0, 4)
             cores = os.cpu_count() or 1
-            nc = max(512, min(192 * cores, 32768))
+            nc = max(512, min(2048 * cores, 32768))   # ~20 core-seconds of CPU work
             cpu_sample_run(min(nc, 32 * cores), cores)
             tc = cpu_sample_run(nc, cores, seed_off=3)
             res["cpu_baseline"] = {"value": nc / tc, "unit": "columns/s", "cores": cores, "kind": "port",
