@@ -372,6 +372,9 @@ def main():
                 if tj.get("band_kernel") == args.band_kernel:
                     roof["traffic"] = tj["dram_bytes_per_column"] * ncol
                     roof["traffic_note"] = tj.get("note")
+                    # what the band kernels actually pull through DRAM (scratch included) against the same peak
+                    roof["hbm"]["traffic_gbs"] = roof["traffic"] / (ms_band * 1e-3) / 1e9
+                    roof["hbm"]["traffic_frac"] = roof["hbm"]["traffic_gbs"] / hbm_peak
             except (OSError, ValueError, KeyError):
                 pass
         res = {
