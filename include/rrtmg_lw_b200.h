@@ -130,26 +130,34 @@ int rrtmg_lw_b200_debug_capture(int icol_plus_1);
 int rrtmg_lw_b200_debug_stages(int icol, int* ints6, double* facs, double* taug, double* fracs, int* itr,
                                double* scal, unsigned char* mask);
 
-/* Readback of an init-time table for parity tests: "tau_tbl","exp_tbl","tfn_tbl","rwgt" or
+/* Readback of an init-time table for parity tests: "tau_tbl","exp_tbl","tfn_tbl","rwgt", the rrlw_con scalars
+ * "heatfac" / "fluxfac" (what a column-mode driver needs for its idrv adjustment, src/rrtmg_lw.1col.f90:587-610) or
  * "<band>:<reduced array name>" (e.g. "3:absa", reference element order).  Returns the element
  * count (0 = unknown name); copies min(count, cap) doubles when out != NULL. */
 long rrtmg_lw_b200_get_table(const char* name, double* out, long cap);
 
 /* Upper bound of columns processed per internal pass of a device-pointer call (default 262144; scratch is
- * sized to min(ncol, max_columns), about 70 KB per column). */
+ * sized to min(ncol, max_columns): about 1.3 KB per (column, layer) on the default two-phase path). */
 int rrtmg_lw_b200_set_chunk(int max_columns);
 
-/* Tuning switches (no reference counterpart).  "band_kernel": 2 (default) = one thread per
- * (column, band) with the band's g-points in registers; 3 = g-points spread over the lanes of a
- * unit with the exp/tfn table in shared memory (lw_gband.cuh).  "host_chunk": columns per staged
- * pass of a host-pointer call (default 32768); passes alternate between two staging arenas so the
- * H2D copy of pass k+1 and the D2H copy of pass k-1 overlap the kernels of pass k.  "precision": 64 (default) or 32 = the optional
- * FP32 mode of BASELINE.json's north star: float band kernels (taumol, cldprmc, rtrnmc) with double flux
- * accumulators for clear sky and the fused McICA entry, within 0.05 W m-2 / 0.01 K day-1 of the FP64 results;
- * setcoef indices and McICA masks are unchanged.  "mt_global_ncol" / "mt_col_offset" (irng = 1 only): the columns of
- * the following calls are columns [offset, offset + ncol) of a batch of mt_global_ncol columns; the single
- * Mersenne-Twister stream of that batch (src/mcica_subcol_gen_lw.f90:523-530) is stepped over the other blocks'
- * words, so a column-sharded run reproduces the unsharded one (0 = off: every call is its own stream). */
+/* Tuning switches (no reference counterpart).
+ * "band_kernel": 4 (default) = two-phase path: inatm + setcoef + taumol with one thread per (column, layer), then
+ *   cldprmc + rtrnmc sweep kernels with one thread per (column, band group) that stream the 8-byte layer optical
+ *   depths; 2 = fused per-band kernels (one thread per (column, band), 16-byte sweep state; the optional FP32 mode
+ *   runs on these).
+ * "sweep_groups": 1 (default) = sweep kernels over band groups {1,2} {3} {4} {5} {6,7} {8,9} {10-12} {13-16};
+ *   0 = one sweep kernel per band.
+ * "band_lo" / "band_hi": band range istart..iend of the following runs (default 1..16): only those bands enter the
+ *   flux sums, as in the column-mode program's per-band output (src/rrtmg_lw.1col.f90:463-467); two-phase path.
+ * "host_chunk": columns per staged pass of a host-pointer call (default 32768); passes alternate between two
+ *   staging arenas so the H2D copy of pass k+1 and the D2H copy of pass k-1 overlap the kernels of pass k.
+ * "precision": 64 (default) or 32 = the optional FP32 mode of BASELINE.json's north star: float band kernels
+ *   (taumol, cldprmc, rtrnmc) with double flux accumulators for clear sky and the fused McICA entry, within
+ *   0.05 W m-2 / 0.01 K day-1 of the FP64 results; setcoef indices and McICA masks are unchanged.
+ * "mt_global_ncol" / "mt_col_offset" (irng = 1 only): the columns of the following calls are columns
+ *   [offset, offset + ncol) of a batch of mt_global_ncol columns; the single Mersenne-Twister stream of that batch
+ *   (src/mcica_subcol_gen_lw.f90:523-530) is reproduced for the block, so a column-sharded run equals the unsharded
+ *   one (0 = off: every call is its own stream). */
 int rrtmg_lw_b200_set_option(const char* name, int value);
 
 /* Host-only self test of the n-step jumps of the KISS generator used by the sub-column-parallel
@@ -162,8 +170,16 @@ long rrtmg_lw_b200_launch_count(int reset);
  * call when timing capture is enabled with rrtmg_lw_b200_set_timing(1). */
 int rrtmg_lw_b200_set_timing(int enable);
 int rrtmg_lw_b200_last_timing(float* ms_band_kernels, float* ms_all_kernels);
-/* Same capture, per band: ms16[b-1] = CUDA-event time of band b's kernel summed over the passes. */
+/* Same capture, per band: ms16[b-1] = CUDA-event time of band b's kernel summed over the passes (fused band
+ * kernels; on the two-phase path slot 0 is the taumol kernel and slots 1.. the sweep kernels). */
 int rrtmg_lw_b200_last_band_timing(float* ms16);
+/* Same capture, per timed stage of the pipeline between the prep kernels and the finalize kernel: returns the number
+ * of stages n and copies min(n, cap) times (two-phase path: taumol, then each sweep kernel in launch order). */
+int rrtmg_lw_b200_last_stage_timing(float* ms, int cap);
+/* (column, layer), both 1-based, of the input error most recently reported by a compute entry or by
+ * rrtmg_lw_b200_sync; the column counts from the first column of the CALL, also for host-pointer calls that the
+ * library cuts into staged passes. */
+int rrtmg_lw_b200_last_error(int* col, int* lay);
 
 /* Measured FP64 FMA throughput of the current device in TFLOP/s (an FMA = 2 flops); the FP64
  * roofline denominator used by bench.py. */

@@ -22,8 +22,12 @@ _ip = C.POINTER(C.c_int)
 
 
 def build(force: bool = False):
-    if force or not os.path.exists(_LIB):
+    """(Re)build liborc.so / liborc_count.so when a source is newer than the library (make decides)."""
+    try:
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    except (OSError, subprocess.CalledProcessError):
+        if not os.path.exists(_LIB):   # no toolchain and no prebuilt library: nothing to check against
+            raise
 
 
 def lib():

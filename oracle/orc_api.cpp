@@ -209,6 +209,8 @@ extern "C" long orc_get_table(const char* name, double* out, long cap) {
     else if (n == "exp_tbl") { src = G.exp_tbl; cnt = NTBL + 1; }
     else if (n == "tfn_tbl") { src = G.tfn_tbl; cnt = NTBL + 1; }
     else if (n == "rwgt") { src = G.rwgt; cnt = 256; }
+    else if (n == "heatfac") { src = &G.heatfac; cnt = 1; }
+    else if (n == "fluxfac") { src = &G.fluxfac; cnt = 1; }
     else {
         size_t p = n.find(':');
         if (p == std::string::npos) return 0;

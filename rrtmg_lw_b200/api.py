@@ -40,6 +40,46 @@ class RrtmgLwError(RuntimeError):
         super().__init__("rrtmg_lw_b200 error %d%s: %s" % (code, (" in " + where) if where else "", msg))
 
 
+_ip = C.POINTER(C.c_int)
+_fp = C.POINTER(C.c_float)
+# argument and result types of every entry point of include/rrtmg_lw_b200.h (tests/test_abi_cpu.py checks the
+# argument counts against the header, so a mis-ordered or missing argument fails on the CPU already)
+SIGNATURES = {
+    "rrtmg_lw_b200_kdata_put": (C.c_int, [C.c_int, C.c_char_p, _dp, C.c_long]),
+    "rrtmg_lw_b200_ini": (C.c_int, [C.c_double, _dp, C.c_long, C.c_int]),
+    "rrtmg_lw_b200_rrtmg_lw": (C.c_int, [C.c_int, C.c_int, C.c_int, _ip, C.c_int] + [_dp] * 16 + [C.c_int] * 3 +
+                               [_dp] * 15 + [C.c_int, C.c_void_p]),
+    "rrtmg_lw_b200_rrtmg_lw_mcica": (C.c_int, [C.c_int] * 7 + [_dp] * 16 + [C.c_int] * 3 + [_dp] * 16 +
+                                     [C.c_int, C.c_void_p]),
+    "rrtmg_lw_b200_mcica_subcol_lw": (C.c_int, [C.c_int] * 6 + [_ip] + [_dp] * 14 + [C.c_int, C.c_void_p]),
+    "rrtmg_lw_b200_get_alpha": (C.c_int, [C.c_int] * 6 + [C.c_double, _dp, _dp, C.c_int, _dp, _dp, C.c_int, C.c_void_p]),
+    "rrtmg_lw_b200_sync": (C.c_int, [_ip, _ip]),
+    "rrtmg_lw_b200_last_error": (C.c_int, [_ip, _ip]),
+    "rrtmg_lw_b200_debug_capture": (C.c_int, [C.c_int]),
+    "rrtmg_lw_b200_debug_stages": (C.c_int, [C.c_int, _ip, _dp, _dp, _dp, _ip, _dp, C.POINTER(C.c_ubyte)]),
+    "rrtmg_lw_b200_get_table": (C.c_long, [C.c_char_p, _dp, C.c_long]),
+    "rrtmg_lw_b200_set_chunk": (C.c_int, [C.c_int]),
+    "rrtmg_lw_b200_set_option": (C.c_int, [C.c_char_p, C.c_int]),
+    "rrtmg_lw_b200_kiss_jump_selftest": (C.c_int, []),
+    "rrtmg_lw_b200_launch_count": (C.c_long, [C.c_int]),
+    "rrtmg_lw_b200_set_timing": (C.c_int, [C.c_int]),
+    "rrtmg_lw_b200_last_timing": (C.c_int, [_fp, _fp]),
+    "rrtmg_lw_b200_last_band_timing": (C.c_int, [_fp]),
+    "rrtmg_lw_b200_last_stage_timing": (C.c_int, [_fp, C.c_int]),
+    "rrtmg_lw_b200_fp64_peak": (C.c_int, [C.POINTER(C.c_double)]),
+    "rrtmg_lw_b200_strerror": (C.c_char_p, [C.c_int]),
+    "rrtmg_lw_b200_version": (C.c_char_p, []),
+    "rrtmg_lw_b200_finalize": (None, []),
+}
+
+
+def _declare(L):
+    for name, (res, args) in SIGNATURES.items():
+        f = getattr(L, name)
+        f.restype = res
+        f.argtypes = args
+
+
 def lib():
     """Load the CUDA library; raises if it has not been built (no fallback)."""
     global _lib
@@ -48,11 +88,7 @@ def lib():
             raise RuntimeError("librrtmg_lw_b200.so not built -- run `python -c 'import __graft_entry__ as g; "
                                "g.build()'` (there is no CPU fallback)")
         _lib = C.CDLL(LIB_PATH)
-        _lib.rrtmg_lw_b200_strerror.restype = C.c_char_p
-        _lib.rrtmg_lw_b200_version.restype = C.c_char_p
-        _lib.rrtmg_lw_b200_get_table.restype = C.c_long
-        _lib.rrtmg_lw_b200_launch_count.restype = C.c_long
-        _lib.rrtmg_lw_b200_ini.argtypes = [C.c_double, _dp, C.c_long, C.c_int]
+        _declare(_lib)
     return _lib
 
 
@@ -123,9 +159,7 @@ def kdata_put(band: int, name: str, array: np.ndarray):
     """Hand over one unreduced k-array (Fortran element order) -- what the Fortran shim does after
     the reference's ``lw_kgbNN``; ``rrtmg_lw_ini(cpdair, None)`` then consumes the staged arrays."""
     a = np.ascontiguousarray(np.asarray(array, dtype=np.float64).ravel(order="F"))
-    L = lib()
-    L.rrtmg_lw_b200_kdata_put.argtypes = [C.c_int, C.c_char_p, _dp, C.c_long]
-    rc = L.rrtmg_lw_b200_kdata_put(int(band), name.encode(), _ptr(a), a.size)
+    rc = lib().rrtmg_lw_b200_kdata_put(int(band), name.encode(), _ptr(a), a.size)
     if rc:
         raise RrtmgLwError(rc, "kdata_put(%d,%s)" % (band, name))
 
@@ -183,7 +217,7 @@ def get_alpha(iplon, ncol, nlayers, icld, idcor, decorr_con, dz, lat, juldat, cl
     arrs = [dz, lat, cldfrac, alpha]
     space = _space(arrs)
     rc = lib().rrtmg_lw_b200_get_alpha(int(iplon), int(ncol), int(ld or ncol), int(nlayers), int(icld), int(idcor),
-                                       C.c_double(decorr_con), _ptr(dz), _ptr(lat), int(juldat), _ptr(cldfrac),
+                                       float(decorr_con), _ptr(dz), _ptr(lat), int(juldat), _ptr(cldfrac),
                                        _ptr(alpha), space, _stream(space))
     if rc:
         raise RrtmgLwError(rc, "get_alpha")
@@ -205,7 +239,7 @@ def set_chunk(n):
 
 
 def set_option(name, value):
-    """Tuning switches of the library (``rrtmg_lw_b200_set_option``), e.g. ``("band_kernel", 3)``."""
+    """Tuning switches of the library (``rrtmg_lw_b200_set_option``), e.g. ``("band_kernel", 2)``."""
     rc = lib().rrtmg_lw_b200_set_option(str(name).encode(), int(value))
     if rc:
         raise RrtmgLwError(rc, "set_option(%s)" % name)
@@ -240,6 +274,21 @@ def last_band_timing():
     a = (C.c_float * 16)()
     lib().rrtmg_lw_b200_last_band_timing(a)
     return [float(x) for x in a]
+
+
+def last_stage_timing():
+    """CUDA-event milliseconds of each timed stage between the prep kernels and the finalize kernel of the last call
+    made with timing enabled (two-phase path: taumol, then every sweep kernel in launch order)."""
+    a = (C.c_float * 32)()
+    n = lib().rrtmg_lw_b200_last_stage_timing(a, 32)
+    return [float(a[k]) for k in range(max(0, min(n, 32)))]
+
+
+def last_error():
+    """(column, layer), 1-based, of the input error most recently reported (column of the CALL)."""
+    col, lay = C.c_int(0), C.c_int(0)
+    lib().rrtmg_lw_b200_last_error(C.byref(col), C.byref(lay))
+    return col.value, lay.value
 
 
 def debug_capture(col):

@@ -7,7 +7,7 @@ What the reference does (``src/rrtmg_lw.1col.f90``):
     records (icld = 4/5: idcor, decorr_con | juldat, lat), the layer records (form1/form2/form3,
     iform 0 or 1) and the optional cross-section block (``xsident`` :1296-1362);
   * ``readcld`` (:1139-1206) reads ``IN_CLD_RRTM``, ``readaer`` (:1209-1291) reads ``IN_AER_RRTM``;
-  * the main program (:440-705) runs ``nmca`` = 200 McICA samples with ``permuteseed = ims`` and
+  * the main program (:440-705) runs ``nmca`` = 200 McICA samples with ``permuteseed = ims * 140`` (``mcica_subcol_gen_lw.1col.f90:251``) and
     ``irng = 1`` (:417), averages them (:640-702), applies the idrv ``dtbound`` adjustment
     (:587-610) and writes ``OUTPUT_RRTM`` blocks (formats 9899-9958, :737-751).
 
@@ -30,6 +30,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 NBND = 16
+NGPT = 140            # nsubclw = ngptlw (modules/parrrtm.f90)
 NMCA = 200            # 1col:459-460
 
 _XS_ALIASES = (       # xsident's alias table, 1col:1313-1320 (index = slot in wx: ccl4, cfc11, cfc12, cfc22)
@@ -323,6 +324,11 @@ class GpuBackend:
     def _np(o):
         return {k: (v.detach().cpu().numpy() if hasattr(v, "detach") else v) for k, v in o.items()}
 
+    def heatfac(self):
+        """rrlw_con's heatfac as rrtmg_lw_ini set it (src/rrtmg_lw_init.f90:298)."""
+        from . import api
+        return float(api.get_table("heatfac")[0])
+
     def clear(self, b, idrv):
         from . import driver
         return self._np(driver.run_clear_or_strict(b, icld=0, idrv=idrv, device=self.device))
@@ -356,7 +362,9 @@ def run_case(c: Case, backend, nmca: int | None = None, irng: int = 1):
             alpha = None
             if c.icld in (4, 5):
                 alpha = backend.get_alpha(b, c.icld, c.idcor, c.decorr_con, c.juldat)
-            o = backend.mcica(b, c.icld, c.idrv, ims, irng, (c.inflag, c.iceflag, c.liqflag), alpha)
+            # the column-mode generator seeds every sample with permuteseed = ims * nsubclw
+            # (src/mcica_subcol_gen_lw.1col.f90:251, nsubclw = ngptlw = 140)
+            o = backend.mcica(b, c.icld, c.idrv, ims * NGPT, irng, (c.inflag, c.iceflag, c.liqflag), alpha)
         else:
             o = backend.clear(b, c.idrv)
         uflx = np.asarray(o["uflx"], dtype=np.float64).reshape(L + 1).copy()
@@ -365,7 +373,7 @@ def run_case(c: Case, backend, nmca: int | None = None, irng: int = 1):
         fnet = uflx - dflx
         if c.idrv == 1:                                                  # 1col:587-610
             d = np.asarray(o["duflx_dt"], dtype=np.float64).reshape(L + 1)
-            heatfac = _heatfac(htr, fnet, pz)
+            heatfac = backend.heatfac()
             uflx = uflx + d * c.dtbound
             fnet = uflx - dflx
             htr = np.concatenate([heatfac * (fnet[:-1] - fnet[1:]) / (pz[:-1] - pz[1:]), [0.0]])
@@ -376,15 +384,6 @@ def run_case(c: Case, backend, nmca: int | None = None, irng: int = 1):
     acc["pz"] = pz
     acc["nmca"] = n
     return acc
-
-
-def _heatfac(htr, fnet, pz):
-    """The library's heating-rate factor (``heatfac``, set by rrtmg_lw_ini from cpdair,
-    ``src/rrtmg_lw_init.f90:149-158``) recovered from its own output, so that the idrv re-computation
-    (1col:604-605) uses exactly the constant the kernels used."""
-    num = (fnet[:-1] - fnet[1:]) / (pz[:-1] - pz[1:])
-    j = int(np.argmax(np.abs(num)))
-    return float(htr[j] / num[j]) if num[j] != 0.0 else 0.0
 
 
 # ----------------------------------------------------------------------------------------------

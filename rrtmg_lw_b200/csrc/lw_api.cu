@@ -9,7 +9,7 @@
 
 #include "../../include/rrtmg_lw_b200.h"
 #include "../../include/rrtmg_lw_kdata_layout.h"
-#include "lw_gband.cuh"
+#include "lw_band.cuh"
 #include "lw_launch.h"
 
 // numeric blob of tools/extract_static_tables.py, embedded at build time
@@ -35,6 +35,7 @@ struct Ctx {
     Scratch S{};
     long cap_cols = 0;
     int cap_lay = 0;
+    unsigned have = 0;        // ScratchPiece bits allocated at the current capacity
     std::vector<void*> scratch_allocs;
     // host-mode staging arena
     double* stage = nullptr;
@@ -43,7 +44,10 @@ struct Ctx {
     int host_chunk = 32768;   // columns per staged pass of a host-pointer call (H2D / compute / D2H overlap)
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t e_in[2] = {nullptr, nullptr}, e_done[2] = {nullptr, nullptr}, e_out[2] = {nullptr, nullptr};
-    int band_kernel = 2;  // 2 = column-lane kernel (lw_band.cuh, fastest measured), 3 = g-lane kernel (lw_gband.cuh)
+    int band_kernel = 4;  // 4 = two-phase path (lw_taumol.cuh + lw_rtrnmc.cuh), 2 = fused per-band kernels (lw_band.cuh)
+    int sweep_groups = 1; // two-phase path: 1 = sweep kernels over the default band groups, 0 = one sweep kernel per band
+    int band_lo = 1, band_hi = NBND;  // band range of a run (two-phase path; the column-mode harness' istart / iend)
+    int nstage = 0;       // timed stages of the last timed pass (ms_bands[0 .. nstage))
     int sms = 0;
     long launches = 0;
     bool dbg = false;
@@ -55,10 +59,13 @@ struct Ctx {
     // set_option("mt_global_ncol" / "mt_col_offset"): the call's columns are columns [offset, offset + ncol) of a
     // larger batch of mt_global_ncol columns whose single Mersenne-Twister stream is to be reproduced (sharded runs)
     long mt_opt_total = 0, mt_opt_base = 0;
+    // (column, layer) of the input error a host-pointer call returned (1-based column of the CALL, not of the pass)
+    long last_err_col = 0, err_col0 = 0;
+    int last_err_lay = 0;
     float ms_band = 0.f, ms_all = 0.f;
-    float ms_bands[NBND] = {};
+    float ms_bands[NBND + 2] = {};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t evb[NBND + 1] = {};
+    cudaEvent_t evb[NBND + 3] = {};
     std::mutex mu;
 };
 Ctx G;
@@ -83,64 +90,79 @@ void free_scratch() {
     G.scratch_allocs.clear();
     G.cap_cols = 0;
     G.cap_lay = 0;
+    G.have = 0;
 }
 
-int ensure_scratch(long cols, int nlay) {
-    if (cols <= G.cap_cols && nlay <= G.cap_lay) return 0;
-    const unsigned long long* old_status = G.S.status;
-    (void)old_status;
-    free_scratch();
-    const long P = ((cols + 127) / 128) * 128;  // whole 128-column blocks (RunCfg::fld_block layouts)
+// what a pass needs from the scratch (allocated lazily, piece by piece: a path that is not used costs no memory)
+enum ScratchPiece {
+    SP_FUSED = 1,    // fused band kernels (band_kernel = 2): setcoef fields, packed indices, 16-byte sweep state
+    SP_TWOPHASE = 2, // two-phase path (band_kernel = 4): 8-byte optical depths, Planck-fraction etas, secdiff
+    SP_CLDB = 4,     // two-phase path, McICA mask entry: per-band cloud optical depth of cloudy layers
+    SP_GCLD = 8,     // two-phase path, strict rrtmg_lw() entry with clouds: per-g efclfrac / odcld
+    SP_FP32IN = 16,  // FP32 mode: float copies of the caller arrays
+};
+
+int ensure_scratch(long cols, int nlay, unsigned need) {
+    if (cols > G.cap_cols || nlay > G.cap_lay) {
+        free_scratch();
+        const long P = ((cols + 127) / 128) * 128;  // whole 128-column blocks
+        Scratch& S = G.S;
+        S = Scratch{};
+        S.pitch = P;
+        G.cap_cols = P;
+        G.cap_lay = nlay;
+    }
     Scratch& S = G.S;
-    S = Scratch{};
-    S.pitch = P;
+    const long P = S.pitch;
+    nlay = G.cap_lay;
     auto A = [&](auto** p, size_t n) -> int {
         int rc = dalloc(p, n);
         if (rc == 0) G.scratch_allocs.push_back((void*)*p);
         return rc;
     };
     const size_t plane = (size_t)nlay * P;
-    if (A(&S.fld, (size_t)NFIELD * plane)) return RRTMG_LW_ERR_CUDA;
-    if (A(&S.ipack, plane)) return RRTMG_LW_ERR_CUDA;
-    if (A(&S.pwvcm, (size_t)P)) return RRTMG_LW_ERR_CUDA;
-    if (A(&S.laytrop, (size_t)P)) return RRTMG_LW_ERR_CUDA;
-    if (A(&S.mask, 5 * plane)) return RRTMG_LW_ERR_CUDA;
-    if (A(&S.ctop, (size_t)P)) return RRTMG_LW_ERR_CUDA;
-    if (A(&S.state, (size_t)5 * 16 * plane)) return RRTMG_LW_ERR_CUDA;
-    if (A(&S.abscld, plane)) return RRTMG_LW_ERR_CUDA;
-    if (A(&S.fluxB, (size_t)6 * (nlay + 1) * P)) return RRTMG_LW_ERR_CUDA;
-    // FP32 mode: the float kernels reuse the same memory through float views; caller-array copies are extra
-    S.fldf = reinterpret_cast<float*>(S.fld);
-    S.statef = reinterpret_cast<float*>(S.state);
-    S.abscldf = reinterpret_cast<float*>(S.abscld);
-    if (A(&S.inf, (size_t)(40 * (size_t)(nlay + 1) + 32) * P)) return RRTMG_LW_ERR_CUDA;
-    if (A(&S.status, (size_t)1)) return RRTMG_LW_ERR_CUDA;
-    // g-lane path: layer-fastest copies, level-fastest band fluxes, per-resident-warp state slots
-    S.LP = ((nlay + 15) / 16) * 16;
-    S.LP1 = ((nlay + 1 + 15) / 16) * 16;
-    if (G.sms == 0) {
-        int dev = 0;
-        CK(cudaGetDevice(&dev));
-        CK(cudaDeviceGetAttribute(&G.sms, cudaDevAttrMultiProcessorCount, dev));
+    if (!S.status) {  // pieces every path uses
+        if (A(&S.pwvcm, (size_t)P)) return RRTMG_LW_ERR_CUDA;
+        if (A(&S.laytrop, (size_t)P)) return RRTMG_LW_ERR_CUDA;
+        if (A(&S.mask, 5 * plane)) return RRTMG_LW_ERR_CUDA;
+        if (A(&S.ctop, (size_t)P)) return RRTMG_LW_ERR_CUDA;
+        if (A(&S.fluxB, (size_t)6 * (nlay + 1) * P)) return RRTMG_LW_ERR_CUDA;
+        if (A(&S.status, (size_t)1)) return RRTMG_LW_ERR_CUDA;
+        CK(cudaMemset(S.status, 0, sizeof(unsigned long long)));
+        if (A(&S.dbg_taug, (size_t)NGPT * nlay)) return RRTMG_LW_ERR_CUDA;
+        if (A(&S.dbg_fracs, (size_t)NGPT * nlay)) return RRTMG_LW_ERR_CUDA;
+        if (A(&S.dbg_itr, (size_t)2 * NGPT * nlay)) return RRTMG_LW_ERR_CUDA;
+        if (A(&S.dbg_ints, (size_t)6 * nlay)) return RRTMG_LW_ERR_CUDA;
+        if (A(&S.dbg_facs, (size_t)4 * nlay)) return RRTMG_LW_ERR_CUDA;
+        if (A(&S.dbg_scal, (size_t)2)) return RRTMG_LW_ERR_CUDA;
+        S.dbg_col = -1;
     }
-    S.gwarps = G.sms * GB_WARPS;
-    if (A(&S.fldT, (size_t)NFIELD * P * S.LP)) return RRTMG_LW_ERR_CUDA;
-    if (A(&S.ipackT, (size_t)P * S.LP)) return RRTMG_LW_ERR_CUDA;
-    if (A(&S.maskT, (size_t)5 * P * S.LP)) return RRTMG_LW_ERR_CUDA;
-    if (A(&S.fluxT, (size_t)6 * P * S.LP1)) return RRTMG_LW_ERR_CUDA;
-    if (A(&S.fluxC, (size_t)6 * P * (nlay + 1))) return RRTMG_LW_ERR_CUDA;
-    if (A(&S.gstate, (size_t)S.gwarps * nlay * 128)) return RRTMG_LW_ERR_CUDA;
-    if (A(&S.gstateB, (size_t)S.gwarps * nlay * 256)) return RRTMG_LW_ERR_CUDA;
-    CK(cudaMemset(S.status, 0, sizeof(unsigned long long)));
-    if (A(&S.dbg_taug, (size_t)NGPT * nlay)) return RRTMG_LW_ERR_CUDA;
-    if (A(&S.dbg_fracs, (size_t)NGPT * nlay)) return RRTMG_LW_ERR_CUDA;
-    if (A(&S.dbg_itr, (size_t)2 * NGPT * nlay)) return RRTMG_LW_ERR_CUDA;
-    if (A(&S.dbg_ints, (size_t)6 * nlay)) return RRTMG_LW_ERR_CUDA;
-    if (A(&S.dbg_facs, (size_t)4 * nlay)) return RRTMG_LW_ERR_CUDA;
-    if (A(&S.dbg_scal, (size_t)2)) return RRTMG_LW_ERR_CUDA;
-    S.dbg_col = -1;
-    G.cap_cols = P;
-    G.cap_lay = nlay;
+    const unsigned miss = need & ~G.have;
+    if (miss & SP_FUSED) {
+        if (A(&S.fld, (size_t)NFIELD * plane)) return RRTMG_LW_ERR_CUDA;
+        if (A(&S.ipack, plane)) return RRTMG_LW_ERR_CUDA;
+        if (A(&S.state, (size_t)5 * 16 * plane)) return RRTMG_LW_ERR_CUDA;
+        if (A(&S.abscld, plane)) return RRTMG_LW_ERR_CUDA;
+        // FP32 mode: the float kernels reuse the same memory through float views
+        S.fldf = reinterpret_cast<float*>(S.fld);
+        S.statef = reinterpret_cast<float*>(S.state);
+        S.abscldf = reinterpret_cast<float*>(S.abscld);
+    }
+    if (miss & SP_TWOPHASE) {
+        if (A(&S.od, (size_t)NGPT * plane)) return RRTMG_LW_ERR_CUDA;
+        if (A(&S.pfs, (size_t)NPF * plane)) return RRTMG_LW_ERR_CUDA;
+        if (A(&S.secdiff, (size_t)NBND * P)) return RRTMG_LW_ERR_CUDA;
+    }
+    if (miss & SP_CLDB) {
+        if (A(&S.cldb, (size_t)2 * NBND * plane)) return RRTMG_LW_ERR_CUDA;
+    }
+    if (miss & SP_GCLD) {
+        if (A(&S.gcld, (size_t)2 * NGPT * plane)) return RRTMG_LW_ERR_CUDA;
+    }
+    if (miss & SP_FP32IN) {
+        if (A(&S.inf, (size_t)(40 * (size_t)(nlay + 1) + 32) * P)) return RRTMG_LW_ERR_CUDA;
+    }
+    G.have |= need;
     return 0;
 }
 
@@ -160,8 +182,10 @@ int decode_status(int* col, int* lay) {
     CK(cudaMemcpy(&v, G.S.status, sizeof(v), cudaMemcpyDeviceToHost));
     if (v == 0) return RRTMG_LW_OK;
     CK(cudaMemset(G.S.status, 0, sizeof(v)));
-    if (col) *col = (int)((v >> 24) & 0xffffffffull);
-    if (lay) *lay = (int)(v & 0xffffff);
+    G.last_err_col = (long)((v >> 24) & 0xffffffffull);
+    G.last_err_lay = (int)(v & 0xffffff);
+    if (col) *col = (int)G.last_err_col;
+    if (lay) *lay = G.last_err_lay;
     return (int)(v >> 56);
 }
 
@@ -179,12 +203,15 @@ bool launch_band32(int band, int cld, int idrv, const ColInF& in, const ColOut& 
            launch_band32_tu4(band, cld, idrv, in, out, s, r, st) || launch_band32_tu5(band, cld, idrv, in, out, s, r, st);
 }
 
-bool launch_gband(int band, int cld, int grid, const ColIn& in, const Scratch& s, const RunCfg& r, cudaStream_t st) {
-    return launch_gband_tu0(band, cld, grid, in, s, r, st) || launch_gband_tu1(band, cld, grid, in, s, r, st) ||
-           launch_gband_tu2(band, cld, grid, in, s, r, st) || launch_gband_tu3(band, cld, grid, in, s, r, st) ||
-           launch_gband_tu4(band, cld, grid, in, s, r, st) || launch_gband_tu5(band, cld, grid, in, s, r, st) ||
-           launch_gband_tu6(band, cld, grid, in, s, r, st) || launch_gband_tu7(band, cld, grid, in, s, r, st);
+// sweep kernels of bands [b0, b0 + nb) of the two-phase path
+bool launch_sweep(int b0, int nb, int cld, int idrv, const ColIn& in, const ColOut& out, const Scratch& s, const RunCfg& r,
+                  cudaStream_t st) {
+    return launch_sweep_stu1(b0, nb, cld, idrv, in, out, s, r, st) || launch_sweep_stu2(b0, nb, cld, idrv, in, out, s, r, st) ||
+           launch_sweep_stu3(b0, nb, cld, idrv, in, out, s, r, st) || launch_sweep_stu4(b0, nb, cld, idrv, in, out, s, r, st) ||
+           launch_sweep_stu5(b0, nb, cld, idrv, in, out, s, r, st);
 }
+// default band groups of the sweep kernels: {first band, bands}
+const int kSweepGroups[][2] = {{1, 2}, {3, 1}, {4, 1}, {5, 1}, {6, 2}, {8, 2}, {10, 3}, {13, 4}};
 
 enum Mode { MODE_STRICT = 0, MODE_FUSED = 1 };
 
@@ -194,17 +221,23 @@ int run_device(Mode mode, int ncol, int nlay, int icld, int idrv, int inflag, in
     if (nlay < 4 && mode == MODE_FUSED && icld > 0 && irng == 0) return RRTMG_LW_ERR_ARG;  // KISS seeds need 4 layers
     if (nlay < 1 || nlay > LW_MAXLAY) return RRTMG_LW_ERR_ARG;
     const int chunk = G.chunk;
-    int rc = ensure_scratch(ncol < chunk ? ncol : chunk, nlay);
-    if (rc) return rc;
     const int cld = icld == 0 ? CLD_NONE : (mode == MODE_FUSED ? CLD_MASK : CLD_ARRAYS);
+    // optional FP32 mode: float band kernels for clear sky and the fused McICA entry (fused band kernels only; the
+    // strict entry with per-g cloud arrays stays FP64)
+    const bool fp32 = G.precision == 32 && cld != CLD_ARRAYS;
+    const bool two_phase = G.band_kernel == 4 && !fp32;  // the FP32 mode lives in the fused band kernels
+    unsigned need = two_phase ? SP_TWOPHASE : SP_FUSED;
+    if (two_phase && cld == CLD_MASK) need |= SP_CLDB;
+    if (two_phase && cld == CLD_ARRAYS) need |= SP_GCLD;
+    if (fp32) need |= SP_FP32IN;
+    int rc = ensure_scratch(ncol < chunk ? ncol : chunk, nlay, need);
+    if (rc) return rc;
+    const int b_lo = G.band_lo, b_hi = G.band_hi;  // band range of the run (1..16 unless the band_lo / band_hi options say otherwise)
     if (G.timing) {
         for (auto& e : G.ev)
             if (!e) CK(cudaEventCreate(&e));
         for (auto& e : G.evb)
             if (!e) CK(cudaEventCreate(&e));
-        G.ms_band = 0.f;
-        G.ms_all = 0.f;
-        for (auto& m : G.ms_bands) m = 0.f;
     }
     for (long c0 = 0; c0 < ncol; c0 += chunk) {
         RunCfg r{};
@@ -214,16 +247,15 @@ int run_device(Mode mode, int ncol, int nlay, int icld, int idrv, int inflag, in
         r.idrv = idrv;
         r.inflag = inflag; r.iceflag = iceflag; r.liqflag = liqflag;
         r.icld = icld; r.irng = irng; r.permuteseed = permuteseed;
-        // optional FP32 mode: float band kernels for clear sky and the fused McICA entry (the strict entry with
-        // per-g cloud arrays and the g-lane kernel stay FP64)
-        const bool fp32 = G.precision == 32 && cld != CLD_ARRAYS && G.band_kernel != 3;
         r.fp32 = fp32 ? 1 : 0;
-        r.fld_block = G.band_kernel == 3 ? 0 : 1;
+        r.fld_block = 1;
         Scratch S = G.S;
+        S.err_base = G.err_col0;
         S.dbg_col = (G.dbg && G.dbg_col >= c0 && G.dbg_col < c0 + r.ncol) ? (int)(G.dbg_col - c0) : -1;
         if (S.dbg_col >= 0) G.dbg_nlay = nlay;
         if (G.timing) CK(cudaEventRecord(G.ev[0], st));
-        launch_prep(in, S, r, st); G.launches++;
+        if (two_phase) launch_colprep(in, S, r, st); else launch_prep(in, S, r, st);
+        G.launches++;
         if (cld == CLD_MASK) {
             if (irng == 0) {
                 launch_mcica_kiss(in, S, r, st); G.launches++;
@@ -238,27 +270,41 @@ int run_device(Mode mode, int ncol, int nlay, int icld, int idrv, int inflag, in
             }
         }
         if (cld == CLD_ARRAYS) { launch_cldflags(in, S, r, st); G.launches += 2; }
-        if (G.band_kernel == 3) { launch_transposes(S, r, cld != CLD_NONE, st); G.launches += cld != CLD_NONE ? 3 : 2; }
         if (G.timing) CK(cudaEventRecord(G.ev[1], st));
-        if (G.band_kernel == 3) {
-            for (int b = 1; b <= NBND; ++b) {
-                if (!launch_gband(b, cld, G.sms, in, S, r, st)) return RRTMG_LW_ERR_ARG;
+        int nstage = 0;  // timed stages between ev[1] and ev[2]
+        if (two_phase) {
+            if (G.timing) CK(cudaEventRecord(G.evb[nstage++], st));
+            launch_taumol(in, S, r, st); G.launches++;
+            bool first = true;
+            auto sweep = [&](int b0, int nb) -> bool {
+                if (G.timing) CK(cudaEventRecord(G.evb[nstage++], st)) ;
+                RunCfg rr = r;
+                rr.first_band = first ? 1 : 0;
+                first = false;
                 G.launches++;
+                return launch_sweep(b0, nb, cld, idrv, in, out, S, rr, st);
+            };
+            if (G.sweep_groups && b_lo == 1 && b_hi == NBND) {
+                for (const auto& g : kSweepGroups)
+                    if (!sweep(g[0], g[1])) return RRTMG_LW_ERR_ARG;
+            } else {
+                for (int b = b_lo; b <= b_hi; ++b)
+                    if (!sweep(b, 1)) return RRTMG_LW_ERR_ARG;
             }
+            if (G.timing) CK(cudaEventRecord(G.evb[nstage], st));
         } else {
             ColInF inf{};
             if (fp32) { G.launches += launch_cvt_inputs(in, S, r, cld != CLD_NONE, inflag, &inf, st); }
             for (int b = 1; b <= NBND; ++b) {
-                if (G.timing) CK(cudaEventRecord(G.evb[b - 1], st));
+                if (G.timing) CK(cudaEventRecord(G.evb[nstage++], st));
                 if (fp32 ? !launch_band32(b, cld, idrv, inf, out, S, r, st) : !launch_band(b, cld, idrv, in, out, S, r, st))
                     return RRTMG_LW_ERR_ARG;
                 G.launches++;
             }
-            if (G.timing) CK(cudaEventRecord(G.evb[NBND], st));
+            if (G.timing) CK(cudaEventRecord(G.evb[nstage], st));
         }
         if (G.timing) CK(cudaEventRecord(G.ev[2], st));
-        if (G.band_kernel == 3) launch_finalizeT(in, out, S, r, cld != CLD_NONE, st);
-        else launch_finalize(in, out, S, r, cld != CLD_NONE, st);
+        launch_finalize(in, out, S, r, cld != CLD_NONE, st);
         G.launches++;
         if (G.timing) {
             CK(cudaEventRecord(G.ev[3], st));
@@ -268,12 +314,12 @@ int run_device(Mode mode, int ncol, int nlay, int icld, int idrv, int inflag, in
             CK(cudaEventElapsedTime(&b, G.ev[0], G.ev[3]));
             G.ms_band += a;
             G.ms_all += b;
-            if (G.band_kernel != 3)
-                for (int k = 0; k < NBND; ++k) {
-                    float m = 0.f;
-                    CK(cudaEventElapsedTime(&m, G.evb[k], G.evb[k + 1]));
-                    G.ms_bands[k] += m;
-                }
+            G.nstage = nstage;
+            for (int k = 0; k < nstage; ++k) {
+                float m = 0.f;
+                CK(cudaEventElapsedTime(&m, G.evb[k], G.evb[k + 1]));
+                G.ms_bands[k] += m;
+            }
         }
         CK(cudaGetLastError());
     }
@@ -334,6 +380,14 @@ int host_pipeline(Mode mode, int ncol, int ld, int nlay, int icld, int idrv, int
     rc = ensure_stage(2 * half);
     if (rc) return rc;
     const int saved_chunk = G.chunk;
+    // every exit, error or not, first drains the three streams: the caller may free or reuse its (pinned) arrays
+    // as soon as the call returns
+    auto drain = [&](int code) {
+        cudaStreamSynchronize(G.s_in);
+        cudaStreamSynchronize(st);
+        cudaStreamSynchronize(G.s_out);
+        return code;
+    };
     int k = 0;
     for (long c0 = 0; c0 < ncol; c0 += chunk, ++k) {
         const int a = k & 1;
@@ -342,7 +396,7 @@ int host_pipeline(Mode mode, int ncol, int ld, int nlay, int icld, int idrv, int
         Stager sg{G.stage + (size_t)a * half, 0, P, G.s_in};
         ColIn in{};
         rc = stage_in(sg, in, c0, nc);
-        if (rc) return rc;
+        if (rc) return drain(rc);
         in.ld = P; in.nlay = nlay;
         ColOut out{};
         out.ld = P;
@@ -350,32 +404,40 @@ int host_pipeline(Mode mode, int ncol, int ld, int nlay, int icld, int idrv, int
         out.uflxc = sg.carve((size_t)P * (nlay + 1)); out.dflxc = sg.carve((size_t)P * (nlay + 1));
         out.duflx_dt = sg.carve((size_t)P * (nlay + 1)); out.duflxc_dt = sg.carve((size_t)P * (nlay + 1));
         out.hr = sg.carve((size_t)P * nlay); out.hrc = sg.carve((size_t)P * nlay);
-        CK(cudaEventRecord(G.e_in[a], G.s_in));
-        CK(cudaStreamWaitEvent(st, G.e_in[a], 0));
+        if (cudaEventRecord(G.e_in[a], G.s_in) != cudaSuccess || cudaStreamWaitEvent(st, G.e_in[a], 0) != cudaSuccess)
+            return drain(RRTMG_LW_ERR_CUDA);
         const long dbg_save = G.dbg_col;
         if (G.dbg) G.dbg_col = dbg_save - c0;  // chunk-relative for the staged pass
         G.chunk = chunk;
+        G.err_col0 = c0;  // a staged pass sees its columns as 0 .. nc-1; input errors are reported with the call's column
         G.mt_total = G.mt_opt_total ? G.mt_opt_total : (long)ncol; G.mt_base = G.mt_opt_base + c0;
         rc = run_device(mode, nc, nlay, icld, idrv, inflag, iceflag, liqflag, permuteseed, irng, in, out, st);
         G.mt_total = 0; G.mt_base = 0;
+        G.err_col0 = 0;
         G.chunk = saved_chunk;
         G.dbg_col = dbg_save;
-        if (rc) return rc;
-        CK(cudaEventRecord(G.e_done[a], st));
-        CK(cudaStreamWaitEvent(G.s_out, G.e_done[a], 0));
+        if (rc) return drain(rc);
+        if (cudaEventRecord(G.e_done[a], st) != cudaSuccess || cudaStreamWaitEvent(G.s_out, G.e_done[a], 0) != cudaSuccess)
+            return drain(RRTMG_LW_ERR_CUDA);
         sg.st = G.s_out;
         if (sg.out(ho.uflx, out.uflx, 1, ld, c0, nc, nlay + 1) || sg.out(ho.dflx, out.dflx, 1, ld, c0, nc, nlay + 1) ||
             sg.out(ho.uflxc, out.uflxc, 1, ld, c0, nc, nlay + 1) || sg.out(ho.dflxc, out.dflxc, 1, ld, c0, nc, nlay + 1) ||
             sg.out(ho.hr, out.hr, 1, ld, c0, nc, nlay) || sg.out(ho.hrc, out.hrc, 1, ld, c0, nc, nlay))
-            return RRTMG_LW_ERR_CUDA;
+            return drain(RRTMG_LW_ERR_CUDA);
         if (idrv == 1 && (sg.out(ho.duflx_dt, out.duflx_dt, 1, ld, c0, nc, nlay + 1) ||
                           sg.out(ho.duflxc_dt, out.duflxc_dt, 1, ld, c0, nc, nlay + 1)))
-            return RRTMG_LW_ERR_CUDA;
-        CK(cudaEventRecord(G.e_out[a], G.s_out));
+            return drain(RRTMG_LW_ERR_CUDA);
+        if (cudaEventRecord(G.e_out[a], G.s_out) != cudaSuccess) return drain(RRTMG_LW_ERR_CUDA);
     }
-    CK(cudaStreamSynchronize(G.s_out));
-    CK(cudaStreamSynchronize(st));
+    drain(RRTMG_LW_OK);
     return decode_status(nullptr, nullptr);
+}
+
+void reset_timing() {
+    G.ms_band = 0.f;
+    G.ms_all = 0.f;
+    G.nstage = 0;
+    for (auto& m : G.ms_bands) m = 0.f;
 }
 
 bool check_common(int ncol, int ld, int nlay) { return ncol >= 1 && ld >= ncol && nlay >= 1 && nlay <= LW_MAXLAY; }
@@ -551,14 +613,12 @@ extern "C" int rrtmg_lw_b200_ini(double cpdair, const double* kdata, long nkdata
     CK(upload_constants_tu3(H.ct, dp, rr, &cf));
     CK(upload_constants_tu4(H.ct, dp, rr, &cf));
     CK(upload_constants_tu5(H.ct, dp, rr, &cf));
-    CK(upload_constants_gtu0(H.ct, dp, rr));
-    CK(upload_constants_gtu1(H.ct, dp, rr));
-    CK(upload_constants_gtu2(H.ct, dp, rr));
-    CK(upload_constants_gtu3(H.ct, dp, rr));
-    CK(upload_constants_gtu4(H.ct, dp, rr));
-    CK(upload_constants_gtu5(H.ct, dp, rr));
-    CK(upload_constants_gtu6(H.ct, dp, rr));
-    CK(upload_constants_gtu7(H.ct, dp, rr));
+    CK(upload_constants_stu0(H.ct, dp, rr, &cf));
+    CK(upload_constants_stu1(H.ct, dp, rr, &cf));
+    CK(upload_constants_stu2(H.ct, dp, rr, &cf));
+    CK(upload_constants_stu3(H.ct, dp, rr, &cf));
+    CK(upload_constants_stu4(H.ct, dp, rr, &cf));
+    CK(upload_constants_stu5(H.ct, dp, rr, &cf));
     CK(cudaDeviceSynchronize());
     G.inited = true;
     return RRTMG_LW_OK;
@@ -588,6 +648,7 @@ extern "C" int rrtmg_lw_b200_rrtmg_lw(int ncol, int ld, int nlay, int* icld, int
         return RRTMG_LW_ERR_ARG;
     if (cloudy && (!cldfmcl || !taucmcl || !ciwpmcl || !clwpmcl || !reicmcl || !relqmcl)) return RRTMG_LW_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
+    reset_timing();
     if (memspace == RRTMG_LW_DEVICE) {
         ColIn in{};
         in.play = play; in.plev = plev; in.tlay = tlay; in.tlev = tlev; in.tsfc = tsfc; in.h2o = h2ovmr; in.o3 = o3vmr;
@@ -649,6 +710,7 @@ extern "C" int rrtmg_lw_b200_rrtmg_lw_mcica(int ncol, int ld, int nlay, int icld
     if (icld_overlap >= 4 && !alpha) return RRTMG_LW_ERR_ARG;
     if (irng != 0) irng = 1;
     cudaStream_t st = (cudaStream_t)stream;
+    reset_timing();
     if (memspace == RRTMG_LW_DEVICE) {
         ColIn in{};
         in.play = play; in.plev = plev; in.tlay = tlay; in.tlev = tlev; in.tsfc = tsfc; in.h2o = h2ovmr; in.o3 = o3vmr;
@@ -705,7 +767,7 @@ extern "C" int rrtmg_lw_b200_mcica_subcol_lw(int iplon, int ncol, int ld, int nl
     int cap = G.chunk;
     if (memspace == RRTMG_LW_HOST && G.host_chunk < cap) cap = G.host_chunk;
     const int chunk = cap < ncol ? cap : ncol;
-    int rc = ensure_scratch(chunk, nlay);
+    int rc = ensure_scratch(chunk, nlay, 0);
     if (rc) return rc;
     const long P = ((chunk + 31) / 32) * 32;
     if (memspace == RRTMG_LW_HOST) {
@@ -719,18 +781,18 @@ extern "C" int rrtmg_lw_b200_mcica_subcol_lw(int iplon, int ncol, int ld, int nl
         ColIn in{};
         in.nlay = nlay;
         auto generate = [&]() -> int {
-            if (*irng == 0) { launch_mcica_kiss(in, G.S, r, st); G.launches++; return 0; }
+            if (*irng == 0) { launch_mcica_kiss(in, G.S, r, st); G.launches++; return RRTMG_LW_OK; }
             if (G.mt_opt_base + ncol > (G.mt_opt_total ? G.mt_opt_total : (long)ncol)) return RRTMG_LW_ERR_ARG;
             const int nl = launch_mcica_mt(in, G.S, r, G.mt_opt_total ? G.mt_opt_total : (long)ncol, G.mt_opt_base + c0, st);
             if (nl < 0) return RRTMG_LW_ERR_CUDA;
             G.launches += nl;
-            return 0;
+            return RRTMG_LW_OK;
         };
         if (memspace == RRTMG_LW_DEVICE) {
             r.c0 = c0;
             in.play = play; in.cldfrac = cldfrac; in.ciwp = ciwp; in.clwp = clwp; in.rei = rei; in.rel = rel;
             in.tauc = tauc; in.alpha = alpha; in.ld = ld;
-            if (generate()) return RRTMG_LW_ERR_CUDA;
+            if ((rc = generate()) != RRTMG_LW_OK) return rc;
             launch_materialize(in, G.S, r, cldfmcl, ciwpmcl, clwpmcl, reicmcl, relqmcl, taucmcl, st);
             G.launches++;
         } else {
@@ -747,7 +809,7 @@ extern "C" int rrtmg_lw_b200_mcica_subcol_lw(int iplon, int ncol, int ld, int nl
             double* o_cld = sg.carve((size_t)140 * P * nlay); double* o_ciwp = sg.carve((size_t)140 * P * nlay);
             double* o_clwp = sg.carve((size_t)140 * P * nlay); double* o_tauc = sg.carve((size_t)140 * P * nlay);
             double* o_rei = sg.carve((size_t)P * nlay); double* o_rel = sg.carve((size_t)P * nlay);
-            if (generate()) return RRTMG_LW_ERR_CUDA;
+            if ((rc = generate()) != RRTMG_LW_OK) return rc;
             launch_materialize(in, G.S, r, o_cld, o_ciwp, o_clwp, o_rei, o_rel, o_tauc, st);
             G.launches++;
             if (sg.out(cldfmcl, o_cld, 140, ld, c0, r.ncol, nlay) || sg.out(ciwpmcl, o_ciwp, 140, ld, c0, r.ncol, nlay) ||
@@ -804,6 +866,13 @@ extern "C" int rrtmg_lw_b200_sync(int* col, int* lay) {
     return decode_status(col, lay);
 }
 
+extern "C" int rrtmg_lw_b200_last_error(int* col, int* lay) {
+    std::lock_guard<std::mutex> lk(G.mu);
+    if (col) *col = (int)G.last_err_col;
+    if (lay) *lay = G.last_err_lay;
+    return RRTMG_LW_OK;
+}
+
 extern "C" int rrtmg_lw_b200_debug_capture(int col_plus1) {
     std::lock_guard<std::mutex> lk(G.mu);
     G.dbg = col_plus1 > 0;
@@ -849,6 +918,8 @@ extern "C" long rrtmg_lw_b200_get_table(const char* name, double* out, long cap)
     else if (n == "exp_tbl") { src = G.H.exp_tbl.data(); cnt = NTBL + 1; }
     else if (n == "tfn_tbl") { src = G.H.tfn_tbl.data(); cnt = NTBL + 1; }
     else if (n == "rwgt") { src = G.H.rwgt; cnt = 256; }
+    else if (n == "heatfac") { src = &G.H.ct.heatfac; cnt = 1; }   // rrlw_con, set by rrtmg_lw_ini (init.f90:298)
+    else if (n == "fluxfac") { src = &G.H.ct.fluxfac; cnt = 1; }
     else {
         for (auto& kv : G.H.named)
             if (kv.first == n) { src = kv.second.data(); cnt = (long)kv.second.size(); break; }
@@ -869,8 +940,19 @@ extern "C" int rrtmg_lw_b200_set_option(const char* name, int value) {
     std::lock_guard<std::mutex> lk(G.mu);
     if (!name) return RRTMG_LW_ERR_ARG;
     if (std::strcmp(name, "band_kernel") == 0) {
-        if (value != 2 && value != 3) return RRTMG_LW_ERR_ARG;
+        if (value != 2 && value != 4) return RRTMG_LW_ERR_ARG;
         G.band_kernel = value;
+        return RRTMG_LW_OK;
+    }
+    if (std::strcmp(name, "sweep_groups") == 0) {
+        if (value != 0 && value != 1) return RRTMG_LW_ERR_ARG;
+        G.sweep_groups = value;
+        return RRTMG_LW_OK;
+    }
+    if (std::strcmp(name, "band_lo") == 0 || std::strcmp(name, "band_hi") == 0) {
+        // band range istart..iend of the following runs (two-phase path): only those bands enter the flux sums
+        if (value < 1 || value > NBND) return RRTMG_LW_ERR_ARG;
+        (name[5] == 'l' ? G.band_lo : G.band_hi) = value;
         return RRTMG_LW_OK;
     }
     if (std::strcmp(name, "precision") == 0) {
@@ -924,6 +1006,13 @@ extern "C" int rrtmg_lw_b200_last_band_timing(float* ms16) {
     if (!ms16) return RRTMG_LW_ERR_ARG;
     for (int k = 0; k < NBND; ++k) ms16[k] = G.ms_bands[k];
     return RRTMG_LW_OK;
+}
+
+extern "C" int rrtmg_lw_b200_last_stage_timing(float* ms, int cap) {
+    std::lock_guard<std::mutex> lk(G.mu);
+    if (!ms || cap < 0) return -1;
+    for (int k = 0; k < G.nstage && k < cap; ++k) ms[k] = G.ms_bands[k];
+    return G.nstage;
 }
 
 extern "C" const char* rrtmg_lw_b200_strerror(int code) {

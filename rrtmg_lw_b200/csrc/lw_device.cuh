@@ -64,17 +64,14 @@ struct Scratch {
     float* abscldf;     // aliases abscld
     float* inf;         // float copies of caller arrays, see lw_api.cu: carve_fp32_inputs
     unsigned long long* status;  // sticky error word: code<<56 | (col+1)<<24 | lay
+    long err_base;      // added to the column an input error is reported with (first column of a staged host pass)
     long pitch;         // columns per row of every scratch array (multiple of 32)
-    // ---- g-lane band kernel (lw_gband.cuh): layer-fastest copies and per-warp state slots
-    double* fldT;       // NFIELD x pitch x LP   (layer fastest)
-    int* ipackT;        // pitch x LP
-    unsigned* maskT;    // 5 x pitch x LP
-    double* fluxT;      // 6 x pitch x LP1 : dflx, dflxc, uflx, uflxc, duflx_dt, duflxc_dt band sums, level fastest
-    double* fluxC;      // 6 x (nlay+1) x pitch : same sums of the narrow bands, column fastest
-    double* gstate;     // per resident warp: nlay x 4 x 32 (atrans, bbugas of the lane's two g-points)
-    double* gstateB;    // per resident warp: nlay x 8 x 32 (atot, bbutot, efclfrac, cldfmc), cloudy layers only
-    int LP, LP1;        // padded layer / level extents (multiples of 16)
-    int gwarps;         // resident warps the state slots were sized for (grid x warps per CTA)
+    // ---- two-phase path (lw_taumol.cuh -> lw_rtrnmc.cuh)
+    double* od;         // [pitch / 128][nlay][70][128][2] : odepth = max(0, secdiff * (taug + tauaer)) of g-point pairs
+    double* pfs;        // [pitch / 128][nlay][9][128] : eta (specmult) of the Planck-fraction interpolation, binary bands
+    double* secdiff;    // 16 x pitch : diffusivity angle per band (rtrnmc.f90:258-281)
+    double* cldb;       // [pitch / 128][nlay][16][2][128] : {odcld, 1 - exp(-odcld)} of a band's cloudy sub-columns (CLD_MASK)
+    double* gcld;       // 2 x 140 x nlay x pitch : efclfrac, odcld per g-point (strict rrtmg_lw() entry only)
     // debug capture of one column
     int dbg_col;        // chunk-relative column or -1
     double *dbg_taug, *dbg_fracs;  // (140, nlay)
@@ -92,7 +89,9 @@ struct RunCfg {
     int inflag, iceflag, liqflag;
     int icld, irng, permuteseed;
     int fp32;        // 1 = the prep kernel writes float fields (Scratch::fldf) for the FP32-mode band kernels
-    int fld_block;   // layout of Scratch::fld: 0 = [field][layer][column] (g-lane kernel), 1 = blocks of 128 columns,
+    int first_band;  // two-phase sweep kernels: 1 = this launch opens the band sum (writes the running level fluxes instead
+                     // of adding to them); band-range runs start at any band
+    int fld_block;   // layout of Scratch::fld: 0 = [field][layer][column], 1 = blocks of 128 columns,
                      // [column / 128][layer][field][column % 128] (column-lane kernel: a CTA's fields of one layer are
                      // one contiguous run, addressed as one base + compile-time offsets); pitch is a multiple of 128
 };

@@ -13,7 +13,7 @@ cudaError_t upload_constants_kernels(const ConstTab& c, const DevPtrs& d, const 
 }
 
 __device__ __forceinline__ void raise(const Scratch& s, int code, long col, int lay) {
-    const unsigned long long v = ((unsigned long long)code << 56) | ((unsigned long long)(col + 1) << 24) |
+    const unsigned long long v = ((unsigned long long)code << 56) | ((unsigned long long)(col + s.err_base + 1) << 24) |
                                  (unsigned long long)(lay & 0xffffff);
     atomicCAS(s.status, 0ull, v);
 }
@@ -145,6 +145,52 @@ __global__ void __launch_bounds__(128) prep_kernel(ColIn in, Scratch s, RunCfg r
 }
 
 // ---------------------------------------------------------------------------------------------
+// Column scalars: laytrop (setcoef.f90:312-313), pwvcm (rad.f90:860-870, sums in layer order) and the diffusivity
+// angle of every band (rtrnmc.f90:258-281).  One thread per column.
+__global__ void __launch_bounds__(128) colprep_kernel(ColIn in, Scratch s, RunCfg r) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= r.ncol) return;
+    const long ci = r.c0 + i;
+    const int nlay = r.nlay;
+    const double amd = 28.9660, amw = 18.0160;
+    double amttl = 0.0, wvttl = 0.0;
+    int laytrop = 0;
+    double pz_lo = in.plev[ci];
+    const double pz0 = pz_lo;
+    for (int l = 0; l < nlay; ++l) {
+        const long a = ci + in.ld * l;
+        const double pavel = in.play[a];
+        const double pz_hi = in.plev[ci + in.ld * (l + 1)];
+        const double h2o = in.h2o[a];
+        const double amm = (1. - h2o) * amd + h2o * amw;
+        const double coldry = (pz_lo - pz_hi) * 1.e3 * C.avogad / (1.e2 * C.grav * amm * (1. + h2o));
+        pz_lo = pz_hi;
+        const double w1 = coldry * h2o;
+        amttl = amttl + coldry + w1;
+        wvttl = wvttl + w1;
+        const double plog = log(pavel);
+        if (!(plog <= 4.56)) laytrop = laytrop + 1;
+    }
+    const double wvsh = (amw * wvttl) / (amd * amttl);
+    const double pwvcm = wvsh * (1.e3 * pz0) / (1.e2 * C.grav);
+    s.pwvcm[i] = pwvcm;
+    s.laytrop[i] = laytrop;
+#pragma unroll
+    for (int b = 1; b <= NBND; ++b) {
+        double secdiff;
+        if (b == 1 || b == 4 || b >= 10) {
+            secdiff = 1.66;
+        } else {
+            secdiff = C.a0[b - 1] + C.a1[b - 1] * exp(C.a2[b - 1] * pwvcm);
+            if (secdiff > 1.80) secdiff = 1.80;
+            if (secdiff < 1.50) secdiff = 1.50;
+        }
+        s.secdiff[(long)(b - 1) * s.pitch + i] = secdiff;
+    }
+    if (s.dbg_col == i) { s.dbg_scal[0] = laytrop; s.dbg_scal[1] = pwvcm; }
+}
+
+// ---------------------------------------------------------------------------------------------
 // KISS generator step, src/mcica_subcol_gen_lw.f90:731-741 (INT32 wrap-around, logical shifts)
 struct Kiss {
     unsigned s1, s2, s3, s4;
@@ -211,7 +257,12 @@ __global__ void __launch_bounds__(128) mcica_kiss_kernel(ColIn in, Scratch s, Ru
     Kiss k;
     {
         const double p1 = in.play[ci] * 1.e2, p2 = in.play[ci + in.ld] * 1.e2;
-        if (p1 < p2) { raise(s, 4, ci, 1); s.ctop[i] = 0; return; }
+        if (p1 < p2) {
+            raise(s, 4, ci, 1);
+            s.ctop[i] = 0;
+            for (int k = 0; k < nlay * 5; ++k) s.mask[(long)k * P + i] = 0u;
+            return;
+        }
         const double p3 = in.play[ci + 2 * in.ld] * 1.e2, p4 = in.play[ci + 3 * in.ld] * 1.e2;
         k.s1 = (unsigned)(int)((p1 - (double)(int)p1) * 1000000000.0);
         k.s2 = (unsigned)(int)((p2 - (double)(int)p2) * 1000000000.0);
@@ -442,8 +493,9 @@ __global__ void __launch_bounds__(160) mcica_kiss_par_kernel(ColIn in, Scratch s
     const bool act = sc < NGPT;
     const double cldmin = 1.0e-20;
     const double p1 = in.play[ci] * 1.e2, p2 = in.play[ci + in.ld] * 1.e2;
-    if (p1 < p2) {  // uniform over the CTA
+    if (p1 < p2) {  // uniform over the CTA: the reference STOPs (mcica:465); the column is left cloud-free
         if (threadIdx.x == 0) { raise(s, 4, ci, 1); s.ctop[i] = 0; }
+        for (int k = threadIdx.x; k < nlay * 5; k += blockDim.x) s.mask[(long)k * P + i] = 0u;
         return;
     }
     if (threadIdx.x == 0) mk_words[nlay * 5] = 0u;
@@ -733,65 +785,6 @@ __global__ void __launch_bounds__(128) finalize_kernel(ColIn in, ColOut out, Scr
     }
 }
 
-// flux close-out for the g-lane path: band sums are level-fastest in s.fluxT (6 x pitch x LP1)
-__global__ void __launch_bounds__(128) finalizeT_kernel(ColIn in, ColOut out, Scratch s, RunCfg r, int cloudy) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= r.ncol) return;
-    const long ci = r.c0 + i;
-    const int nlay = r.nlay;
-    const bool sep = cloudy && s.ctop[i] > 0;
-    const long fxs = s.pitch * (long)s.LP1;
-    const double* fx = s.fluxT + (long)i * s.LP1;          // wide bands, level fastest
-    const long fcs = (long)(nlay + 1) * s.pitch;
-    const double* fc = s.fluxC + i;                         // narrow bands, column fastest
-    double fnet_lo = 0., fnetc_lo = 0., pz_lo = 0.;
-    for (int lev = 0; lev <= nlay; ++lev) {
-        const long o = ci + out.ld * lev;
-        const long oc = (long)lev * s.pitch;
-        const double d = (fx[lev] + fc[oc]) * C.fluxfac;
-        const double u = (fx[2 * fxs + lev] + fc[2 * fcs + oc]) * C.fluxfac;
-        double uc, dc;
-        if (sep) {
-            dc = (fx[fxs + lev] + fc[fcs + oc]) * C.fluxfac;
-            uc = (fx[3 * fxs + lev] + fc[3 * fcs + oc]) * C.fluxfac;
-        } else { uc = u; dc = d; }
-        out.uflx[o] = u; out.dflx[o] = d; out.uflxc[o] = uc; out.dflxc[o] = dc;
-        if (r.idrv == 1) {
-            const double du = fx[4 * fxs + lev] + fc[4 * fcs + oc];
-            out.duflx_dt[o] = du;
-            out.duflxc_dt[o] = sep ? fx[5 * fxs + lev] + fc[5 * fcs + oc] : du;
-        }
-        const double fnet = u - d, fnetc = uc - dc;
-        const double pz = in.plev[ci + in.ld * lev];
-        if (lev > 0) {
-            const long oh = ci + out.ld * (lev - 1);
-            out.hr[oh] = C.heatfac * (fnet_lo - fnet) / (pz_lo - pz);
-            out.hrc[oh] = C.heatfac * (fnetc_lo - fnetc) / (pz_lo - pz);
-        }
-        fnet_lo = fnet; fnetc_lo = fnetc; pz_lo = pz;
-    }
-}
-
-// column-fastest planes -> layer-fastest planes: dst[(p*P + i)*LP + l] = src[p*pstride + l*lstride + i]
-template <typename T>
-__global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ src, T* __restrict__ dst, long pstride,
-                                                        long lstride, int nlay, int ncol, long P, int LP) {
-    __shared__ T tile[32][33];
-    const int p = blockIdx.z;
-    const int c0 = blockIdx.x * 32, l0 = blockIdx.y * 32;
-    const T* sp = src + (long)p * pstride;
-    T* dp = dst + (long)p * P * LP;
-    for (int k = threadIdx.y; k < 32; k += 8) {
-        const int l = l0 + k, c = c0 + threadIdx.x;
-        if (l < nlay && c < ncol) tile[k][threadIdx.x] = sp[(long)l * lstride + c];
-    }
-    __syncthreads();
-    for (int k = threadIdx.y; k < 32; k += 8) {
-        const int c = c0 + k, l = l0 + threadIdx.x;
-        if (c < ncol && l < nlay) dp[(long)c * LP + l] = tile[threadIdx.x][k];
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
 // get_alpha, src/mcica_subcol_gen_lw.f90:129-178
 __global__ void get_alpha_kernel(int ncol, long ld, int nlay, int icld, int idcor, double decorr_con, const double* dz,
@@ -852,6 +845,9 @@ __global__ void materialize_kernel(ColIn in, Scratch s, RunCfg r, double* cldfmc
 
 // ---------------------------------------------------------------------------------------------
 
+void launch_colprep(const ColIn& in, const Scratch& s, const RunCfg& r, cudaStream_t st) {
+    colprep_kernel<<<nblk(r.ncol, 128), 128, 0, st>>>(in, s, r);
+}
 void launch_prep(const ColIn& in, const Scratch& s, const RunCfg& r, cudaStream_t st) {
     prep_kernel<<<nblk(r.ncol, 128), 128, 0, st>>>(in, s, r);
 }
@@ -911,21 +907,6 @@ void launch_cldflags(const ColIn& in, const Scratch& s, const RunCfg& r, cudaStr
 }
 void launch_finalize(const ColIn& in, const ColOut& out, const Scratch& s, const RunCfg& r, int cloudy, cudaStream_t st) {
     finalize_kernel<<<nblk(r.ncol, 128), 128, 0, st>>>(in, out, s, r, cloudy);
-}
-void launch_finalizeT(const ColIn& in, const ColOut& out, const Scratch& s, const RunCfg& r, int cloudy, cudaStream_t st) {
-    finalizeT_kernel<<<nblk(r.ncol, 128), 128, 0, st>>>(in, out, s, r, cloudy);
-}
-void launch_transposes(const Scratch& s, const RunCfg& r, int with_mask, cudaStream_t st) {
-    const dim3 blk(32, 8);
-    const long plane = (long)r.nlay * s.pitch;
-    const dim3 g1(nblk(r.ncol, 32), nblk(r.nlay, 32), NFIELD);
-    transpose_kernel<double><<<g1, blk, 0, st>>>(s.fld, s.fldT, plane, s.pitch, r.nlay, r.ncol, s.pitch, s.LP);
-    const dim3 g2(nblk(r.ncol, 32), nblk(r.nlay, 32), 1);
-    transpose_kernel<int><<<g2, blk, 0, st>>>(s.ipack, s.ipackT, plane, s.pitch, r.nlay, r.ncol, s.pitch, s.LP);
-    if (with_mask) {
-        const dim3 g3(nblk(r.ncol, 32), nblk(r.nlay, 32), 5);
-        transpose_kernel<unsigned><<<g3, blk, 0, st>>>(s.mask, s.maskT, s.pitch, 5 * s.pitch, r.nlay, r.ncol, s.pitch, s.LP);
-    }
 }
 void launch_get_alpha(int ncol, long ld, int nlay, int icld, int idcor, double decorr_con, const double* dz,
                       const double* lat, int juldat, const double* cldfrac, double* alpha, double am1, double am2,

@@ -42,13 +42,18 @@ cudaError_t upload_constants_kernels(const ConstTab&, const DevPtrs&, const doub
 LW_DECL_TU(0) LW_DECL_TU(1) LW_DECL_TU(2) LW_DECL_TU(3) LW_DECL_TU(4) LW_DECL_TU(5)
 #undef LW_DECL_TU
 
-// g-lane band kernels (lw_gband.cuh): grid = persistent CTAs
-#define LW_NUM_GBAND_TUS 8
-#define LW_DECL_GTU(n)                                                                                      \
-    bool launch_gband_tu##n(int band, int cld, int grid, const ColIn&, const Scratch&, const RunCfg&, cudaStream_t); \
-    cudaError_t upload_constants_gtu##n(const ConstTab&, const DevPtrs&, const double (*refrat)[5]);
-LW_DECL_GTU(0) LW_DECL_GTU(1) LW_DECL_GTU(2) LW_DECL_GTU(3) LW_DECL_GTU(4) LW_DECL_GTU(5) LW_DECL_GTU(6) LW_DECL_GTU(7)
-#undef LW_DECL_GTU
-void launch_transposes(const Scratch&, const RunCfg&, int with_mask, cudaStream_t);
-void launch_finalizeT(const ColIn&, const ColOut&, const Scratch&, const RunCfg&, int cloudy, cudaStream_t);
+// two-phase path (lw_taumol.cuh, lw_rtrnmc.cuh; instantiated in lw_twophase_inst.cu, one TU per -DLW_STU=n)
+#ifndef LW_TAUMOL_MINB
+#define LW_TAUMOL_MINB 4  // resident CTAs per SM the (column, layer) taumol kernel is compiled for
+#endif
+#define LW_NUM_SWEEP_TUS 6
+void launch_colprep(const ColIn&, const Scratch&, const RunCfg&, cudaStream_t);
+void launch_taumol(const ColIn&, const Scratch&, const RunCfg&, cudaStream_t);
+#define LW_DECL_STU(n)                                                                                             \
+    bool launch_sweep_stu##n(int b0, int nb, int cld, int idrv, const ColIn&, const ColOut&, const Scratch&, const RunCfg&, \
+                             cudaStream_t);                                                                        \
+    cudaError_t upload_constants_stu##n(const ConstTab&, const DevPtrs&, const double (*refrat)[5], const ConstTabF*);
+LW_DECL_STU(1) LW_DECL_STU(2) LW_DECL_STU(3) LW_DECL_STU(4) LW_DECL_STU(5)
+#undef LW_DECL_STU
+cudaError_t upload_constants_stu0(const ConstTab&, const DevPtrs&, const double (*refrat)[5], const ConstTabF*);
 }  // namespace lw

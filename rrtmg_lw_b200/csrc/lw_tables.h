@@ -25,6 +25,28 @@ constexpr int NGPAD[NBND] = {12, 12, 16, 16, 16, 8, 12, 8, 12, 8, 8, 8, 4, 4, 4,
 constexpr int NSPA[NBND] = {1, 1, 9, 9, 9, 1, 9, 1, 9, 1, 1, 9, 9, 1, 9, 9};
 constexpr int NSPB[NBND] = {1, 1, 5, 5, 5, 0, 1, 1, 1, 1, 1, 0, 0, 1, 0, 0};
 
+// slot of a binary-species band in Scratch::pfs (band order 3, 4, 5, 7, 9, 12, 13, 15, 16), -1 for single-key bands
+#ifdef __CUDACC__
+#define LW_HD __host__ __device__
+#else
+#define LW_HD
+#endif
+LW_HD constexpr int pf_slot(int b) {
+    switch (b) {
+        case 3: return 0;
+        case 4: return 1;
+        case 5: return 2;
+        case 7: return 3;
+        case 9: return 4;
+        case 12: return 5;
+        case 13: return 6;
+        case 15: return 7;
+        case 16: return 8;
+        default: return -1;
+    }
+}
+constexpr int NPF = 9;
+
 // Pointers into the device table arena for one band.  Minor-gas tables m[] and per-g vectors
 // v[] are numbered in the order the band lists them in include/rrtmg_lw_kdata_layout.h:
 //   band 1: m0 ka_mn2 m1 kb_mn2        band 3: m0 ka_mn2o(9,19) m1 kb_mn2o(5,19)

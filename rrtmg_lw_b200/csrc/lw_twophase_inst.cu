@@ -1,0 +1,82 @@
+// lw_twophase_inst.cu -- instantiations of the two-phase kernels (lw_taumol.cuh, lw_rtrnmc.cuh); compiled once per
+// -DLW_STU=n so that the band groups x cloud modes x idrv variants build in parallel.
+//   STU 0: column scalars + the (column, layer) taumol kernel
+//   STU 1-3: the default band groups of the sweep kernel
+//   STU 4-5: single-band sweep kernels (band-range runs, e.g. the per-band output blocks of the column-mode harness)
+#include <cstdlib>
+
+#include "lw_rtrnmc.cuh"
+#include "lw_launch.h"
+
+#ifndef LW_STU
+#error "compile with -DLW_STU=0..5"
+#endif
+
+#define LW_CAT2(a, b) a##b
+#define LW_CAT(a, b) LW_CAT2(a, b)
+
+namespace lw {
+
+cudaError_t LW_CAT(upload_constants_stu, LW_STU)(const ConstTab& c, const DevPtrs& d, const double (*refrat)[5],
+                                                  const ConstTabF* cf) {
+    return upload_constants_here(c, d, refrat, cf);
+}
+
+#if LW_STU == 0
+void launch_taumol(const ColIn& in, const Scratch& s, const RunCfg& r, cudaStream_t st) {
+    const dim3 grid((unsigned)((r.ncol + TAUMOL_THREADS - 1) / TAUMOL_THREADS), (unsigned)r.nlay);
+    taumol_kernel<0xffffu, LW_TAUMOL_MINB><<<grid, TAUMOL_THREADS, 0, st>>>(in, s, r);
+}
+#else
+
+// registers a sweep kernel wants: the group's recurrences (total + clear stream, + their dT derivatives) and ~70 more
+constexpr int sweep_minb(int ngg, int cld, int idrv) {
+    const int est = (cld != CLD_NONE ? 4 : 2) * ngg * (idrv ? 2 : 1) + 72;
+    return est <= 128 ? 4 : (est <= 168 ? 3 : 2);
+}
+
+template <int B0, int NB>
+static void launch_g(int cld, int idrv, const ColIn& in, const ColOut& out, const Scratch& s, const RunCfg& r,
+                     cudaStream_t st) {
+    const int threads = SWEEP_THREADS;
+    const int blocks = (r.ncol + threads - 1) / threads;
+    const size_t smem = SweepRing<B0, NB>::BYTES;
+    constexpr int NGG = Grp<B0, NB>::NGG;
+#define LW_GO(CLD, IDRV)                                                                                         \
+    do {                                                                                                         \
+        auto kern = rtrnmc_kernel<B0, NB, CLD, IDRV, sweep_minb(NGG, CLD, IDRV)>;                                \
+        static bool attr_set = false;                                                                            \
+        if (!attr_set) {                                                                                         \
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                  \
+            attr_set = true;                                                                                     \
+        }                                                                                                        \
+        kern<<<blocks, threads, smem, st>>>(in, out, s, r);                                                      \
+    } while (0)
+    if (cld == CLD_NONE) { if (idrv) LW_GO(CLD_NONE, 1); else LW_GO(CLD_NONE, 0); }
+    else if (cld == CLD_MASK) { if (idrv) LW_GO(CLD_MASK, 1); else LW_GO(CLD_MASK, 0); }
+    else { if (idrv) LW_GO(CLD_ARRAYS, 1); else LW_GO(CLD_ARRAYS, 0); }
+#undef LW_GO
+}
+
+#if LW_STU == 1
+#define LW_STU_GROUPS(X) X(1, 2) X(6, 2)
+#elif LW_STU == 2
+#define LW_STU_GROUPS(X) X(3, 1) X(4, 1) X(5, 1)
+#elif LW_STU == 3
+#define LW_STU_GROUPS(X) X(8, 2) X(10, 3) X(13, 4)
+#elif LW_STU == 4
+#define LW_STU_GROUPS(X) X(1, 1) X(2, 1) X(6, 1) X(7, 1) X(8, 1)
+#else
+#define LW_STU_GROUPS(X) X(9, 1) X(10, 1) X(11, 1) X(12, 1) X(13, 1) X(14, 1) X(15, 1) X(16, 1)
+#endif
+
+bool LW_CAT(launch_sweep_stu, LW_STU)(int b0, int nb, int cld, int idrv, const ColIn& in, const ColOut& out,
+                                      const Scratch& s, const RunCfg& r, cudaStream_t st) {
+#define LW_CASE(B0, NB) if (b0 == B0 && nb == NB) { launch_g<B0, NB>(cld, idrv, in, out, s, r, st); return true; }
+    LW_STU_GROUPS(LW_CASE)
+#undef LW_CASE
+    return false;
+}
+#endif
+
+}  // namespace lw

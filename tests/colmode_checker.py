@@ -7,6 +7,9 @@ class OracleBackend:
     def __init__(self, orc):
         self.orc = orc
 
+    def heatfac(self):
+        return float(self.orc.get_table("heatfac")[0])
+
     def clear(self, b, idrv):
         o = self.orc.rrtmg_lw(b, icld=0, idrv=idrv)
         assert o["rc"] == 0

@@ -34,10 +34,13 @@ def gpu(kblob):
     assert torch.cuda.is_available(), "gpu tests need a CUDA device; the library has no CPU fallback"
     from rrtmg_lw_b200 import api
     api.rrtmg_lw_ini(1004.0, kblob, 4)
-    # RRTMG_LW_BAND_KERNEL=2|3 runs the whole suite against the other band-kernel mapping
+    # RRTMG_LW_BAND_KERNEL=2|4 runs the whole suite against the fused per-band kernels / the two-phase path (default)
     bk = os.environ.get("RRTMG_LW_BAND_KERNEL")
     if bk:
         api.set_option("band_kernel", int(bk))
+    sg = os.environ.get("RRTMG_LW_SWEEP_GROUPS")
+    if sg:
+        api.set_option("sweep_groups", int(sg))
     return api
 
 

@@ -172,3 +172,34 @@ def test_idrv_adjustment_is_the_reference_formula(suite, oracle):
     # (the second-order term 6 sigma T^2 dT^2 is 0.74 W m-2 at the surface)
     assert abs(hot["uflx"][0] - r5["uflx"][0]) < 1.0
     assert abs(hot["uflx"][-1] - r5["uflx"][-1]) < 1.0
+
+
+def test_mcica_samples_are_seeded_like_the_column_mode_generator(suite):
+    """The column-mode generator seeds sample ims with permuteseed = ims * nsubclw = 140 ims
+    (src/mcica_subcol_gen_lw.1col.f90:251), not with ims; the harness must hand exactly those seeds to
+    mcica_subcol_lw, with irng = 1 (src/rrtmg_lw.1col.f90:417), and use rrlw_con's heatfac for the idrv adjustment."""
+    seen = []
+
+    class Recorder:
+        def heatfac(self):
+            return 8.4391
+
+        def get_alpha(self, *a):
+            raise AssertionError("icld 2 needs no alpha")
+
+        def clear(self, b, idrv):
+            raise AssertionError("a cloudy McICA case must not take the clear path")
+
+        def mcica(self, b, icld, idrv, permuteseed, irng, flags, alpha):
+            seen.append((permuteseed, irng))
+            L = b.nlay
+            return dict(uflx=np.zeros(L + 1), dflx=np.zeros(L + 1), hr=np.zeros(L), duflx_dt=np.zeros(L + 1))
+
+    c = colmode.Case(**suite["MLS-cld7-imca1-icld2"]["case"])
+    r = colmode.run_case(c, Recorder(), nmca=5)
+    assert seen == [(140 * ims, 1) for ims in range(1, 6)]
+    assert r["nmca"] == 5
+    ref_src = "/root/reference/src/mcica_subcol_gen_lw.1col.f90"
+    if os.path.exists(ref_src):
+        src = open(ref_src).read()
+        assert "permuteseed = ims*nsubclw" in src

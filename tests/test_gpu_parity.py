@@ -268,9 +268,10 @@ def test_full_size_column_independence(gpu, oracle):
         assert err <= tol, (k, err)
 
 
-@pytest.mark.parametrize("kernel", [2, 3])
+@pytest.mark.parametrize("kernel", [2, 4])
 def test_both_band_kernel_mappings_match_oracle(gpu, oracle, kernel):
-    """The two band-kernel mappings (set_option("band_kernel", 2|3)) reproduce the oracle: clear sky
+    """Both kernel structures (set_option("band_kernel", 4 = two-phase taumol + sweep kernels, 2 = fused per-band
+    kernels) reproduce the oracle: clear sky
     with idrv = 1 and a McICA cloudy batch with aerosol."""
     try:
         gpu.set_option("band_kernel", kernel)
@@ -287,7 +288,7 @@ def test_both_band_kernel_mappings_match_oracle(gpu, oracle, kernel):
         _check(got, ref, 1, what="kernel %d cloudy" % kernel)
     finally:
         import os
-        gpu.set_option("band_kernel", int(os.environ.get("RRTMG_LW_BAND_KERNEL", "2")))
+        gpu.set_option("band_kernel", int(os.environ.get("RRTMG_LW_BAND_KERNEL", "4")))
 
 
 @pytest.mark.parametrize("icld", [1, 2, 3, 4, 5])

@@ -39,10 +39,10 @@ def step():
 step(); step()
 torch.cuda.synchronize()
 api.set_timing(True)
-acc = np.zeros(16); tot = 0.0; alln = 0.0; n = 3
+acc = None; tot = 0.0; alln = 0.0; n = 3
 for _ in range(n):
     step(); torch.cuda.synchronize()
-    acc += np.array(api.last_band_timing()); t = api.last_timing(); tot += t[0]; alln += t[1]
+    st_ = np.array(api.last_stage_timing()); acc = st_ if acc is None else acc + st_; t = api.last_timing(); tot += t[0]; alln += t[1]
 api.set_timing(False)
 api.sync()
 cur = {k: out[k][:, :8192].cpu().numpy() for k in ("uflx", "dflx", "uflxc", "dflxc", "hr", "hrc")}
@@ -53,5 +53,5 @@ if os.environ.get("EXP_REF") and os.path.exists(os.environ["EXP_REF"]):
 if os.environ.get("EXP_SAVE"):
     np.savez(os.environ["EXP_SAVE"], **cur)
 print(json.dumps({"lib": os.path.basename(api.LIB_PATH), "opts": os.environ.get("EXP_OPTS", ""), "ncol": ncol, "chunk": int(os.environ.get("EXP_CHUNK", 262144)),
-                  "bands_ms": [round(x / n, 3) for x in acc], "bands_total_ms": round(tot / n, 3),
+                  "stages_ms": [round(x / n, 3) for x in acc], "bands_total_ms": round(tot / n, 3),
                   "all_ms": round(alln / n, 3), "maxdiff_vs_ref": err}), flush=True)
