@@ -270,6 +270,7 @@ int run_device(Mode mode, int ncol, int nlay, int icld, int idrv, int inflag, in
             }
         }
         if (cld == CLD_ARRAYS) { launch_cldflags(in, S, r, st); G.launches += 2; }
+        if (two_phase && cld == CLD_MASK) { launch_cldoptics(in, S, r, st); G.launches++; }
         if (G.timing) CK(cudaEventRecord(G.ev[1], st));
         int nstage = 0;  // timed stages between ev[1] and ev[2]
         if (two_phase) {

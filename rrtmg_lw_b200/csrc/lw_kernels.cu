@@ -191,6 +191,82 @@ __global__ void __launch_bounds__(128) colprep_kernel(ColIn in, Scratch s, RunCf
 }
 
 // ---------------------------------------------------------------------------------------------
+// cldprmc for the McICA mask entry of the two-phase path (cldprmc.f90:177-266 + rtrnmc.f90:316-326): one thread per
+// (column, layer).  Every sub-column of a band that holds cloud in this layer has the same water paths and radii
+// (they are the grid-mean values, mcica:658-679), hence the same band optical depth: the kernel writes, per band whose
+// sub-column bits are not all clear, odcld = secdiff * taucmc and abscld = 1 - exp(-odcld) for the sweep kernels.
+// The layer axis is parallel here, so the exp() and the table lookups stay out of the sweeps' vertical recurrences.
+__global__ void __launch_bounds__(128) cldoptics_kernel(ColIn in, Scratch s, RunCfg r) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int l = blockIdx.y;
+    if (i >= r.ncol) return;
+    const long P = s.pitch;
+    const unsigned* mw = s.mask + ((long)l * 5) * P + i;
+    const unsigned w4 = mw[4 * P];
+    if ((w4 >> 31) == 0) return;  // icldlyr = 0
+    const long ci = r.c0 + i;
+    const long a = ci + in.ld * l;
+    const unsigned w[5] = {mw[0], mw[P], mw[2 * P], mw[3 * P], w4 & 0x7fffffffu};
+    const double ciwp = in.ciwp[a], clwp = in.clwp[a];
+    const double radice = in.rei[a], radliq = in.rel[a];
+    const double cwp = ciwp + clwp;
+    double* q = s.cldb + ((((long)(i >> 7) * r.nlay + l) * NBND) * 2) * 128 + (i & 127);
+    for (int b = 0; b < NBND; ++b) {
+        // the band's sub-column bits: g-points GOFF[b] .. GOFF[b] + NGC[b] - 1
+        const int goff[NBND] = {0, 10, 22, 38, 52, 68, 76, 88, 96, 108, 114, 122, 130, 134, 136, 138};
+        const int ngc[NBND] = {10, 12, 16, 14, 16, 8, 12, 8, 12, 6, 8, 8, 4, 2, 2, 2};
+        const int g0 = goff[b], ng = ngc[b];
+        const int wlo = g0 >> 5, sh = g0 & 31;
+        unsigned bits = w[wlo] >> sh;
+        if (sh + ng > 32) bits |= w[wlo + 1] << (32 - sh);
+        bits &= (1u << ng) - 1u;
+        if (!bits) continue;
+        double tauc = in.tauc ? in.tauc[b + 16 * a] : 0.0;
+        if (r.inflag == 2 && (cwp >= 1.e-20 || tauc >= 1.e-20)) {
+            double abscoice = 0.0, abscoliq = 0.0;
+            if (ciwp != 0.0) {
+                if (r.iceflag == 0) {
+                    abscoice = C.absice0[0] + C.absice0[1] / radice;
+                } else if (r.iceflag == 1) {
+                    const int icb[16] = {1, 2, 3, 3, 3, 4, 4, 4, 5, 5, 5, 5, 5, 5, 5, 5};
+                    abscoice = C.absice1[0 + 2 * (icb[b] - 1)] + C.absice1[1 + 2 * (icb[b] - 1)] / radice;
+                } else {
+                    const double factor = (radice - 2.) / 3.;
+                    int index = (int)factor;
+                    const int nrad = r.iceflag == 2 ? 43 : 46;
+                    if (index == nrad) index = nrad - 1;
+                    if (index < 1) index = 1;        // unreachable for valid radii; keeps loads in bounds
+                    if (index > nrad - 1) index = nrad - 1;
+                    const double fint = factor - (double)index;
+                    const double* t = (r.iceflag == 2 ? D.absice2 : D.absice3) + nrad * b;
+                    const double x0 = ldg(t + index - 1), x1 = ldg(t + index);
+                    abscoice = x0 + fint * (x1 - (x0));
+                }
+            }
+            if (clwp != 0.0) {
+                if (r.liqflag == 0) {
+                    abscoliq = C.absliq0;
+                } else {
+                    int index = (int)(radliq - 1.5);
+                    if (index == 0) index = 1;
+                    if (index == 58) index = 57;
+                    if (index < 1) index = 1;
+                    if (index > 57) index = 57;
+                    const double fint = radliq - 1.5 - (double)index;
+                    const double* t = D.absliq1 + 58 * b;
+                    const double x0 = ldg(t + index - 1), x1 = ldg(t + index);
+                    abscoliq = x0 + fint * (x1 - (x0));
+                }
+            }
+            tauc = ciwp * abscoice + clwp * abscoliq;
+        }
+        const double odcld = s.secdiff[(long)b * P + i] * tauc;
+        q[(b * 2) * 128] = odcld;
+        q[(b * 2 + 1) * 128] = 1. - exp(-odcld);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // KISS generator step, src/mcica_subcol_gen_lw.f90:731-741 (INT32 wrap-around, logical shifts)
 struct Kiss {
     unsigned s1, s2, s3, s4;
@@ -847,6 +923,10 @@ __global__ void materialize_kernel(ColIn in, Scratch s, RunCfg r, double* cldfmc
 
 void launch_colprep(const ColIn& in, const Scratch& s, const RunCfg& r, cudaStream_t st) {
     colprep_kernel<<<nblk(r.ncol, 128), 128, 0, st>>>(in, s, r);
+}
+void launch_cldoptics(const ColIn& in, const Scratch& s, const RunCfg& r, cudaStream_t st) {
+    const dim3 grid((unsigned)nblk(r.ncol, 128), (unsigned)r.nlay);
+    cldoptics_kernel<<<grid, 128, 0, st>>>(in, s, r);
 }
 void launch_prep(const ColIn& in, const Scratch& s, const RunCfg& r, cudaStream_t st) {
     prep_kernel<<<nblk(r.ncol, 128), 128, 0, st>>>(in, s, r);

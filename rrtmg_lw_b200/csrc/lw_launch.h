@@ -48,6 +48,7 @@ LW_DECL_TU(0) LW_DECL_TU(1) LW_DECL_TU(2) LW_DECL_TU(3) LW_DECL_TU(4) LW_DECL_TU
 #endif
 #define LW_NUM_SWEEP_TUS 6
 void launch_colprep(const ColIn&, const Scratch&, const RunCfg&, cudaStream_t);
+void launch_cldoptics(const ColIn&, const Scratch&, const RunCfg&, cudaStream_t);  // needs the masks and secdiff
 void launch_taumol(const ColIn&, const Scratch&, const RunCfg&, cudaStream_t);
 #define LW_DECL_STU(n)                                                                                             \
     bool launch_sweep_stu##n(int b0, int nb, int cld, int idrv, const ColIn&, const ColOut&, const Scratch&, const RunCfg&, \

@@ -46,15 +46,14 @@ struct Grp {
 // ===== LW_PRECISION_BEGIN =====
 // shared-memory ring of one sweep kernel: rows of SWEEP_THREADS doubles per stage.  Rows [0, NGG): the optical depths as
 // NGG / 2 pair rows (thread t owns doubles [2 t, 2 t + 1] of a pair row); then one row each for tlay, tlev, the group's
-// Planck-fraction etas, two rows of 4-byte words (icldlyr word, mask word lo, mask word hi) and four cloud-optics inputs.
+// Planck-fraction etas and two rows of 4-byte words (icldlyr word, mask word lo, mask word hi).
 template <int B0, int NB>
 struct SweepRing {
     using G = Grp<B0, NB>;
     static constexpr int IPS = (int)(sizeof(double) / sizeof(int));
     static constexpr int S_TLAY = G::NGG, S_TLEV = G::NGG + 1, S_PF = G::NGG + 2;
     static constexpr int S_INT = S_PF + G::NPFG;
-    static constexpr int S_CLD = S_INT + 4 / IPS;
-    static constexpr int SLOTS = S_CLD + 4;
+    static constexpr int SLOTS = S_INT + 4 / IPS;
     static constexpr int NST = 2;
     static constexpr size_t BYTES = (size_t)NST * SLOTS * SWEEP_THREADS * sizeof(double);
 };
@@ -75,40 +74,46 @@ __device__ __forceinline__ void planck_pos(double t, int& it, double& frac) {
 
 // Planck fractions fracs(lay, g) of band B, rebuilt from the reduced fracref tables exactly as taugbB forms them
 // (e.g. taumol.f90:556-561, 692-693 for the eta-interpolated bands; a g-constant otherwise); sm = specmult of the
-// Planck-fraction interpolation passed by phase 1 (jpl = 1 + int(sm), fpl = mod(sm, 1))
+// Planck-fraction interpolation passed by phase 1 (jpl = 1 + int(sm), fpl = mod(sm, 1)).  The fraction of a g-point is
+// fetched where it is used (one or two L1-resident loads) instead of being held in registers across the g loop: the
+// registers buy more g-points in flight.  One straight-line form for every case: a + fpl * (b - a) with fpl = 0 and
+// b = a where the band takes a g-constant (bit-identical: a + 0 * 0 == a), times 0 where the reference sets fracs = 0.
 template <int B>
-__device__ __forceinline__ void planck_fracs(bool lower, double sm, double* pf) {
-    constexpr int NG = NGC[B - 1], RS = NGPAD[B - 1];
-    constexpr bool BIN_LO = NSPA[B - 1] == 9, BIN_UP = NSPB[B - 1] == 5;
-    const BandTab& T = C.bandp[B - 1];
-    double buf[RS];
-    auto rows2 = [&](const double* tab) {
+struct PlFrac {
+    static constexpr int RS = NGPAD[B - 1];
+    static constexpr bool BIN_LO = NSPA[B - 1] == 9, BIN_UP = NSPB[B - 1] == 5;
+    static constexpr bool ANY_BIN = BIN_LO || BIN_UP;
+    static constexpr bool HAS_ZERO = (B == 12 || B == 15);
+    const double* p0;
+    int dnext;     // element offset of the second row (0 = no interpolation)
+    double fpl;
+    bool zero;
+    __device__ __forceinline__ void setup(bool lower, double sm) {
+        const BandTab& T = C.bandp[B - 1];
         const int jpl = 1 + (int)sm;
-        const double fpl = sm - (double)(int)sm;
-        const double* p = tab + (jpl - 1) * RS;
-#pragma unroll
-        for (int g = 0; g < RS; g += 4) {
-            const D4 p0 = ldv<D4>(p + g), p1 = ldv<D4>(p + RS + g);
-            unpack(p0 + fpl * (p1 - p0), buf + g);
+        const double f = sm - (double)(int)sm;
+        zero = false;
+        if (lower) {
+            if constexpr (BIN_LO) { p0 = T.fracrefa + (jpl - 1) * RS; dnext = RS; fpl = f; }
+            else { p0 = T.fracrefa; dnext = 0; fpl = 0.; }
+        } else {
+            if constexpr (BIN_UP) { p0 = T.fracrefb + (jpl - 1) * RS; dnext = RS; fpl = f; }
+            else if constexpr (B == 6) { p0 = T.fracrefa; dnext = 0; fpl = 0.; }
+            else if constexpr (HAS_ZERO) { p0 = T.fracrefa; dnext = 0; fpl = 0.; zero = true; }
+            else { p0 = T.fracrefb; dnext = 0; fpl = 0.; }
         }
-    };
-    auto row1 = [&](const double* tab) {
-#pragma unroll
-        for (int g = 0; g < RS; g += 4) unpack(ldv<D4>(tab + g), buf + g);
-    };
-    if (lower) {
-        if constexpr (BIN_LO) rows2(T.fracrefa); else row1(T.fracrefa);
-    } else {
-        if constexpr (BIN_UP) rows2(T.fracrefb);
-        else if constexpr (B == 6) row1(T.fracrefa);
-        else if constexpr (B == 12 || B == 15) {
-#pragma unroll
-            for (int g = 0; g < RS; ++g) buf[g] = 0.0;
-        } else row1(T.fracrefb);
     }
-#pragma unroll
-    for (int g = 0; g < NG; ++g) pf[g] = buf[g];
-}
+    __device__ __forceinline__ double get(int g) const {
+        const double a = ldg(p0 + g);
+        double v = a;
+        if constexpr (ANY_BIN) {
+            const double b = ldg(p0 + dnext + g);
+            v = a + fpl * (b - a);
+        }
+        if constexpr (HAS_ZERO) v = zero ? 0.0 : v;
+        return v;
+    }
+};
 
 // cldprmc for one (sub-column, layer) of band B: cloud optical depth from the water paths and effective radii
 // (cldprmc.f90:177-266); tauc_in is the caller's value, returned unchanged unless inflag = 2 finds cloud water
@@ -158,9 +163,6 @@ __device__ __forceinline__ double cld_tauc(double ciwp, double clwp, double radi
     return tauc;
 }
 
-// One g-point of a layer that holds cloud in some sub-column (icldlyr = 1), rtrnmc.f90:358-425.  dpl = dplankdn on the
-// way down, dplankup on the way up; bb_gas / bb_tot are the Planck sources of the gas-only and the gas + cloud path
-// (bbd / bbdtot down, bbugas / bbutot up); gassrc is formed only on the way down, with the reference's association.
 // itr = int(tblint * tblind + 0.5) (rtrnmc.f90:386, 404, 412), kept inside the table for out-of-range cloud inputs
 // (a negative cloud optical depth would index the reference's tables out of bounds; here it must not fault the device)
 __device__ __forceinline__ int tbl_index(double tblind) {
@@ -168,74 +170,71 @@ __device__ __forceinline__ int tbl_index(double tblind) {
     return it < 0 ? 0 : (it > NTBL ? NTBL : it);
 }
 
-template <bool DOWN>
-__device__ __forceinline__ void cloudy_point(double odepth, double odc, double plfrac, double blay, double dpl,
-                                             double bpade, double& atrans, double& atot, double& bb_gas, double& bb_tot,
-                                             double& gassrc, int& d0, int& d1) {
-    const double rec_6 = 0.166667;
-    double odtot = odepth + odc;
-    d0 = -1; d1 = -1;
-    gassrc = 0.;
-    if (odtot < 0.06) {
-        atrans = odepth - 0.5 * odepth * odepth;
-        const double odepth_rec = rec_6 * odepth;
-        if (DOWN) gassrc = plfrac * fmadd(dpl, odepth_rec, blay) * atrans;
-        atot = odtot - 0.5 * odtot * odtot;
-        const double odtot_rec = rec_6 * odtot;
-        bb_tot = plfrac * fmadd(dpl, odtot_rec, blay);
-        bb_gas = plfrac * fmadd(dpl, odepth_rec, blay);
-    } else if (odepth <= 0.06) {
-        atrans = odepth - 0.5 * odepth * odepth;
-        const double odepth_rec = rec_6 * odepth;
-        if (DOWN) gassrc = plfrac * fmadd(dpl, odepth_rec, blay) * atrans;
-        odtot = odepth + odc;
-        const double tblind = odtot / (bpade + odtot);
-        const int ittot = tbl_index(tblind);
-        d1 = ittot;
-        const double2 et = __ldg(D.exptfn + ittot);
-        const double tfactot = et.y;
-        bb_tot = plfrac * fmadd(tfactot, dpl, blay);
-        bb_gas = plfrac * fmadd(dpl, odepth_rec, blay);
-        atot = 1. - et.x;
-    } else {
-        double tblind = odepth / (bpade + odepth);
-        const int itgas = tbl_index(tblind);
-        d0 = itgas;
-        odepth = ldg(D.tau_tbl + itgas);
-        const double2 eg = __ldg(D.exptfn + itgas);
-        atrans = 1. - eg.x;
-        const double tfacgas = eg.y;
-        if (DOWN) gassrc = atrans * plfrac * fmadd(tfacgas, dpl, blay);
-        odtot = odepth + odc;
-        tblind = odtot / (bpade + odtot);
-        const int ittot = tbl_index(tblind);
-        d1 = ittot;
-        const double2 et = __ldg(D.exptfn + ittot);
-        const double tfactot = et.y;
-        bb_tot = plfrac * fmadd(tfactot, dpl, blay);
-        bb_gas = plfrac * fmadd(tfacgas, dpl, blay);
-        atot = 1. - et.x;
-    }
+// predicated gathers: lanes that do not need the value issue no memory access
+__device__ __forceinline__ double2 ldg2_if(const double2* p, bool on) {
+    double2 v;
+#ifdef LW_F32
+    asm("{ .reg .pred q; setp.ne.s32 q, %3, 0; mov.f32 %0, 0f00000000; mov.f32 %1, 0f00000000;"
+        " @q ld.global.nc.v2.f32 {%0,%1}, [%2]; }" : "=f"(v.x), "=f"(v.y) : "l"(p), "r"((int)on));
+#else
+    v.x = 0.; v.y = 0.;
+    asm("{ .reg .pred q; setp.ne.s32 q, %3, 0; @q ld.global.nc.v2.f64 {%0,%1}, [%2]; }" : "+d"(v.x), "+d"(v.y) : "l"(p), "r"((int)on));
+#endif
+    return v;
+}
+__device__ __forceinline__ double ldg1_if(const double* p, bool on) {
+    double v;
+#ifdef LW_F32
+    asm("{ .reg .pred q; setp.ne.s32 q, %2, 0; mov.f32 %0, 0f00000000; @q ld.global.nc.f32 %0, [%1]; }"
+        : "=f"(v) : "l"(p), "r"((int)on));
+#else
+    asm("{ .reg .pred q; setp.ne.s32 q, %2, 0; mov.f64 %0, 0d0000000000000000; @q ld.global.nc.f64 %0, [%1]; }"
+        : "=d"(v) : "l"(p), "r"((int)on));
+#endif
+    return v;
 }
 
-// One g-point of a cloud-free layer, rtrnmc.f90:426-445, as selects instead of branches: both the small-optical-depth
-// series and the table lookup are evaluated and one is chosen, so that the g-points of a thread form independent
-// instruction streams.  bb = plfrac * (blay + tausfac * dpl) is bbd on the way down and bbugas on the way up.
-__device__ __forceinline__ void clear_point(double odepth, double plfrac, double blay, double dpl, double bpade,
-                                            double& atrans, double& bb, int& itr_out) {
+// Gas-only transmittance and Planck source of one (g, layer) from the state word of phase 1 (lw_taumol.cuh
+// od_state): the optical depth itself where the reference takes its small-optical-depth series (odepth <= 0.06,
+// rtrnmc.f90:429-431), the table index itr where it takes the lookup (:433-440).  bb = plfrac * (blay + tausfac * dpl)
+// is bbd on the way down (dpl = dplankdn) and bbugas on the way up (dpl = dplankup).  Selects, no branches: the
+// g-points of a thread form independent instruction streams; the table gather is issued only by the lanes that use it.
+__device__ __forceinline__ void gas_point(double st, double plfrac, double blay, double dpl, double& atrans, double& bb,
+                                          bool& big, int& itr) {
     const double rec_6 = 0.166667;
-    const bool small = odepth <= 0.06;
-    const double tblind = div_fast(odepth, bpade + odepth);
-    const int itr = (int)(10000.0 * tblind + 0.5);
-    const double2 e = __ldg(D.exptfn + itr);
-#ifdef LW_TAIL_FMA
-    atrans = small ? fmadd(-0.5 * odepth, odepth, odepth) : 1. - e.x;
+    big = od_state_is_index(st);
+    itr = od_state_index(st);
+#ifdef LW_EXP_FAKE_GATHER   // bounding experiment: every gather hits the same few L1 lines (wrong results)
+    const double2 e = ldg2_if(D.exptfn + 2000 + (itr & 31), big);
 #else
-    atrans = small ? odepth - 0.5 * odepth * odepth : 1. - e.x;
+    const double2 e = ldg2_if(D.exptfn + itr, big);
 #endif
-    const double tausfac = small ? rec_6 * odepth : e.y;
+#ifdef LW_TAIL_FMA
+    atrans = big ? 1. - e.x : fmadd(-0.5 * st, st, st);
+#else
+    atrans = big ? 1. - e.x : st - 0.5 * st * st;
+#endif
+    const double tausfac = big ? e.y : rec_6 * st;
     bb = plfrac * fmadd(tausfac, dpl, blay);
-    itr_out = small ? -1 : itr;
+}
+
+// Gas + cloud path of a sub-column that holds cloud (cldfmc = 1) in this layer, rtrnmc.f90:358-425: total optical depth
+// odtot = odepth + odcld, where the gas part is the table value tau_tbl(itgas) once it has gone through the lookup
+// (:387); atot / bb_tot from the series (odtot < 0.06) or from the lookup at ittot.  Lanes with on = false get
+// finite don't-care values and touch no memory.
+__device__ __forceinline__ void cloud_point(double st, bool big, int itr, double odc, bool on, double plfrac, double blay,
+                                            double dpl, double bpade, double& atot, double& bb_tot, int& ittot_out) {
+    const double rec_6 = 0.166667;
+    const double odg = big ? ldg1_if(D.tau_tbl + itr, on && big) : st;
+    const double odtot = odg + odc;
+    const bool tsmall = odtot < 0.06;
+    const double tblind = div_fast(odtot, bpade + odtot);
+    const int ittot = tbl_index(tblind);
+    const double2 et = ldg2_if(D.exptfn + ittot, on && !tsmall);
+    atot = tsmall ? odtot - 0.5 * odtot * odtot : 1. - et.x;
+    const double tfactot = tsmall ? rec_6 * odtot : et.y;
+    bb_tot = plfrac * fmadd(tfactot, dpl, blay);
+    ittot_out = tsmall ? -1 : ittot;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -279,7 +278,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
     double* S_OC = s.gcld + (long)NGPT * plane;
 
     // ---- asynchronous prefetch of one layer's inputs into this thread's slots of ring stage `stage`.
-    // DOWN: tlev = level below the layer (planklev(lev-1)), cloud-optics inputs ride along; UP: tlev = level above.
+    // DOWN: tlev = level below the layer (planklev(lev-1)); UP: tlev = level above.
     auto issue = [&](int stage, int lev, bool down) {
         if (lev >= 1 && lev <= nlay) {
             const int l0 = lev - 1;
@@ -303,12 +302,6 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
                     constexpr int wlo = G0 >> 5, sh = G0 & 31;
                     cp_async4(di(1), mw + (long)wlo * P);
                     if constexpr (sh + NGG > 32) cp_async4(di(2), mw + (long)(wlo + 1) * P);
-                    if (down && lev <= ctop) {  // cloud-optics inputs: only layers at or below the column's cloud top can need them
-                        cp_async_val(dst + (RG::S_CLD + 0) * SWEEP_THREADS + tid, in.ciwp + a);
-                        cp_async_val(dst + (RG::S_CLD + 1) * SWEEP_THREADS + tid, in.clwp + a);
-                        cp_async_val(dst + (RG::S_CLD + 2) * SWEEP_THREADS + tid, in.rei + a);
-                        cp_async_val(dst + (RG::S_CLD + 3) * SWEEP_THREADS + tid, in.rel + a);
-                    }
                 }
             }
         }
@@ -328,6 +321,14 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
         unsigned lo = ((unsigned)st_i(stage, 1)) >> sh;
         if constexpr (sh + NGG > 32) lo |= ((unsigned)st_i(stage, 2)) << (32 - sh);
         return NGG == 32 ? lo : (lo & ((1u << (NGG & 31)) - 1u));
+    };
+    auto prefetch_entries = [&](int stg) {
+#pragma unroll
+        for (int p = 0; p < NGG / 2; ++p) {
+            const double2 w = st_od(stg, p);
+            if (od_state_is_index(w.x)) asm volatile("prefetch.global.L1 [%0];" ::"l"(D.exptfn + od_state_index(w.x)));
+            if (od_state_is_index(w.y)) asm volatile("prefetch.global.L1 [%0];" ::"l"(D.exptfn + od_state_index(w.y)));
+        }
     };
     auto for_bands = [&](auto&& f) {
         f(IC<0>{});
@@ -377,73 +378,79 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
             constexpr int GO = GR::goff(K);
             const double blay = planck_at<B>(it_lay, fr_lay);
             const double dplankdn = planck_at<B>(it_lev, fr_lev) - blay;  // planklev(lev-1) - planklay(lev)
-            double pf[NG];
             double sm = 0.;
             if constexpr (pf_slot(B) >= 0) sm = st_d(stage, RG::S_PF + pf_slot(B) - GR::PF0);
-            planck_fracs<B>(lower, sm, pf);
-            // cloud state of this (column, layer) for this band
+            PlFrac<B> pf;
+            pf.setup(lower, sm);
+            // cloud state of this (column, layer) for this band: sub-column bits of the McICA mask; the band's cloud
+            // optical depth along the diffusivity angle and its absorptivity come from the cloud-optics kernel
             unsigned bits = 0;
             double odcld_b = 0., abscld_b = 0.;
             if constexpr (CLD == CLD_MASK) {
                 if (cldlyr) {
                     bits = (gbits >> GO) & ((1u << NG) - 1u);
-                    if (bits) {
-                        const double tauc_in = in.tauc ? in.tauc[(B - 1) + 16 * a] : 0.0;
-                        const double tauc = cld_tauc<B>(st_d(stage, RG::S_CLD), st_d(stage, RG::S_CLD + 1), st_d(stage, RG::S_CLD + 2),
-                                                        st_d(stage, RG::S_CLD + 3), tauc_in, r);
-                        odcld_b = ldg(s.secdiff + (long)(B - 1) * P + i) * tauc;
-                        abscld_b = 1. - exp(-odcld_b);
-                        if (live) { double* q = cldb(l0, B); q[0] = odcld_b; q[128] = abscld_b; }
-                    }
+                    if (bits) { const double* q = cldb(l0, B); odcld_b = __ldg(q); abscld_b = __ldg(q + 128); }
                 }
             }
             acc_t dsum = 0., dcsum = 0.;
-            if (CLD != CLD_NONE && cldlyr) {
+            // does any column of the warp hold cloud in this band's sub-columns of this layer?  (warp-uniform: the
+            // loop with the cloud path is straight-line code for all lanes, the one without it never sees a cloud)
+            bool wcld = false;
+            if constexpr (CLD == CLD_MASK) wcld = __any_sync(0xffffffffu, bits != 0);
+            if constexpr (CLD == CLD_ARRAYS) wcld = __any_sync(0xffffffffu, cldlyr);
+            if (CLD != CLD_NONE && wcld) {
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
                     const double2 odp = st_od(stage, (GO + g) >> 1);
-                    const double odepth = ((GO + g) & 1) ? odp.y : odp.x;
-                    double cf, odc, ef;
+                    const double st = ((GO + g) & 1) ? odp.y : odp.x;
+                    double atrans, bbd;
+                    bool big;
+                    int itr;
+                    gas_point(st, pf.get(g), blay, dplankdn, atrans, bbd, big, itr);
+                    bool on;
+                    double odc, ef;
                     if constexpr (CLD == CLD_MASK) {
-                        const bool on = (bits >> g) & 1u;
-                        cf = on ? 1. : 0.; odc = on ? odcld_b : 0.; ef = on ? abscld_b : 0.;
+                        on = (bits >> g) & 1u;
+                        odc = on ? odcld_b : 0.; ef = on ? abscld_b : 0.;
                     } else {
-                        // strict rrtmg_lw(): per-g cloud arrays, cldprmc evaluated on the fly
-                        const long ag = (G0 + GO + g) + 140 * a;
-                        cf = in.cldfmcl[ag];
-                        double tauc = in.taucmcl[ag];
-                        if (cf >= 1.e-20) tauc = cld_tauc<B>(in.ciwpmcl[ag], in.clwpmcl[ag], in.reicmcl[a], in.relqmcl[a], tauc, r);
-                        if (cf == 1.) {
-                            odc = ldg(s.secdiff + (long)(B - 1) * P + i) * tauc;
-                            ef = (1. - exp(-odc)) * cf;
-                        } else {
-                            odc = 0.; ef = 0.;
+                        // strict rrtmg_lw(): per-g cloud arrays, cldprmc evaluated on the fly; only cldfmc == 1 is
+                        // cloud to rtrnmc (rtrnmc.f90:316-329)
+                        on = false; odc = 0.; ef = 0.;
+                        if (cldlyr) {
+                            const long ag = (G0 + GO + g) + 140 * a;
+                            const double cf = in.cldfmcl[ag];
+                            if (cf == 1.) {
+                                const double tauc = cld_tauc<B>(in.ciwpmcl[ag], in.clwpmcl[ag], in.reicmcl[a], in.relqmcl[a],
+                                                                in.taucmcl[ag], r);
+                                on = true;
+                                odc = ldg(s.secdiff + (long)(B - 1) * P + i) * tauc;
+                                ef = (1. - exp(-odc)) * cf;
+                            }
+                            if (live) { S_EF[(long)(G0 + GO + g) * plane + idx] = ef; S_OC[(long)(G0 + GO + g) * plane + idx] = odc; }
                         }
-                        if (live) { S_EF[(long)(G0 + GO + g) * plane + idx] = ef; S_OC[(long)(G0 + GO + g) * plane + idx] = odc; }
                     }
-                    double atrans, atot, bbd, bbdtot, gassrc;
-                    int d0, d1;
-                    cloudy_point<true>(odepth, odc, pf[g], blay, dplankdn, bpade, atrans, atot, bbd, bbdtot, gassrc, d0, d1);
-                    radld[GO + g] = relaxed_cld(radld[GO + g], atrans + ef * (1. - atrans), gassrc, cf * (bbdtot * atot - gassrc));
+                    double atot, bbdtot;
+                    int ittot;
+                    cloud_point(st, big, itr, odc, on, pf.get(g), blay, dplankdn, bpade, atot, bbdtot, ittot);
+                    const double gassrc = bbd * atrans;
+                    const acc_t xc = relaxed_cld(radld[GO + g], atrans + ef * (1. - atrans), gassrc, bbdtot * atot - gassrc);
+                    const acc_t xr = relaxed(radld[GO + g], bbd, atrans);
+                    radld[GO + g] = on ? xc : xr;
                     dsum = dsum + radld[GO + g];
                     // clear-sky stream: identical to the total stream until the first cloudy layer from the top
                     const acc_t sep = relaxed(radclrd[GO + g], bbd, atrans);
                     radclrd[GO + g] = (lev <= ctop) ? sep : radld[GO + g];
                     dcsum = dcsum + radclrd[GO + g];
-                    if (dbg) {
-                        const long o = (long)(G0 + GO + g) * nlay + l0;
-                        s.dbg_fracs[o] = pf[g];
-                        s.dbg_itr[2 * o] = d0; s.dbg_itr[2 * o + 1] = d1;
-                    }
                 }
             } else {
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
                     const double2 odp = st_od(stage, (GO + g) >> 1);
-                    const double odepth = ((GO + g) & 1) ? odp.y : odp.x;
+                    const double st = ((GO + g) & 1) ? odp.y : odp.x;
                     double atrans, bbd;
+                    bool big;
                     int itr;
-                    clear_point(odepth, pf[g], blay, dplankdn, bpade, atrans, bbd, itr);
+                    gas_point(st, pf.get(g), blay, dplankdn, atrans, bbd, big, itr);
                     radld[GO + g] = relaxed(radld[GO + g], bbd, atrans);
                     dsum = dsum + radld[GO + g];
                     if (CLD != CLD_NONE) {
@@ -451,11 +458,30 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
                         radclrd[GO + g] = (lev <= ctop) ? sep : radld[GO + g];
                         dcsum = dcsum + radclrd[GO + g];
                     }
-                    if (dbg) {
-                        const long o = (long)(G0 + GO + g) * nlay + l0;
-                        s.dbg_fracs[o] = pf[g];
-                        s.dbg_itr[2 * o] = itr; s.dbg_itr[2 * o + 1] = -1;
+                }
+            }
+            // stage dump of the captured column (kept out of the g loops: a branch per g-point would cut the straight-line
+            // code the scheduler interleaves): Planck fractions and the table indices itgas / ittot the reference forms
+            // (ittot for every sub-column of a layer with icldlyr = 1, rtrnmc.f90:386, 404, 412)
+            if (dbg) {
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    const double2 odp = st_od(stage, (GO + g) >> 1);
+                    const double st = ((GO + g) & 1) ? odp.y : odp.x;
+                    const bool big = od_state_is_index(st);
+                    const int itr = od_state_index(st);
+                    const long o = (long)(G0 + GO + g) * nlay + l0;
+                    s.dbg_fracs[o] = pf.get(g);
+                    s.dbg_itr[2 * o] = big ? itr : -1;
+                    int d1 = -1;
+                    if (CLD != CLD_NONE && cldlyr) {
+                        double odc = 0.;
+                        if constexpr (CLD == CLD_MASK) odc = ((bits >> g) & 1u) ? odcld_b : 0.;
+                        if constexpr (CLD == CLD_ARRAYS) odc = S_OC[(long)(G0 + GO + g) * plane + idx];
+                        double t0, t1;
+                        cloud_point(st, big, itr, odc, true, pf.get(g), blay, dplankdn, bpade, t0, t1, d1);
                     }
+                    s.dbg_itr[2 * o + 1] = d1;
                 }
             }
             // band close-out for level lev-1: flux += (rad * wtdiff) * delwave, rtrnmc.f90:538-550
@@ -467,6 +493,12 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
             o[0] = acc_d;
             if (CLD != CLD_NONE && ctop > 0) o[128] = acc_dc;
         }
+#ifdef LW_SWEEP_PREFETCH
+        // the next layer's state words arrived in the other stage one layer ago: put the exp/tfn entries its table
+        // lookups will gather into L1 now, so that the gathers of the next layer find them there
+        cp_wait<0>();
+        if (lev > 1) prefetch_entries(stage ^ 1);
+#endif
         issue(stage, lev - RG::NST, true);
         stage ^= 1;
     }
@@ -518,14 +550,14 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
                 dplankbnd_dt = semiss * (da + fr_b * (db - da));
             }
             const double reflect = 1. - semiss;
-            double pf[NG];
             double sm = 0.;
             if constexpr (pf_slot(B) >= 0) sm = pf_src(0)[(pf_slot(B) - GR::PF0) * 128];
-            planck_fracs<B>(lower1, sm, pf);  // fracs(1, g)
+            PlFrac<B> pf;
+            pf.setup(lower1, sm);  // fracs(1, g)
             acc_t usum = 0., ucsum = 0., dusum = 0.;
 #pragma unroll
             for (int g = 0; g < NG; ++g) {
-                const double rad0 = pf[g] * plankbnd;
+                const double rad0 = pf.get(g) * plankbnd;
                 radlu[GO + g] = rad0 + reflect * radld[GO + g];
                 radclru[GO + g] = rad0 + reflect * radclrd[GO + g];
             }
@@ -537,7 +569,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
             if constexpr (IDRV == 1) {
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
-                    d_radlu[GO + g] = pf[g] * dplankbnd_dt;
+                    d_radlu[GO + g] = pf.get(g) * dplankbnd_dt;
                     d_radclru[GO + g] = d_radlu[GO + g];
                     dusum = dusum + d_radlu[GO + g];
                 }
@@ -595,42 +627,57 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
             constexpr int GO = GR::goff(K);
             const double blay = planck_at<B>(it_lay, fr_lay);
             const double dplankup = planck_at<B>(it_lev, fr_lev) - blay;  // planklev(lev) - planklay(lev)
-            double pf[NG];
             double sm = 0.;
             if constexpr (pf_slot(B) >= 0) sm = st_d(stage, RG::S_PF + pf_slot(B) - GR::PF0);
-            planck_fracs<B>(lower, sm, pf);
+            PlFrac<B> pf;
+            pf.setup(lower, sm);
             unsigned bits = 0;
             double odcld_b = 0., abscld_b = 0.;
             if constexpr (CLD == CLD_MASK) {
                 if (cldlyr) {
                     bits = (gbits >> GO) & ((1u << NG) - 1u);
-                    if (bits) { const double* q = cldb(l0, B); odcld_b = __ldcg(q); abscld_b = __ldcg(q + 128); }
+                    if (bits) { const double* q = cldb(l0, B); odcld_b = __ldg(q); abscld_b = __ldg(q + 128); }
                 }
             }
             acc_t usum = 0., ucsum = 0., dusum = 0., ducsum = 0.;
-            if (CLD != CLD_NONE && cldlyr) {
+            bool wcld = false;
+            if constexpr (CLD == CLD_MASK) wcld = __any_sync(0xffffffffu, bits != 0);
+            if constexpr (CLD == CLD_ARRAYS) wcld = __any_sync(0xffffffffu, cldlyr);
+            if (CLD != CLD_NONE && wcld) {
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
                     const double2 odp = st_od(stage, (GO + g) >> 1);
-                    const double odepth = ((GO + g) & 1) ? odp.y : odp.x;
-                    double cf, odc, ef;
+                    const double st = ((GO + g) & 1) ? odp.y : odp.x;
+                    double atrans, bbugas;
+                    bool big;
+                    int itr;
+                    gas_point(st, pf.get(g), blay, dplankup, atrans, bbugas, big, itr);
+                    bool on;
+                    double odc, ef;
                     if constexpr (CLD == CLD_MASK) {
-                        const bool on = (bits >> g) & 1u;
-                        cf = on ? 1. : 0.; odc = on ? odcld_b : 0.; ef = on ? abscld_b : 0.;
+                        on = (bits >> g) & 1u;
+                        odc = on ? odcld_b : 0.; ef = on ? abscld_b : 0.;
                     } else {
-                        cf = in.cldfmcl[(G0 + GO + g) + 140 * a];
-                        ef = S_EF[(long)(G0 + GO + g) * plane + idx];
-                        odc = S_OC[(long)(G0 + GO + g) * plane + idx];
+                        on = false; odc = 0.; ef = 0.;
+                        if (cldlyr) {
+                            on = in.cldfmcl[(G0 + GO + g) + 140 * a] == 1.;
+                            ef = S_EF[(long)(G0 + GO + g) * plane + idx];
+                            odc = S_OC[(long)(G0 + GO + g) * plane + idx];
+                        }
                     }
-                    double atrans, atot, bbugas, bbutot, unused;
-                    int d0, d1;
-                    cloudy_point<false>(odepth, odc, pf[g], blay, dplankup, bpade, atrans, atot, bbugas, bbutot, unused, d0, d1);
+                    double atot, bbutot;
+                    int ittot;
+                    cloud_point(st, big, itr, odc, on, pf.get(g), blay, dplankup, bpade, atot, bbutot, ittot);
                     const double gassrc = bbugas * atrans;
-                    radlu[GO + g] = relaxed_cld(radlu[GO + g], atrans + ef * (1. - atrans), gassrc, cf * (bbutot * atot - gassrc));
-                    if constexpr (IDRV == 1)
-                        d_radlu[GO + g] = d_radlu[GO + g] * cf * (1.0 - atot) + d_radlu[GO + g] * (1.0 - cf) * (1.0 - atrans);
+                    const acc_t xc = relaxed_cld(radlu[GO + g], atrans + ef * (1. - atrans), gassrc, bbutot * atot - gassrc);
+                    const acc_t xr = relaxed(radlu[GO + g], bbugas, atrans);
+                    radlu[GO + g] = on ? xc : xr;
                     usum = usum + radlu[GO + g];
-                    if constexpr (IDRV == 1) dusum = dusum + d_radlu[GO + g];
+                    if constexpr (IDRV == 1) {
+                        // d_radlu * cldfmc * (1 - atot) + d_radlu * (1 - cldfmc) * (1 - atrans) with cldfmc = 0 or 1
+                        d_radlu[GO + g] = d_radlu[GO + g] * (1.0 - (on ? atot : atrans));
+                        dusum = dusum + d_radlu[GO + g];
+                    }
                     radclru[GO + g] = relaxed(radclru[GO + g], bbugas, atrans);
                     ucsum = ucsum + radclru[GO + g];
                     if constexpr (IDRV == 1) {
@@ -642,10 +689,11 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
                     const double2 odp = st_od(stage, (GO + g) >> 1);
-                    const double odepth = ((GO + g) & 1) ? odp.y : odp.x;
+                    const double st = ((GO + g) & 1) ? odp.y : odp.x;
                     double atrans, bbugas;
+                    bool big;
                     int itr;
-                    clear_point(odepth, pf[g], blay, dplankup, bpade, atrans, bbugas, itr);
+                    gas_point(st, pf.get(g), blay, dplankup, atrans, bbugas, big, itr);
                     radlu[GO + g] = relaxed(radlu[GO + g], bbugas, atrans);
                     usum = usum + radlu[GO + g];
                     if constexpr (IDRV == 1) {
@@ -678,6 +726,10 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
                 if (CLD != CLD_NONE && ctop > 0) o[640] = acc_duc;
             }
         }
+#ifdef LW_SWEEP_PREFETCH
+        cp_wait<0>();
+        if (lev < nlay) prefetch_entries(stage ^ 1);
+#endif
         issue(stage, lev + RG::NST, false);
         stage ^= 1;
     }

@@ -29,6 +29,21 @@ constexpr int TAUMOL_THREADS = 128;
 // ===== LW_COMMON_END =====
 
 // ===== LW_PRECISION_BEGIN =====
+// The 8-byte sweep-state word of one (g, layer, column).  rtrnmc uses the layer optical depth odepth in one of two ways
+// (rtrnmc.f90:429-440): odepth <= 0.06 -> the small-optical-depth series in odepth itself; otherwise ONLY through the
+// table index itr = int(1e4 * odepth / (bpade + odepth) + 0.5) (transmittance exp_tbl(itr), Planck weight
+// tfn_tbl(itr), and in cloudy layers the table optical depth tau_tbl(itr), :386-387).  Phase 1 therefore stores the
+// optical depth itself in the first case and the index in the second -- as the low word of a double whose sign bit is
+// set (an optical depth is never negative) -- so that the sweeps, which run the vertical recurrences and are latency
+// bound, neither divide nor convert: the division happens once here, where the FP64 pipe has idle slots.
+__device__ __forceinline__ double od_state(double odepth, double bpade) {
+    const double tblind = div_fast(odepth, bpade + odepth);
+    const int itr = (int)(10000.0 * tblind + 0.5);
+    return odepth <= 0.06 ? odepth : __hiloint2double((int)0x80000000u, itr);
+}
+__device__ __forceinline__ bool od_state_is_index(double st) { return __double2hiint(st) < 0; }
+__device__ __forceinline__ int od_state_index(double st) { return __double2loint(st); }
+
 // setcoef fields of this thread's (column, layer): its own column of a [field][thread] block of shared memory
 struct LayerFs {
     const double* base;
@@ -64,7 +79,7 @@ __device__ __forceinline__ void band_odepth(const LayerFs& L, int ipk, bool lowe
                 for (int k = 0; k < 2; ++k) {
                     const double taut = a[j + k] + taua;  // rad.f90:548-553
                     const double odepth = secdiff * taut; // rtrnmc.f90:352
-                    od[k] = odepth < 0.0 ? 0.0 : odepth;
+                    od[k] = od_state(odepth < 0.0 ? 0.0 : odepth, C.bpade);
                     if (dbg) s.dbg_taug[(long)(G0 + g + j + k) * nlay + l] = a[j + k];
                 }
                 if (live) __stcs(reinterpret_cast<double2*>(odp + (G0 + g + j) * TAUMOL_THREADS), make_double2(od[0], od[1]));
@@ -199,16 +214,67 @@ __global__ void __launch_bounds__(TAUMOL_THREADS, MINB) taumol_kernel(ColIn in, 
 
     // ---- taumol, band by band (loops 1..laytrop / laytrop+1..nlayers, taumol.f90:335, 367)
     const bool lower = l < s.laytrop[i];
-    const LayerFs L{fq};
+#ifndef LW_TAUMOL_NO_SORT
+    // The band evaluations are bound by the L1 data pipe: every lane pulls its own k-table rows into registers, and a
+    // 256-bit load costs the fewer L1 wavefronts the fewer distinct rows the lanes of an 8-lane group touch.  Columns of
+    // a CTA are independent, so the (column -> lane) assignment is free: a counting sort on the (pressure level jp,
+    // temperature index jt) pair puts columns that read the same (p, T) corner rows in neighbouring lanes.  Each thread
+    // then evaluates the bands of the column it was handed (fields, indices and flags come from shared memory).
+    __shared__ int sh_hist[64];
+    __shared__ int sh_perm[TAUMOL_THREADS];
+    __shared__ int sh_ipk[TAUMOL_THREADS];
+    __shared__ double sh_pavel[TAUMOL_THREADS];
+    __shared__ int sh_jpmin;
+    if (tid < 64) sh_hist[tid] = 0;
+    if (tid == 0) sh_jpmin = 64;
+    sh_ipk[tid] = ipk | (lower ? (1 << 30) : 0);
+    sh_pavel[tid] = pavel;
+    __syncthreads();
+    atomicMin(&sh_jpmin, jp);
+    __syncthreads();
+    int bin = (jp - sh_jpmin) * 5 + (jt - 1);
+    bin = bin > 63 ? 63 : bin;
+    const int pos = atomicAdd(&sh_hist[bin], 1);
+    __syncthreads();
+    if (tid < 32) {  // exclusive scan of the 64 bin counts
+        const int c0 = sh_hist[2 * tid], c1 = sh_hist[2 * tid + 1];
+        int incl = c0 + c1;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, d);
+            if (tid >= d) incl += up;
+        }
+        const int excl = incl - (c0 + c1);
+        sh_hist[2 * tid] = excl;
+        sh_hist[2 * tid + 1] = excl + c0;
+    }
+    __syncthreads();
+    sh_perm[sh_hist[bin] + pos] = tid;
+    __syncthreads();
+    const int src = sh_perm[tid];                       // the column (of this CTA) this thread evaluates
+    const int i_src_raw = blockIdx.x * TAUMOL_THREADS + src;
+    const bool live_e = i_src_raw < r.ncol;
+    const int i_e = live_e ? i_src_raw : r.ncol - 1;
+    const int ipk_e = sh_ipk[src] & ~(1 << 30);
+    const bool lower_e = (sh_ipk[src] >> 30) & 1;
+    const double pavel_e = sh_pavel[src];
+    const bool dbg_e = live_e && (s.dbg_col == i_e);
+#else
+    const int src = tid;
+    const bool live_e = live, lower_e = lower, dbg_e = dbg;
+    const int i_e = i, ipk_e = ipk;
+    const double pavel_e = pavel;
+#endif
+    const LayerFs L{fs + src};
     const long rec = (long)blockIdx.x * nlay + l;  // (column block, layer)
-    double* odp = s.od + rec * NGPT * TAUMOL_THREADS + 2 * tid;
-    double* pfp = s.pfs + rec * NPF * TAUMOL_THREADS + tid;
-    const double* sdp = s.secdiff + i;
-    const double* tap = in.tauaer + ci + in.ld * l;
+    double* odp = s.od + rec * NGPT * TAUMOL_THREADS + 2 * src;
+    double* pfp = s.pfs + rec * NPF * TAUMOL_THREADS + src;
+    const double* sdp = s.secdiff + i_e;
+    const double* tap = in.tauaer + (r.c0 + i_e) + in.ld * l;
     const long tas = in.ld * (long)nlay;
 #define LW_BAND(B)                                                                                                   \
     if constexpr ((BMASK >> (B - 1)) & 1u)                                                                           \
-        band_odepth<B>(L, ipk, lower, pavel, sdp[(long)(B - 1) * s.pitch], tap[tas * (B - 1)], odp, pfp, live, dbg, s, l, nlay);
+        band_odepth<B>(L, ipk_e, lower_e, pavel_e, sdp[(long)(B - 1) * s.pitch], tap[tas * (B - 1)], odp, pfp, live_e, dbg_e, s, l, nlay);
     LW_BAND(1) LW_BAND(2) LW_BAND(3) LW_BAND(4) LW_BAND(5) LW_BAND(6) LW_BAND(7) LW_BAND(8)
     LW_BAND(9) LW_BAND(10) LW_BAND(11) LW_BAND(12) LW_BAND(13) LW_BAND(14) LW_BAND(15) LW_BAND(16)
 #undef LW_BAND

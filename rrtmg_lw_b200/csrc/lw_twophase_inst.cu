@@ -30,8 +30,11 @@ void launch_taumol(const ColIn& in, const Scratch& s, const RunCfg& r, cudaStrea
 #else
 
 // registers a sweep kernel wants: the group's recurrences (total + clear stream, + their dT derivatives) and ~70 more
+#ifndef LW_SWEEP_BASE_REGS
+#define LW_SWEEP_BASE_REGS 72
+#endif
 constexpr int sweep_minb(int ngg, int cld, int idrv) {
-    const int est = (cld != CLD_NONE ? 4 : 2) * ngg * (idrv ? 2 : 1) + 72;
+    const int est = (cld != CLD_NONE ? 4 : 2) * ngg * (idrv ? 2 : 1) + LW_SWEEP_BASE_REGS;
     return est <= 128 ? 4 : (est <= 168 ? 3 : 2);
 }
 

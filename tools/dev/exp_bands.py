@@ -32,8 +32,14 @@ cl = [b.cldfrac, b.ciwp, b.clwp, b.rei, b.rel, b.tauc]
 du = torch.zeros_like(out["uflx"]) if idrv else None
 duc = torch.zeros_like(out["uflx"]) if idrv else None
 
+icld = int(os.environ.get("EXP_ICLD", 2))
+
 def step():
-    api.rrtmg_lw_mcica(ncol, 72, 2, idrv, 1, 0, *at, 2, 3, 1, *cl, None, b.tauaer, out["uflx"], out["dflx"],
+    if icld == 0:   # clear sky through the strict entry
+        api.rrtmg_lw(ncol, 72, 0, idrv, *at, 0, 0, 0, None, None, None, None, None, None, b.tauaer, out["uflx"],
+                     out["dflx"], out["hr"], out["uflxc"], out["dflxc"], out["hrc"], du, duc)
+        return
+    api.rrtmg_lw_mcica(ncol, 72, icld, idrv, 1, 0, *at, 2, 3, 1, *cl, None, b.tauaer, out["uflx"], out["dflx"],
                        out["hr"], out["uflxc"], out["dflxc"], out["hrc"], du, duc)
 
 step(); step()
