@@ -33,6 +33,13 @@ struct Ctx {
     double *d_absice2 = nullptr, *d_absice3 = nullptr, *d_absliq1 = nullptr;
     // scratch, sized for (cap_cols, cap_lay)
     Scratch S{};
+    SweepTab sweep_tab{};     // tables of the sweep kernels (kernel parameter)
+    // two-phase path: the McICA generator / cloud optics run beside the taumol kernel, and the sweep kernels (which own
+    // their flux slots) beside each other, on side streams forked from and joined to the caller's stream
+    static constexpr int NSIDE = 3;
+    cudaStream_t side[NSIDE] = {};
+    cudaEvent_t e_fork = nullptr, e_colprep = nullptr, e_t = nullptr, e_cld = nullptr, e_side[NSIDE] = {};
+    int concurrency = 1;      // set_option("concurrency", 0) keeps every kernel on the caller's stream
     long cap_cols = 0;
     int cap_lay = 0;
     unsigned have = 0;        // ScratchPiece bits allocated at the current capacity
@@ -45,7 +52,8 @@ struct Ctx {
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t e_in[2] = {nullptr, nullptr}, e_done[2] = {nullptr, nullptr}, e_out[2] = {nullptr, nullptr};
     int band_kernel = 4;  // 4 = two-phase path (lw_taumol.cuh + lw_rtrnmc.cuh), 2 = fused per-band kernels (lw_band.cuh)
-    int sweep_groups = 1; // two-phase path: 1 = sweep kernels over the default band groups, 0 = one sweep kernel per band
+    int sweep_groups = 0; // two-phase path: 0 = one sweep kernel per band (band sums added in the reference's order),
+                          // 1 = sweep kernels over band groups {1,2} {3} {4} {5} {6,7} {8,9} {10-12} {13-16}
     int band_lo = 1, band_hi = NBND;  // band range of a run (two-phase path; the column-mode harness' istart / iend)
     int nstage = 0;       // timed stages of the last timed pass (ms_bands[0 .. nstage))
     int sms = 0;
@@ -126,7 +134,6 @@ int ensure_scratch(long cols, int nlay, unsigned need) {
         if (A(&S.laytrop, (size_t)P)) return RRTMG_LW_ERR_CUDA;
         if (A(&S.mask, 5 * plane)) return RRTMG_LW_ERR_CUDA;
         if (A(&S.ctop, (size_t)P)) return RRTMG_LW_ERR_CUDA;
-        if (A(&S.fluxB, (size_t)6 * (nlay + 1) * P)) return RRTMG_LW_ERR_CUDA;
         if (A(&S.status, (size_t)1)) return RRTMG_LW_ERR_CUDA;
         CK(cudaMemset(S.status, 0, sizeof(unsigned long long)));
         if (A(&S.dbg_taug, (size_t)NGPT * nlay)) return RRTMG_LW_ERR_CUDA;
@@ -143,6 +150,7 @@ int ensure_scratch(long cols, int nlay, unsigned need) {
         if (A(&S.ipack, plane)) return RRTMG_LW_ERR_CUDA;
         if (A(&S.state, (size_t)5 * 16 * plane)) return RRTMG_LW_ERR_CUDA;
         if (A(&S.abscld, plane)) return RRTMG_LW_ERR_CUDA;
+        if (A(&S.fluxB, (size_t)6 * (nlay + 1) * P)) return RRTMG_LW_ERR_CUDA;
         // FP32 mode: the float kernels reuse the same memory through float views
         S.fldf = reinterpret_cast<float*>(S.fld);
         S.statef = reinterpret_cast<float*>(S.state);
@@ -152,6 +160,7 @@ int ensure_scratch(long cols, int nlay, unsigned need) {
         if (A(&S.od, (size_t)NGPT * plane)) return RRTMG_LW_ERR_CUDA;
         if (A(&S.pfs, (size_t)NPF * plane)) return RRTMG_LW_ERR_CUDA;
         if (A(&S.secdiff, (size_t)NBND * P)) return RRTMG_LW_ERR_CUDA;
+        if (A(&S.fluxP, (size_t)NBND * 6 * (nlay + 1) * P)) return RRTMG_LW_ERR_CUDA;
     }
     if (miss & SP_CLDB) {
         if (A(&S.cldb, (size_t)2 * NBND * plane)) return RRTMG_LW_ERR_CUDA;
@@ -206,14 +215,23 @@ bool launch_band32(int band, int cld, int idrv, const ColInF& in, const ColOut& 
 // sweep kernels of bands [b0, b0 + nb) of the two-phase path
 bool launch_sweep(int b0, int nb, int cld, int idrv, const ColIn& in, const ColOut& out, const Scratch& s, const RunCfg& r,
                   cudaStream_t st) {
-    return launch_sweep_stu1(b0, nb, cld, idrv, in, out, s, r, st) || launch_sweep_stu2(b0, nb, cld, idrv, in, out, s, r, st) ||
-           launch_sweep_stu3(b0, nb, cld, idrv, in, out, s, r, st) || launch_sweep_stu4(b0, nb, cld, idrv, in, out, s, r, st) ||
-           launch_sweep_stu5(b0, nb, cld, idrv, in, out, s, r, st);
+    const SweepTab& tb = G.sweep_tab;
+    return launch_sweep_stu1(b0, nb, cld, idrv, in, out, s, r, tb, st) || launch_sweep_stu2(b0, nb, cld, idrv, in, out, s, r, tb, st) ||
+           launch_sweep_stu3(b0, nb, cld, idrv, in, out, s, r, tb, st) || launch_sweep_stu4(b0, nb, cld, idrv, in, out, s, r, tb, st) ||
+           launch_sweep_stu5(b0, nb, cld, idrv, in, out, s, r, tb, st);
 }
 // default band groups of the sweep kernels: {first band, bands}
 const int kSweepGroups[][2] = {{1, 2}, {3, 1}, {4, 1}, {5, 1}, {6, 2}, {8, 2}, {10, 3}, {13, 4}};
 
 enum Mode { MODE_STRICT = 0, MODE_FUSED = 1 };
+
+int ensure_side_streams() {
+    if (G.side[0]) return 0;
+    for (auto& q : G.side) CK(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
+    for (cudaEvent_t* e : {&G.e_fork, &G.e_colprep, &G.e_t, &G.e_cld}) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    for (auto& e : G.e_side) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return 0;
+}
 
 // Device-resident pipeline over column chunks.  `in`/`out` hold device pointers with their ld.
 int run_device(Mode mode, int ncol, int nlay, int icld, int idrv, int inflag, int iceflag, int liqflag, int permuteseed,
@@ -254,46 +272,92 @@ int run_device(Mode mode, int ncol, int nlay, int icld, int idrv, int inflag, in
         S.dbg_col = (G.dbg && G.dbg_col >= c0 && G.dbg_col < c0 + r.ncol) ? (int)(G.dbg_col - c0) : -1;
         if (S.dbg_col >= 0) G.dbg_nlay = nlay;
         if (G.timing) CK(cudaEventRecord(G.ev[0], st));
-        if (two_phase) launch_colprep(in, S, r, st); else launch_prep(in, S, r, st);
-        G.launches++;
-        if (cld == CLD_MASK) {
-            if (irng == 0) {
-                launch_mcica_kiss(in, S, r, st); G.launches++;
-            } else {
-                // one global stream over (sub-column, column, layer): position of this chunk inside the whole call
-                const long mt_tot = G.mt_total ? G.mt_total : (G.mt_opt_total ? G.mt_opt_total : (long)ncol);
-                const long mt_b0 = G.mt_total ? G.mt_base : G.mt_opt_base;
-                if (mt_b0 + ncol > mt_tot) return RRTMG_LW_ERR_ARG;
-                const int nl = launch_mcica_mt(in, S, r, mt_tot, mt_b0 + c0, st);
-                if (nl < 0) return RRTMG_LW_ERR_CUDA;
-                G.launches += nl;
-            }
-        }
-        if (cld == CLD_ARRAYS) { launch_cldflags(in, S, r, st); G.launches += 2; }
-        if (two_phase && cld == CLD_MASK) { launch_cldoptics(in, S, r, st); G.launches++; }
-        if (G.timing) CK(cudaEventRecord(G.ev[1], st));
         int nstage = 0;  // timed stages between ev[1] and ev[2]
+        // McICA mask of the chunk (KISS per-column streams, or the single Mersenne-Twister stream of the call)
+        auto gen_masks = [&](cudaStream_t q) -> int {
+            if (irng == 0) {
+                launch_mcica_kiss(in, S, r, q); G.launches++;
+                return RRTMG_LW_OK;
+            }
+            // one global stream over (sub-column, column, layer): position of this chunk inside the whole call
+            const long mt_tot = G.mt_total ? G.mt_total : (G.mt_opt_total ? G.mt_opt_total : (long)ncol);
+            const long mt_b0 = G.mt_total ? G.mt_base : G.mt_opt_base;
+            if (mt_b0 + ncol > mt_tot) return RRTMG_LW_ERR_ARG;
+            const int nl = launch_mcica_mt(in, S, r, mt_tot, mt_b0 + c0, q);
+            if (nl < 0) return RRTMG_LW_ERR_CUDA;
+            G.launches += nl;
+            return RRTMG_LW_OK;
+        };
         if (two_phase) {
+            // Kernel graph of a pass (arrows = stream order or events):
+            //   colprep -> taumol ----------------------+-> sweep kernels (one flux slot each, any order) -> finalize
+            //   McICA masks -> (colprep) cloud optics --+
+            // With concurrency on (and no per-stage timing) the mask generator and the cloud optics run on a side stream
+            // beside taumol, and the sweep kernels are dealt over the caller's stream and the side streams.
+            const bool conc = G.concurrency != 0 && !G.timing && S.dbg_col < 0;
+            if (conc && (rc = ensure_side_streams()) != 0) return rc;
+            cudaStream_t qm = conc ? G.side[0] : st;  // masks + cloud optics
+            if (conc) {
+                CK(cudaEventRecord(G.e_fork, st));
+                for (auto& q : G.side) CK(cudaStreamWaitEvent(q, G.e_fork, 0));
+            }
+            launch_colprep(in, S, r, st); G.launches++;
+            if (conc) CK(cudaEventRecord(G.e_colprep, st));
+            if (cld == CLD_MASK) {
+                if ((rc = gen_masks(qm)) != RRTMG_LW_OK) return rc;
+                if (conc) CK(cudaStreamWaitEvent(qm, G.e_colprep, 0));
+                launch_cldoptics(in, S, r, qm); G.launches++;
+                if (conc) CK(cudaEventRecord(G.e_cld, qm));
+            }
+            if (cld == CLD_ARRAYS) { launch_cldflags(in, S, r, st); G.launches += 2; }
+            if (G.timing) CK(cudaEventRecord(G.ev[1], st));
             if (G.timing) CK(cudaEventRecord(G.evb[nstage++], st));
             launch_taumol(in, S, r, st); G.launches++;
-            bool first = true;
+            if (conc) {
+                CK(cudaEventRecord(G.e_t, st));
+                for (auto& q : G.side) CK(cudaStreamWaitEvent(q, G.e_t, 0));
+                if (cld == CLD_MASK) {
+                    CK(cudaStreamWaitEvent(st, G.e_cld, 0));
+                    for (int k = 1; k < Ctx::NSIDE; ++k) CK(cudaStreamWaitEvent(G.side[k], G.e_cld, 0));
+                }
+            }
+            unsigned slots = 0;
+            int nsweep = 0;
             auto sweep = [&](int b0, int nb) -> bool {
-                if (G.timing) CK(cudaEventRecord(G.evb[nstage++], st)) ;
-                RunCfg rr = r;
-                rr.first_band = first ? 1 : 0;
-                first = false;
+                cudaStream_t q = st;
+                if (conc) { const int k = nsweep % (Ctx::NSIDE + 1); q = k == 0 ? st : G.side[k - 1]; }
+                ++nsweep;
+                if (G.timing) CK(cudaEventRecord(G.evb[nstage++], st));
+                slots |= 1u << (b0 - 1);
                 G.launches++;
-                return launch_sweep(b0, nb, cld, idrv, in, out, S, rr, st);
+                return launch_sweep(b0, nb, cld, idrv, in, out, S, r, q);
             };
             if (G.sweep_groups && b_lo == 1 && b_hi == NBND) {
                 for (const auto& g : kSweepGroups)
                     if (!sweep(g[0], g[1])) return RRTMG_LW_ERR_ARG;
             } else {
-                for (int b = b_lo; b <= b_hi; ++b)
+                // longest kernels first when they are dealt over several streams (bands by g-point count)
+                const int order[NBND] = {3, 5, 4, 2, 7, 9, 1, 6, 8, 11, 12, 10, 13, 14, 15, 16};
+                for (int k = 0; k < NBND; ++k) {
+                    const int b = conc ? order[k] : k + 1;
+                    if (b < b_lo || b > b_hi) continue;
                     if (!sweep(b, 1)) return RRTMG_LW_ERR_ARG;
+                }
             }
             if (G.timing) CK(cudaEventRecord(G.evb[nstage], st));
+            if (conc)
+                for (int k = 0; k < Ctx::NSIDE; ++k) {
+                    CK(cudaEventRecord(G.e_side[k], G.side[k]));
+                    CK(cudaStreamWaitEvent(st, G.e_side[k], 0));
+                }
+            if (G.timing) CK(cudaEventRecord(G.ev[2], st));
+            launch_finalize_slots(in, out, S, r, cld != CLD_NONE, slots, st);
+            G.launches++;
         } else {
+            launch_prep(in, S, r, st); G.launches++;
+            if (cld == CLD_MASK && (rc = gen_masks(st)) != RRTMG_LW_OK) return rc;
+            if (cld == CLD_ARRAYS) { launch_cldflags(in, S, r, st); G.launches += 2; }
+            if (G.timing) CK(cudaEventRecord(G.ev[1], st));
             ColInF inf{};
             if (fp32) { G.launches += launch_cvt_inputs(in, S, r, cld != CLD_NONE, inflag, &inf, st); }
             for (int b = 1; b <= NBND; ++b) {
@@ -303,10 +367,10 @@ int run_device(Mode mode, int ncol, int nlay, int icld, int idrv, int inflag, in
                 G.launches++;
             }
             if (G.timing) CK(cudaEventRecord(G.evb[nstage], st));
+            if (G.timing) CK(cudaEventRecord(G.ev[2], st));
+            launch_finalize(in, out, S, r, cld != CLD_NONE, st);
+            G.launches++;
         }
-        if (G.timing) CK(cudaEventRecord(G.ev[2], st));
-        launch_finalize(in, out, S, r, cld != CLD_NONE, st);
-        G.launches++;
         if (G.timing) {
             CK(cudaEventRecord(G.ev[3], st));
             CK(cudaEventSynchronize(G.ev[3]));
@@ -556,6 +620,16 @@ extern "C" int rrtmg_lw_b200_ini(double cpdair, const double* kdata, long nkdata
         U.ka = Q(0); U.kb = Q(1); U.selfref = Q(2); U.forref = Q(3); U.fracrefa = Q(4); U.fracrefb = Q(5);
         for (int m = 0; m < 5; ++m) U.m[m] = Q(6 + m);
         U.v[0] = Q(11); U.v[1] = Q(12);
+    }
+    {
+        SweepTab& tb = G.sweep_tab;
+        tb.exptfn = reinterpret_cast<const double2*>(G.d_exptfn);
+        tb.tau_tbl = G.d_tau; tb.totplnk = G.d_totplnk; tb.totplnkderiv = G.d_totplnkderiv;
+        for (int b = 0; b < NBND; ++b) {
+            tb.fracrefa[b] = H.ct.bandp[b].fracrefa; tb.fracrefb[b] = H.ct.bandp[b].fracrefb;
+            tb.delwave[b] = H.ct.delwave[b];
+        }
+        tb.bpade = H.ct.bpade; tb.fluxfac = H.ct.fluxfac;
     }
     DevPtrs dp;
     dp.g = G.d_gtab; dp.totplnk = G.d_totplnk; dp.totplnkderiv = G.d_totplnkderiv;
@@ -943,6 +1017,11 @@ extern "C" int rrtmg_lw_b200_set_option(const char* name, int value) {
     if (std::strcmp(name, "band_kernel") == 0) {
         if (value != 2 && value != 4) return RRTMG_LW_ERR_ARG;
         G.band_kernel = value;
+        return RRTMG_LW_OK;
+    }
+    if (std::strcmp(name, "concurrency") == 0) {
+        if (value != 0 && value != 1) return RRTMG_LW_ERR_ARG;
+        G.concurrency = value;
         return RRTMG_LW_OK;
     }
     if (std::strcmp(name, "sweep_groups") == 0) {

@@ -71,6 +71,7 @@ struct Scratch {
     double* pfs;        // [pitch / 128][nlay][9][128] : eta (specmult) of the Planck-fraction interpolation, binary bands
     double* secdiff;    // 16 x pitch : diffusivity angle per band (rtrnmc.f90:258-281)
     double* cldb;       // [pitch / 128][nlay][16][2][128] : {odcld, 1 - exp(-odcld)} of a band's cloudy sub-columns (CLD_MASK)
+    double* fluxP;      // [pitch / 128][nlay + 1][16][6][128] : level-flux band sums, one slot per sweep launch (first band)
     double* gcld;       // 2 x 140 x nlay x pitch : efclfrac, odcld per g-point (strict rrtmg_lw() entry only)
     // debug capture of one column
     int dbg_col;        // chunk-relative column or -1
@@ -81,6 +82,20 @@ struct Scratch {
     double* dbg_scal;   // 2
 };
 
+// Tables and constants of the sweep kernels (lw_rtrnmc.cuh), passed BY VALUE as a kernel parameter: parameters sit in
+// constant bank 0 and are read as immediate operands with compile-time offsets, whereas the big __constant__ table
+// block needs an LDC per use whose misses showed up as the top stall of the vertical loops.
+struct SweepTab {
+    const double2* exptfn;        // [itr] = {exp_tbl, tfn_tbl}
+    const double* tau_tbl;
+    const double* totplnk;        // (181,16)
+    const double* totplnkderiv;   // (181,16)
+    const double* fracrefa[NBND]; // padded rows (lw_tables.h NGPAD)
+    const double* fracrefb[NBND];
+    double delwave[NBND];
+    double bpade, fluxfac;
+};
+
 struct RunCfg {
     int ncol;        // columns in this chunk
     long c0;         // first caller column of the chunk
@@ -89,8 +104,6 @@ struct RunCfg {
     int inflag, iceflag, liqflag;
     int icld, irng, permuteseed;
     int fp32;        // 1 = the prep kernel writes float fields (Scratch::fldf) for the FP32-mode band kernels
-    int first_band;  // two-phase sweep kernels: 1 = this launch opens the band sum (writes the running level fluxes instead
-                     // of adding to them); band-range runs start at any band
     int fld_block;   // layout of Scratch::fld: 0 = [field][layer][column], 1 = blocks of 128 columns,
                      // [column / 128][layer][field][column % 128] (column-lane kernel: a CTA's fields of one layer are
                      // one contiguous run, addressed as one base + compile-time offsets); pitch is a multiple of 128

@@ -861,6 +861,55 @@ __global__ void __launch_bounds__(128) finalize_kernel(ColIn in, ColOut out, Scr
     }
 }
 
+// flux close-out of the two-phase path: the sweep launches left their band sums in separate slots of s.fluxP
+// ([column / 128][level][slot][6][128], slot = first band of a launch); `slots` = bit mask of the slots written.
+// Slots are added in band order starting from 0.0: the reference's summation order (rtrnmc.f90:538-563).
+__global__ void __launch_bounds__(128) finalize_slots_kernel(ColIn in, ColOut out, Scratch s, RunCfg r, int cloudy, unsigned slots) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= r.ncol) return;
+    const long ci = r.c0 + i;
+    const int nlay = r.nlay;
+    const bool sep = cloudy && s.ctop[i] > 0;
+    const double* fb = s.fluxP + ((long)(i >> 7) * (nlay + 1) * NBND * 6) * 128 + (i & 127);
+    double fnet_lo = 0., fnetc_lo = 0., pz_lo = 0.;
+    for (int lev = 0; lev <= nlay; ++lev) {
+        const long o = ci + out.ld * lev;
+        const double* f = fb + (long)lev * NBND * 6 * 128;
+        double su = 0., sd = 0., suc = 0., sdc = 0., sdu = 0., sduc = 0.;
+#pragma unroll
+        for (int b = 0; b < NBND; ++b) {
+            if ((slots >> b) & 1u) {
+                const double* q = f + b * 6 * 128;
+                sd = sd + q[0];
+                su = su + q[256];
+                if (sep) { sdc = sdc + q[128]; suc = suc + q[384]; }
+                if (r.idrv == 1) {
+                    sdu = sdu + q[512];
+                    if (sep) sduc = sduc + q[640];
+                }
+            }
+        }
+        const double u = su * C.fluxfac;
+        const double d = sd * C.fluxfac;
+        double uc, dc;
+        if (sep) { uc = suc * C.fluxfac; dc = sdc * C.fluxfac; }
+        else { uc = u; dc = d; }
+        out.uflx[o] = u; out.dflx[o] = d; out.uflxc[o] = uc; out.dflxc[o] = dc;
+        if (r.idrv == 1) {
+            out.duflx_dt[o] = sdu;
+            out.duflxc_dt[o] = sep ? sduc : sdu;
+        }
+        const double fnet = u - d, fnetc = uc - dc;
+        const double pz = in.plev[ci + in.ld * lev];
+        if (lev > 0) {
+            const long oh = ci + out.ld * (lev - 1);
+            out.hr[oh] = C.heatfac * (fnet_lo - fnet) / (pz_lo - pz);
+            out.hrc[oh] = C.heatfac * (fnetc_lo - fnetc) / (pz_lo - pz);
+        }
+        fnet_lo = fnet; fnetc_lo = fnetc; pz_lo = pz;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // get_alpha, src/mcica_subcol_gen_lw.f90:129-178
 __global__ void get_alpha_kernel(int ncol, long ld, int nlay, int icld, int idcor, double decorr_con, const double* dz,
@@ -987,6 +1036,10 @@ void launch_cldflags(const ColIn& in, const Scratch& s, const RunCfg& r, cudaStr
 }
 void launch_finalize(const ColIn& in, const ColOut& out, const Scratch& s, const RunCfg& r, int cloudy, cudaStream_t st) {
     finalize_kernel<<<nblk(r.ncol, 128), 128, 0, st>>>(in, out, s, r, cloudy);
+}
+void launch_finalize_slots(const ColIn& in, const ColOut& out, const Scratch& s, const RunCfg& r, int cloudy, unsigned slots,
+                           cudaStream_t st) {
+    finalize_slots_kernel<<<nblk(r.ncol, 128), 128, 0, st>>>(in, out, s, r, cloudy, slots);
 }
 void launch_get_alpha(int ncol, long ld, int nlay, int icld, int idcor, double decorr_con, const double* dz,
                       const double* lat, int juldat, const double* cldfrac, double* alpha, double am1, double am2,

@@ -23,6 +23,7 @@ void free_mt_buffers();
 int launch_cvt_inputs(const ColIn&, const Scratch&, const RunCfg&, int cloudy, int inflag, ColInF* out, cudaStream_t);
 void launch_cldflags(const ColIn&, const Scratch&, const RunCfg&, cudaStream_t);
 void launch_finalize(const ColIn&, const ColOut&, const Scratch&, const RunCfg&, int cloudy, cudaStream_t);
+void launch_finalize_slots(const ColIn&, const ColOut&, const Scratch&, const RunCfg&, int cloudy, unsigned slots, cudaStream_t);
 void launch_get_alpha(int ncol, long ld, int nlay, int icld, int idcor, double decorr_con, const double* dz,
                       const double* lat, int juldat, const double* cldfrac, double* alpha, double am1, double am2,
                       double am4, cudaStream_t);
@@ -52,7 +53,7 @@ void launch_cldoptics(const ColIn&, const Scratch&, const RunCfg&, cudaStream_t)
 void launch_taumol(const ColIn&, const Scratch&, const RunCfg&, cudaStream_t);
 #define LW_DECL_STU(n)                                                                                             \
     bool launch_sweep_stu##n(int b0, int nb, int cld, int idrv, const ColIn&, const ColOut&, const Scratch&, const RunCfg&, \
-                             cudaStream_t);                                                                        \
+                             const SweepTab&, cudaStream_t);                                                                        \
     cudaError_t upload_constants_stu##n(const ConstTab&, const DevPtrs&, const double (*refrat)[5], const ConstTabF*);
 LW_DECL_STU(1) LW_DECL_STU(2) LW_DECL_STU(3) LW_DECL_STU(4) LW_DECL_STU(5)
 #undef LW_DECL_STU

@@ -54,14 +54,17 @@ struct SweepRing {
     static constexpr int S_TLAY = G::NGG, S_TLEV = G::NGG + 1, S_PF = G::NGG + 2;
     static constexpr int S_INT = S_PF + G::NPFG;
     static constexpr int SLOTS = S_INT + 4 / IPS;
-    static constexpr int NST = 2;
+#ifndef LW_SWEEP_NST
+#define LW_SWEEP_NST 2
+#endif
+    static constexpr int NST = LW_SWEEP_NST;  // ring stages = layers of prefetch distance
     static constexpr size_t BYTES = (size_t)NST * SLOTS * SWEEP_THREADS * sizeof(double);
 };
 
 // Planck function of band B at the temperature whose table position is (it, frac), setcoef.f90:173-226
 template <int B>
-__device__ __forceinline__ double planck_at(int it, double frac) {
-    const double* tp = D.totplnk + 181 * (B - 1);
+__device__ __forceinline__ double planck_at(const double* totplnk, int it, double frac) {
+    const double* tp = totplnk + 181 * (B - 1);
     const double a = ldg(tp + it - 1), b = ldg(tp + it);
     const double dbdt = b - a;
     return fmadd(frac, dbdt, a);
@@ -88,8 +91,8 @@ struct PlFrac {
     int dnext;     // element offset of the second row (0 = no interpolation)
     double fpl;
     bool zero;
-    __device__ __forceinline__ void setup(bool lower, double sm) {
-        const BandTab& T = C.bandp[B - 1];
+    __device__ __forceinline__ void setup(const SweepTab& tb, bool lower, double sm) {
+        struct { const double *fracrefa, *fracrefb; } T{tb.fracrefa[B - 1], tb.fracrefb[B - 1]};
         const int jpl = 1 + (int)sm;
         const double f = sm - (double)(int)sm;
         zero = false;
@@ -199,16 +202,12 @@ __device__ __forceinline__ double ldg1_if(const double* p, bool on) {
 // rtrnmc.f90:429-431), the table index itr where it takes the lookup (:433-440).  bb = plfrac * (blay + tausfac * dpl)
 // is bbd on the way down (dpl = dplankdn) and bbugas on the way up (dpl = dplankup).  Selects, no branches: the
 // g-points of a thread form independent instruction streams; the table gather is issued only by the lanes that use it.
-__device__ __forceinline__ void gas_point(double st, double plfrac, double blay, double dpl, double& atrans, double& bb,
-                                          bool& big, int& itr) {
+__device__ __forceinline__ void gas_point(const double2* exptfn, double st, double plfrac, double blay, double dpl,
+                                          double& atrans, double& bb, bool& big, int& itr) {
     const double rec_6 = 0.166667;
     big = od_state_is_index(st);
     itr = od_state_index(st);
-#ifdef LW_EXP_FAKE_GATHER   // bounding experiment: every gather hits the same few L1 lines (wrong results)
-    const double2 e = ldg2_if(D.exptfn + 2000 + (itr & 31), big);
-#else
-    const double2 e = ldg2_if(D.exptfn + itr, big);
-#endif
+    const double2 e = ldg2_if(exptfn + itr, big);
 #ifdef LW_TAIL_FMA
     atrans = big ? 1. - e.x : fmadd(-0.5 * st, st, st);
 #else
@@ -222,15 +221,17 @@ __device__ __forceinline__ void gas_point(double st, double plfrac, double blay,
 // odtot = odepth + odcld, where the gas part is the table value tau_tbl(itgas) once it has gone through the lookup
 // (:387); atot / bb_tot from the series (odtot < 0.06) or from the lookup at ittot.  Lanes with on = false get
 // finite don't-care values and touch no memory.
-__device__ __forceinline__ void cloud_point(double st, bool big, int itr, double odc, bool on, double plfrac, double blay,
-                                            double dpl, double bpade, double& atot, double& bb_tot, int& ittot_out) {
+__device__ __forceinline__ void cloud_point(const SweepTab& tb, double st, bool big, int itr, double odc, bool on,
+                                            double plfrac, double blay, double dpl, double& atot, double& bb_tot,
+                                            int& ittot_out) {
+    const double bpade = tb.bpade;
     const double rec_6 = 0.166667;
-    const double odg = big ? ldg1_if(D.tau_tbl + itr, on && big) : st;
+    const double odg = big ? ldg1_if(tb.tau_tbl + itr, on && big) : st;
     const double odtot = odg + odc;
     const bool tsmall = odtot < 0.06;
     const double tblind = div_fast(odtot, bpade + odtot);
     const int ittot = tbl_index(tblind);
-    const double2 et = ldg2_if(D.exptfn + ittot, on && !tsmall);
+    const double2 et = ldg2_if(tb.exptfn + ittot, on && !tsmall);
     atot = tsmall ? odtot - 0.5 * odtot * odtot : 1. - et.x;
     const double tfactot = tsmall ? rec_6 * odtot : et.y;
     bb_tot = plfrac * fmadd(tfactot, dpl, blay);
@@ -240,7 +241,7 @@ __device__ __forceinline__ void cloud_point(double st, bool big, int itr, double
 // ------------------------------------------------------------------------------------------
 // the sweep kernel of bands B0 .. B0 + NB - 1
 template <int B0, int NB, int CLD, int IDRV, int MINB>
-__global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, ColOut out, Scratch s, RunCfg r) {
+__global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, ColOut out, Scratch s, RunCfg r, const SweepTab tb) {
     using GR = Grp<B0, NB>;
     using RG = SweepRing<B0, NB>;
     constexpr int NGG = GR::NGG;
@@ -255,9 +256,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
     const int nlay = r.nlay;
     const long P = s.pitch;
     const long plane = (long)nlay * P;
-    const double bpade = C.bpade;
     const bool dbg = live && (s.dbg_col == i);
-    const bool first = r.first_band != 0;  // this launch opens the band sum (band istart of the run)
     const int laytrop = s.laytrop[i];
     const int ctop = (CLD != CLD_NONE) ? s.ctop[i] : 0;
     (void)out;
@@ -270,9 +269,11 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
     // {odcld, 1 - exp(-odcld)} of a (layer, band) whose sub-columns hold cloud (CLD_MASK): [block][layer][band][2][128]
     auto cldb = [&](int l0, int b) { return s.cldb + (((blk_lay0 + l0) * NBND + (b - 1)) * 2) * 128 + blk_t; };
     const long blk_lev0 = (long)(i >> 7) * (nlay + 1);
-    // running band sums of the level fluxes: [column / 128][level][6][column % 128]; 0 dflx, 1 dflxc, 2 uflx, 3 uflxc,
-    // 4 duflx_dt, 5 duflxc_dt (the finalize kernel turns them into the caller's arrays)
-    auto flx = [&](int lev) { return s.fluxB + ((blk_lev0 + lev) * 6) * 128 + blk_t; };
+    // band sums of the level fluxes of THIS launch's bands: [column / 128][level][slot][6][column % 128], slot = first band
+    // of the launch; 0 dflx, 1 dflxc, 2 uflx, 3 uflxc, 4 duflx_dt, 5 duflxc_dt.  Every launch owns its slot (no
+    // read-modify-write, no ordering between the sweep kernels, which therefore run concurrently on several streams);
+    // the finalize kernel adds the slots in band order, which is the reference's summation order (rtrnmc.f90:538-563).
+    auto flx = [&](int lev) { return s.fluxP + (((blk_lev0 + lev) * NBND + (B0 - 1)) * 6) * 128 + blk_t; };
     // strict rrtmg_lw(): per-g {efclfrac, odcld} of cloudy layers
     double* S_EF = s.gcld;
     double* S_OC = s.gcld + (long)NGPT * plane;
@@ -322,14 +323,6 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
         if constexpr (sh + NGG > 32) lo |= ((unsigned)st_i(stage, 2)) << (32 - sh);
         return NGG == 32 ? lo : (lo & ((1u << (NGG & 31)) - 1u));
     };
-    auto prefetch_entries = [&](int stg) {
-#pragma unroll
-        for (int p = 0; p < NGG / 2; ++p) {
-            const double2 w = st_od(stg, p);
-            if (od_state_is_index(w.x)) asm volatile("prefetch.global.L1 [%0];" ::"l"(D.exptfn + od_state_index(w.x)));
-            if (od_state_is_index(w.y)) asm volatile("prefetch.global.L1 [%0];" ::"l"(D.exptfn + od_state_index(w.y)));
-        }
-    };
     auto for_bands = [&](auto&& f) {
         f(IC<0>{});
         if constexpr (NB > 1) f(IC<1>{});
@@ -347,20 +340,15 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
     for (int g = 0; g < NGG; ++g) { radld[g] = 0.; radclrd[g] = 0.; }
 
     // ---------------------------------------------------------------- downward sweep, rtrnmc.f90:350-455
-    issue(0, nlay, true);
-    issue(1, nlay - 1, true);
+#pragma unroll
+    for (int k = 0; k < RG::NST; ++k) issue(k, nlay - k, true);
     int stage = 0;
     for (int lev = nlay; lev >= 1; --lev) {
         const int l0 = lev - 1;
         const long idx = (long)l0 * P + i;
         const long a = ci + in.ld * l0;
         cp_wait<RG::NST - 1>();
-        // running band sums of this level, fetched now so their latency hides behind the g loops
         acc_t acc_d = 0., acc_dc = 0.;
-        if (!first && live) {
-            acc_d = __ldcg(flx(l0));
-            if (CLD != CLD_NONE && ctop > 0) acc_dc = __ldcg(flx(l0) + 128);
-        }
         int it_lay, it_lev;
         double fr_lay, fr_lev;
         planck_pos(st_d(stage, RG::S_TLAY), it_lay, fr_lay);
@@ -376,12 +364,12 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
             constexpr int B = B0 + K;
             constexpr int NG = NGC[B - 1];
             constexpr int GO = GR::goff(K);
-            const double blay = planck_at<B>(it_lay, fr_lay);
-            const double dplankdn = planck_at<B>(it_lev, fr_lev) - blay;  // planklev(lev-1) - planklay(lev)
+            const double blay = planck_at<B>(tb.totplnk, it_lay, fr_lay);
+            const double dplankdn = planck_at<B>(tb.totplnk, it_lev, fr_lev) - blay;  // planklev(lev-1) - planklay(lev)
             double sm = 0.;
             if constexpr (pf_slot(B) >= 0) sm = st_d(stage, RG::S_PF + pf_slot(B) - GR::PF0);
             PlFrac<B> pf;
-            pf.setup(lower, sm);
+            pf.setup(tb, lower, sm);
             // cloud state of this (column, layer) for this band: sub-column bits of the McICA mask; the band's cloud
             // optical depth along the diffusivity angle and its absorptivity come from the cloud-optics kernel
             unsigned bits = 0;
@@ -406,7 +394,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
                     double atrans, bbd;
                     bool big;
                     int itr;
-                    gas_point(st, pf.get(g), blay, dplankdn, atrans, bbd, big, itr);
+                    gas_point(tb.exptfn, st, pf.get(g), blay, dplankdn, atrans, bbd, big, itr);
                     bool on;
                     double odc, ef;
                     if constexpr (CLD == CLD_MASK) {
@@ -431,7 +419,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
                     }
                     double atot, bbdtot;
                     int ittot;
-                    cloud_point(st, big, itr, odc, on, pf.get(g), blay, dplankdn, bpade, atot, bbdtot, ittot);
+                    cloud_point(tb, st, big, itr, odc, on, pf.get(g), blay, dplankdn, atot, bbdtot, ittot);
                     const double gassrc = bbd * atrans;
                     const acc_t xc = relaxed_cld(radld[GO + g], atrans + ef * (1. - atrans), gassrc, bbdtot * atot - gassrc);
                     const acc_t xr = relaxed(radld[GO + g], bbd, atrans);
@@ -450,7 +438,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
                     double atrans, bbd;
                     bool big;
                     int itr;
-                    gas_point(st, pf.get(g), blay, dplankdn, atrans, bbd, big, itr);
+                    gas_point(tb.exptfn, st, pf.get(g), blay, dplankdn, atrans, bbd, big, itr);
                     radld[GO + g] = relaxed(radld[GO + g], bbd, atrans);
                     dsum = dsum + radld[GO + g];
                     if (CLD != CLD_NONE) {
@@ -479,28 +467,22 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
                         if constexpr (CLD == CLD_MASK) odc = ((bits >> g) & 1u) ? odcld_b : 0.;
                         if constexpr (CLD == CLD_ARRAYS) odc = S_OC[(long)(G0 + GO + g) * plane + idx];
                         double t0, t1;
-                        cloud_point(st, big, itr, odc, true, pf.get(g), blay, dplankdn, bpade, t0, t1, d1);
+                        cloud_point(tb, st, big, itr, odc, true, pf.get(g), blay, dplankdn, t0, t1, d1);
                     }
                     s.dbg_itr[2 * o + 1] = d1;
                 }
             }
             // band close-out for level lev-1: flux += (rad * wtdiff) * delwave, rtrnmc.f90:538-550
-            acc_d = acc_d + (dsum * (acc_t)0.5) * (acc_t)C.delwave[B - 1];
-            if (CLD != CLD_NONE) acc_dc = acc_dc + ((lev <= ctop ? dcsum : dsum) * (acc_t)0.5) * (acc_t)C.delwave[B - 1];
+            acc_d = acc_d + (dsum * (acc_t)0.5) * (acc_t)tb.delwave[B - 1];
+            if (CLD != CLD_NONE) acc_dc = acc_dc + ((lev <= ctop ? dcsum : dsum) * (acc_t)0.5) * (acc_t)tb.delwave[B - 1];
         });
         if (live) {
             acc_t* o = flx(l0);
             o[0] = acc_d;
             if (CLD != CLD_NONE && ctop > 0) o[128] = acc_dc;
         }
-#ifdef LW_SWEEP_PREFETCH
-        // the next layer's state words arrived in the other stage one layer ago: put the exp/tfn entries its table
-        // lookups will gather into L1 now, so that the gathers of the next layer find them there
-        cp_wait<0>();
-        if (lev > 1) prefetch_entries(stage ^ 1);
-#endif
         issue(stage, lev - RG::NST, true);
-        stage ^= 1;
+        stage = stage + 1 == RG::NST ? 0 : stage + 1;
     }
     cp_wait<0>();
 
@@ -509,24 +491,14 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
     acc_t (&radlu)[NGG] = radld;
     acc_t (&radclru)[NGG] = radclrd;
     acc_t d_radlu[IDRV ? NGG : 1], d_radclru[IDRV ? NGG : 1];
-    issue(0, 1, false);
-    issue(1, 2, false);
+#pragma unroll
+    for (int k = 0; k < RG::NST; ++k) issue(k, 1 + k, false);
     {
         acc_t acc_u = 0., acc_uc = 0., acc_du = 0., acc_duc = 0.;
-        if (first) {
-            // downward flux at the top of the atmosphere is never touched by the sweep: drad(nlayers) = 0
-            if (live) {
-                flx(nlay)[0] = 0.0;
-                if (CLD != CLD_NONE && ctop > 0) flx(nlay)[128] = 0.0;
-            }
-        } else if (live) {
-            const acc_t* o = flx(0);
-            acc_u = __ldcg(o + 256);
-            if (CLD != CLD_NONE && ctop > 0) acc_uc = __ldcg(o + 384);
-            if constexpr (IDRV == 1) {
-                acc_du = __ldcg(o + 512);
-                if (CLD != CLD_NONE && ctop > 0) acc_duc = __ldcg(o + 640);
-            }
+        // downward flux at the top of the atmosphere is never touched by the sweep: drad(nlayers) = 0
+        if (live) {
+            flx(nlay)[0] = 0.0;
+            if (CLD != CLD_NONE && ctop > 0) flx(nlay)[128] = 0.0;
         }
         const double tbound = in.tsfc[ci];
         int it_b;
@@ -540,12 +512,12 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
             constexpr int GO = GR::goff(K);
             // surface emission, setcoef.f90:211-219 / rtrnmc.f90:465-469
             const double semiss = in.emis[ci + in.ld * (B - 1)];
-            const double* tp = D.totplnk + 181 * (B - 1);
+            const double* tp = tb.totplnk + 181 * (B - 1);
             const double pa = ldg(tp + it_b - 1), pb = ldg(tp + it_b);
             const double plankbnd = semiss * (pa + fr_b * (pb - pa));
             double dplankbnd_dt = 0.;
             if constexpr (IDRV == 1) {
-                const double* td = D.totplnkderiv + 181 * (B - 1);
+                const double* td = tb.totplnkderiv + 181 * (B - 1);
                 const double da = ldg(td + it_b - 1), db = ldg(td + it_b);
                 dplankbnd_dt = semiss * (da + fr_b * (db - da));
             }
@@ -553,7 +525,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
             double sm = 0.;
             if constexpr (pf_slot(B) >= 0) sm = pf_src(0)[(pf_slot(B) - GR::PF0) * 128];
             PlFrac<B> pf;
-            pf.setup(lower1, sm);  // fracs(1, g)
+            pf.setup(tb, lower1, sm);  // fracs(1, g)
             acc_t usum = 0., ucsum = 0., dusum = 0.;
 #pragma unroll
             for (int g = 0; g < NG; ++g) {
@@ -574,10 +546,10 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
                     dusum = dusum + d_radlu[GO + g];
                 }
             }
-            acc_u = acc_u + (usum * (acc_t)0.5) * (acc_t)C.delwave[B - 1];
-            acc_uc = acc_uc + (ucsum * (acc_t)0.5) * (acc_t)C.delwave[B - 1];
+            acc_u = acc_u + (usum * (acc_t)0.5) * (acc_t)tb.delwave[B - 1];
+            acc_uc = acc_uc + (ucsum * (acc_t)0.5) * (acc_t)tb.delwave[B - 1];
             if constexpr (IDRV == 1) {
-                const acc_t addd = (dusum * (acc_t)0.5) * (acc_t)C.delwave[B - 1] * (acc_t)C.fluxfac;
+                const acc_t addd = (dusum * (acc_t)0.5) * (acc_t)tb.delwave[B - 1] * (acc_t)tb.fluxfac;
                 acc_du = acc_du + addd;
                 acc_duc = acc_duc + addd;
             }
@@ -601,15 +573,6 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
         const long a = ci + in.ld * l0;
         cp_wait<RG::NST - 1>();
         acc_t acc_u = 0., acc_uc = 0., acc_du = 0., acc_duc = 0.;
-        if (!first && live) {
-            const acc_t* o = flx(lev);
-            acc_u = __ldcg(o + 256);
-            if (CLD != CLD_NONE && ctop > 0) acc_uc = __ldcg(o + 384);
-            if constexpr (IDRV == 1) {
-                acc_du = __ldcg(o + 512);
-                if (CLD != CLD_NONE && ctop > 0) acc_duc = __ldcg(o + 640);
-            }
-        }
         int it_lay, it_lev;
         double fr_lay, fr_lev;
         planck_pos(st_d(stage, RG::S_TLAY), it_lay, fr_lay);
@@ -625,12 +588,12 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
             constexpr int B = B0 + K;
             constexpr int NG = NGC[B - 1];
             constexpr int GO = GR::goff(K);
-            const double blay = planck_at<B>(it_lay, fr_lay);
-            const double dplankup = planck_at<B>(it_lev, fr_lev) - blay;  // planklev(lev) - planklay(lev)
+            const double blay = planck_at<B>(tb.totplnk, it_lay, fr_lay);
+            const double dplankup = planck_at<B>(tb.totplnk, it_lev, fr_lev) - blay;  // planklev(lev) - planklay(lev)
             double sm = 0.;
             if constexpr (pf_slot(B) >= 0) sm = st_d(stage, RG::S_PF + pf_slot(B) - GR::PF0);
             PlFrac<B> pf;
-            pf.setup(lower, sm);
+            pf.setup(tb, lower, sm);
             unsigned bits = 0;
             double odcld_b = 0., abscld_b = 0.;
             if constexpr (CLD == CLD_MASK) {
@@ -651,7 +614,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
                     double atrans, bbugas;
                     bool big;
                     int itr;
-                    gas_point(st, pf.get(g), blay, dplankup, atrans, bbugas, big, itr);
+                    gas_point(tb.exptfn, st, pf.get(g), blay, dplankup, atrans, bbugas, big, itr);
                     bool on;
                     double odc, ef;
                     if constexpr (CLD == CLD_MASK) {
@@ -667,7 +630,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
                     }
                     double atot, bbutot;
                     int ittot;
-                    cloud_point(st, big, itr, odc, on, pf.get(g), blay, dplankup, bpade, atot, bbutot, ittot);
+                    cloud_point(tb, st, big, itr, odc, on, pf.get(g), blay, dplankup, atot, bbutot, ittot);
                     const double gassrc = bbugas * atrans;
                     const acc_t xc = relaxed_cld(radlu[GO + g], atrans + ef * (1. - atrans), gassrc, bbutot * atot - gassrc);
                     const acc_t xr = relaxed(radlu[GO + g], bbugas, atrans);
@@ -693,7 +656,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
                     double atrans, bbugas;
                     bool big;
                     int itr;
-                    gas_point(st, pf.get(g), blay, dplankup, atrans, bbugas, big, itr);
+                    gas_point(tb.exptfn, st, pf.get(g), blay, dplankup, atrans, bbugas, big, itr);
                     radlu[GO + g] = relaxed(radlu[GO + g], bbugas, atrans);
                     usum = usum + radlu[GO + g];
                     if constexpr (IDRV == 1) {
@@ -710,11 +673,11 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
                     }
                 }
             }
-            acc_u = acc_u + (usum * (acc_t)0.5) * (acc_t)C.delwave[B - 1];
-            if (CLD != CLD_NONE) acc_uc = acc_uc + (ucsum * (acc_t)0.5) * (acc_t)C.delwave[B - 1];
+            acc_u = acc_u + (usum * (acc_t)0.5) * (acc_t)tb.delwave[B - 1];
+            if (CLD != CLD_NONE) acc_uc = acc_uc + (ucsum * (acc_t)0.5) * (acc_t)tb.delwave[B - 1];
             if constexpr (IDRV == 1) {
-                acc_du = acc_du + (dusum * (acc_t)0.5) * (acc_t)C.delwave[B - 1] * (acc_t)C.fluxfac;
-                if (CLD != CLD_NONE) acc_duc = acc_duc + (ducsum * (acc_t)0.5) * (acc_t)C.delwave[B - 1] * (acc_t)C.fluxfac;
+                acc_du = acc_du + (dusum * (acc_t)0.5) * (acc_t)tb.delwave[B - 1] * (acc_t)tb.fluxfac;
+                if (CLD != CLD_NONE) acc_duc = acc_duc + (ducsum * (acc_t)0.5) * (acc_t)tb.delwave[B - 1] * (acc_t)tb.fluxfac;
             }
         });
         if (live) {
@@ -726,12 +689,8 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
                 if (CLD != CLD_NONE && ctop > 0) o[640] = acc_duc;
             }
         }
-#ifdef LW_SWEEP_PREFETCH
-        cp_wait<0>();
-        if (lev < nlay) prefetch_entries(stage ^ 1);
-#endif
         issue(stage, lev + RG::NST, false);
-        stage ^= 1;
+        stage = stage + 1 == RG::NST ? 0 : stage + 1;
     }
     cp_wait<0>();
 }

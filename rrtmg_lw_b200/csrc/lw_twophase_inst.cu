@@ -40,7 +40,7 @@ constexpr int sweep_minb(int ngg, int cld, int idrv) {
 
 template <int B0, int NB>
 static void launch_g(int cld, int idrv, const ColIn& in, const ColOut& out, const Scratch& s, const RunCfg& r,
-                     cudaStream_t st) {
+                     const SweepTab& tb, cudaStream_t st) {
     const int threads = SWEEP_THREADS;
     const int blocks = (r.ncol + threads - 1) / threads;
     const size_t smem = SweepRing<B0, NB>::BYTES;
@@ -53,7 +53,7 @@ static void launch_g(int cld, int idrv, const ColIn& in, const ColOut& out, cons
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                  \
             attr_set = true;                                                                                     \
         }                                                                                                        \
-        kern<<<blocks, threads, smem, st>>>(in, out, s, r);                                                      \
+        kern<<<blocks, threads, smem, st>>>(in, out, s, r, tb);                                                    \
     } while (0)
     if (cld == CLD_NONE) { if (idrv) LW_GO(CLD_NONE, 1); else LW_GO(CLD_NONE, 0); }
     else if (cld == CLD_MASK) { if (idrv) LW_GO(CLD_MASK, 1); else LW_GO(CLD_MASK, 0); }
@@ -74,8 +74,8 @@ static void launch_g(int cld, int idrv, const ColIn& in, const ColOut& out, cons
 #endif
 
 bool LW_CAT(launch_sweep_stu, LW_STU)(int b0, int nb, int cld, int idrv, const ColIn& in, const ColOut& out,
-                                      const Scratch& s, const RunCfg& r, cudaStream_t st) {
-#define LW_CASE(B0, NB) if (b0 == B0 && nb == NB) { launch_g<B0, NB>(cld, idrv, in, out, s, r, st); return true; }
+                                      const Scratch& s, const RunCfg& r, const SweepTab& tb, cudaStream_t st) {
+#define LW_CASE(B0, NB) if (b0 == B0 && nb == NB) { launch_g<B0, NB>(cld, idrv, in, out, s, r, tb, st); return true; }
     LW_STU_GROUPS(LW_CASE)
 #undef LW_CASE
     return false;

@@ -51,6 +51,14 @@ for _ in range(n):
     st_ = np.array(api.last_stage_timing()); acc = st_ if acc is None else acc + st_; t = api.last_timing(); tot += t[0]; alln += t[1]
 api.set_timing(False)
 api.sync()
+# whole-step time without the per-stage events (the library may then run independent kernels on side streams)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+step(); torch.cuda.synchronize()
+e0.record()
+for _ in range(n):
+    step()
+e1.record(); torch.cuda.synchronize()
+step_ms = e0.elapsed_time(e1) / n
 cur = {k: out[k][:, :8192].cpu().numpy() for k in ("uflx", "dflx", "uflxc", "dflxc", "hr", "hrc")}
 err = None
 if os.environ.get("EXP_REF") and os.path.exists(os.environ["EXP_REF"]):
@@ -60,4 +68,4 @@ if os.environ.get("EXP_SAVE"):
     np.savez(os.environ["EXP_SAVE"], **cur)
 print(json.dumps({"lib": os.path.basename(api.LIB_PATH), "opts": os.environ.get("EXP_OPTS", ""), "ncol": ncol, "chunk": int(os.environ.get("EXP_CHUNK", 262144)),
                   "stages_ms": [round(x / n, 3) for x in acc], "bands_total_ms": round(tot / n, 3),
-                  "all_ms": round(alln / n, 3), "maxdiff_vs_ref": err}), flush=True)
+                  "all_ms": round(alln / n, 3), "step_ms": round(step_ms, 3), "maxdiff_vs_ref": err}), flush=True)
