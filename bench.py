@@ -6,8 +6,12 @@
     python bench.py --impl reference --gpus N --steps K ...  # CPU reference arm (oracle port)
 
 One "step" = one pass of the hot path (mcica_subcol_lw -> rrtmg_lw, fused device entry) over the
-rank's column batch.  N > 1: one process per GPU (torchrun), the column batch is block-partitioned,
-no data-path collective; value = columns of all ranks / max-over-ranks device time ("weak").
+rank's column batch.  N > 1: one process per GPU (torchrun), the column batch is block-partitioned
+(weak scaling: 1 M columns per GPU); the step INCLUDES the path's one exchange, the NCCL gather of every
+rank's flux / heating-rate arrays into rank 0, overlapped chunk by chunk with the kernels;
+value = columns of all ranks / max-over-ranks device time.  The line also carries device-timed numbers
+of the other BASELINE.json configurations (C2 clear sky, C4 exponential-random + aerosol + dF/dTs,
+C5 the 1440 x 720 x 137-layer grid block-partitioned over the ranks = strong scaling).
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -156,15 +160,15 @@ def run_reference(args, rank):
     }))
 
 
-def make_device_batch(ncol, device, seed_off):
+def make_device_batch(ncol, device, seed_off, nlay=NLAY, aerosol=False):
     """Device-resident synthetic batch generated in pieces (bounded temporaries)."""
     import torch
 
     from rrtmg_lw_b200 import synth
-    piece = 65536
+    piece = 65536 if nlay <= 80 else 32768
     parts = []
     for i, c0 in enumerate(range(0, ncol, piece)):
-        parts.append(synth.make_batch(min(piece, ncol - c0), NLAY, cloudy=True, device=device,
+        parts.append(synth.make_batch(min(piece, ncol - c0), nlay, cloudy=True, aerosol=aerosol, device=device,
                                       col_offset=seed_off * 4096 + i))
     if len(parts) == 1:
         return parts[0]
@@ -186,27 +190,114 @@ def make_device_batch(ncol, device, seed_off):
     return synth.Batch(**kw)
 
 
+# output arrays of one call, as row ranges of ONE packed (rows, columns) buffer: what a rank computes is what it sends
+def out_rows(nlay, idrv=0):
+    rows = [("uflx", nlay + 1), ("dflx", nlay + 1), ("hr", nlay), ("uflxc", nlay + 1), ("dflxc", nlay + 1), ("hrc", nlay)]
+    if idrv:
+        rows += [("duflx_dt", nlay + 1), ("duflxc_dt", nlay + 1)]
+    return rows
+
+
+def packed_views(buf, rows):
+    out, r0 = {}, 0
+    for k, n in rows:
+        out[k] = buf[r0:r0 + n]
+        r0 += n
+    return out
+
+
+class Workload:
+    """One BASELINE.json configuration resident on this rank's GPU: inputs, a packed output buffer, and step()."""
+
+    def __init__(self, api, driver, dev, ncol, nlay, icld, idrv, aerosol, seed_off, clear=False):
+        import torch
+        self.api, self.ncol, self.nlay, self.icld, self.idrv, self.clear = api, ncol, nlay, icld, idrv, clear
+        b = make_device_batch(ncol, dev, seed_off, nlay=nlay, aerosol=aerosol)
+        self.b = b
+        self.rows = out_rows(nlay, idrv)
+        self.R = sum(n for _, n in self.rows)
+        self.pack = torch.zeros((self.R, ncol), dtype=torch.float64, device=dev)
+        self.out = packed_views(self.pack, self.rows)
+        conv = driver._conv(b, dev)
+        self.at = driver.atm_args(b, conv)
+        self.cl = [b.cldfrac, b.ciwp, b.clwp, b.rei, b.rel, b.tauc]
+        self.alpha = None
+        if icld >= 4:
+            self.alpha = torch.zeros_like(b.play)
+            api.get_alpha(1, ncol, nlay, icld, 1, 2500.0, b.dz, b.lat, 200, b.cldfrac, self.alpha)
+        torch.cuda.empty_cache()   # the generator's temporaries go back to the device: the library allocates its own scratch
+
+    def step(self, lo=0, hi=None, out=None, out_ld=None):
+        """The hot path on local columns [lo, hi); outputs into `out` (default: the rank's packed buffer)."""
+        api, o = self.api, (out or self.out)
+        hi = self.ncol if hi is None else hi
+        sub = lo != 0 or hi != self.ncol
+        co = (lambda x, inner=1: api.col_offset(x, lo, inner)) if sub else (lambda x, inner=1: x)
+        du, duc = (o["duflx_dt"], o["duflxc_dt"]) if self.idrv else (None, None)
+        if out_ld is not None:
+            api.set_option("out_ld", out_ld)
+        try:
+            if self.clear:
+                n = None
+                api.rrtmg_lw(hi - lo, self.nlay, 0, self.idrv, *[co(x) for x in self.at], 0, 0, 0, n, n, n, n, n, n,
+                             co(self.b.tauaer), o["uflx"], o["dflx"], o["hr"], o["uflxc"], o["dflxc"], o["hrc"], du, duc,
+                             ld=self.ncol)
+            else:
+                cl = [co(x) for x in self.cl[:5]] + [co(self.cl[5], 16)]
+                al = co(self.alpha) if self.alpha is not None else None
+                api.rrtmg_lw_mcica(hi - lo, self.nlay, self.icld, self.idrv, 1, 0, *[co(x) for x in self.at], 2, 3, 1, *cl,
+                                   al, co(self.b.tauaer), o["uflx"], o["dflx"], o["hr"], o["uflxc"], o["dflxc"], o["hrc"],
+                                   du, duc, ld=self.ncol)
+        finally:
+            if out_ld is not None:
+                api.set_option("out_ld", 0)
+
+
+def timed(torch, dist, world, dev, fn, steps, warmup):
+    """W untimed + K timed calls of fn, device events, barrier + synchronize on both sides, max over ranks (ms total)."""
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(warmup):
+        fn()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--ncol", type=int, default=1048576, help="columns per GPU")
-    ap.add_argument("--chunk", type=int, default=1048576,
-                    help="columns per internal pass (scratch is ~70 KB per column of the pass; the default runs the "
-                         "1 M-column batch in one pass: 73 GB of scratch beside 25 GB of inputs and outputs)")
+    ap.add_argument("--ncol", type=int, default=1048576, help="columns per GPU (C3)")
+    ap.add_argument("--chunk", type=int, default=524288,
+                    help="columns per internal pass of the library (scratch is ~1.3 KB per (column, layer) of the pass)")
     ap.add_argument("--e2e-cols", type=int, default=262144,
                     help="columns per end-to-end step (pinned host buffers, 33 KB per column)")
     ap.add_argument("--ref-cols", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the C2 / C4 / C5 device-timed extras")
     ap.add_argument("--precision", type=int, default=64, choices=[64, 32],
                     help="64 = the headline FP64 path; 32 = the optional FP32 mode of the band kernels (secondary line)")
-    ap.add_argument("--band-kernel", type=int, default=2, choices=[2, 3],
-                    help="2 = one thread per (column, band), all g-points in registers; 3 = g-points across lanes")
-    ap.add_argument("--gather", action="store_true",
-                    help="N > 1 only: also time the step WITH the NCCL gather of the six output arrays into rank 0, "
-                         "pipelined in 4 column chunks (sharding.pipelined_gather); adds a 'gather' object")
+    ap.add_argument("--band-kernel", type=int, default=4, choices=[2, 4],
+                    help="4 = two-phase path (taumol per (column, layer) + sweep kernels); 2 = fused per-band kernels")
+    ap.add_argument("--gather-chunks", type=int, default=8,
+                    help="N > 1: column chunks of a rank's block whose output gathers (NCCL, into rank 0) overlap the next "
+                         "chunk's kernels")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
@@ -238,24 +329,48 @@ def main():
     api.set_chunk(args.chunk)
     api.set_option("band_kernel", args.band_kernel)
     api.set_option("precision", args.precision)
+    W = max(args.warmup, 3)
+    flops = {}
+    try:
+        fj = json.load(open(os.path.join(ROOT, "profiles", "flops_per_column.json")))
+        flops = {k: v["flops"] for k, v in fj.items() if isinstance(v, dict)}
+    except (OSError, ValueError, KeyError):
+        pass
 
+    # ------------------------------------------------------------------ headline: C3, weak scaling
     ncol = args.ncol
-    b = make_device_batch(ncol, dev, rank)
-    out = driver._outputs(NLAY, ncol, like=b.play)
-    conv = driver._conv(b, dev)
-    at = driver.atm_args(b, conv)
-    cl = [b.cldfrac, b.ciwp, b.clwp, b.rei, b.rel, b.tauc]
-
-    def step():
-        api.rrtmg_lw_mcica(ncol, NLAY, 2, 0, 1, 0, *at, 2, 3, 1, *cl, None, b.tauaer, out["uflx"], out["dflx"],
-                           out["hr"], out["uflxc"], out["dflxc"], out["hrc"], None, None)
+    wl = Workload(api, driver, dev, ncol, NLAY, 2, 0, False, rank)
+    rows = wl.rows
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    # N > 1: the step INCLUDES the gather of every rank's six output arrays into rank 0 (the one exchange of the path,
+    # SURVEY 8(e)): the rank's block runs in column chunks whose packed (rows, chunk) output buffers are the send
+    # buffers; chunk i's gather (NCCL stream) overlaps chunk i+1's kernels.  N = 1 has nothing to gather.
+    nch = max(1, args.gather_chunks)
+    cw = -(-ncol // nch)
+    nch = -(-ncol // cw)
+    send = recv = None
+    if world > 1:
+        send = [torch.zeros((wl.R, cw), dtype=torch.float64, device=dev) for _ in range(nch)]
+        if rank == 0:   # [chunk][rank] packed blocks: the gathered result, no further assembly
+            recv = torch.empty((nch, world, wl.R, cw), dtype=torch.float64, device=dev)
+
+    def step_gathered():
+        works = []
+        for c in range(nch):
+            lo, hi = c * cw, min((c + 1) * cw, ncol)
+            wl.step(lo, hi, out=packed_views(send[c], rows), out_ld=cw)
+            works.append(dist.gather(send[c], [recv[c, r] for r in range(world)] if rank == 0 else None, dst=0,
+                                     async_op=True))
+        for w_ in works:
+            w_.wait()
+
+    step = step_gathered if world > 1 else wl.step
+    for _ in range(W):
         step()
     barrier()
     api.sync()
@@ -263,81 +378,43 @@ def main():
     if rank == 0:
         sampler.start()
     api.launch_count(reset=True)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    ms = timed(torch, dist, world, dev, step, args.steps, 0)
     launches = api.launch_count(reset=True)
     clocks = sampler.stop() if rank == 0 else None
     api.sync()
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
     value = world * ncol * args.steps / (ms * 1e-3)
+    gather_res = None
+    if world > 1:
+        # the same step without the exchange, for reference; and the proof that what arrived is what was computed
+        ms_ng = timed(torch, dist, world, dev, wl.step, max(2, min(args.steps, 5)), 1) / max(2, min(args.steps, 5))
+        step_gathered()
+        wl.step()
+        torch.cuda.synchronize()
+        mine = torch.stack([send[c][:, :min(cw, ncol - c * cw)].sum() for c in range(nch)]).sum().reshape(1)
+        sums = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(sums, mine)
+        same = None
+        if rank == 0:
+            got = [float(recv[:, r].sum()) for r in range(world)]
+            same = bool(all(abs(got[r] - float(sums[r])) <= 1e-9 * abs(got[r]) for r in range(world)))
+            same = same and bool(torch.equal(torch.cat([recv[c, 0][:, :min(cw, ncol - c * cw)] for c in range(nch)], dim=1),
+                                             wl.pack))
+        gather_res = {"included_in_value": True, "chunks": nch, "dst": 0, "transport": "NCCL gather (torch.distributed) of "
+                      "packed (rows, chunk) buffers the kernels write directly; no packing, no assembly",
+                      "bytes_into_root_per_step": (world - 1) * ncol * wl.R * 8,
+                      "ungathered": {"value": world * ncol / (ms_ng * 1e-3), "unit": "columns/s", "ms_per_step": ms_ng},
+                      "root_holds_every_ranks_block": same}
 
-    # instrumented extra step: CUDA events (library, launching stream) around the band kernels
+    # instrumented extra step: CUDA events (library, launching stream) around every kernel of the pipeline
     api.set_timing(True)
-    step()
+    wl.step()
     torch.cuda.synchronize()
     ms_band, ms_all = api.last_timing()
-    ms_bands = api.last_band_timing()
+    stages = api.last_stage_timing()
     api.set_timing(False)
-
-    # ---- optional: the same step followed by the output gather to rank 0, chunk i's NCCL gather
-    # overlapping chunk i+1's kernels; timed like the headline (device events, max over ranks)
-    gather_res = None
-    if world > 1 and args.gather:
-        from rrtmg_lw_b200 import sharding
-        rows = [("uflx", NLAY + 1), ("dflx", NLAY + 1), ("hr", NLAY), ("uflxc", NLAY + 1), ("dflxc", NLAY + 1),
-                ("hrc", NLAY)]
-        co = api.col_offset
-
-        def run_chunk(lo, hi, outs):
-            a = [co(x, lo) for x in at]
-            c_ = [co(x, lo) for x in cl[:5]] + [co(b.tauc, lo, 16)]
-            o = {k: co(out[k], lo) for k, _ in rows}
-            api.rrtmg_lw_mcica(hi - lo, NLAY, 2, 0, 1, 0, *a, 2, 3, 1, *c_, None, co(b.tauaer, lo), o["uflx"], o["dflx"],
-                               o["hr"], o["uflxc"], o["dflxc"], o["hrc"], None, None, ld=ncol)
-            for k, _ in rows:
-                outs[k].copy_(out[k][:, lo:hi])
-
-        def step_gather():
-            return sharding.pipelined_gather(world * ncol, rows, run_chunk, nchunks=4, dst=0, device=dev)
-
-        step()
-        torch.cuda.synchronize()
-        keep_local = {k: out[k].clone() for k, _ in rows} if rank == 0 else None
-        g = step_gather()
-        barrier()
-        same = bool(all(torch.equal(g[k][:, :ncol], keep_local[k]) for k, _ in rows)) if rank == 0 else None
-        del g, keep_local
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        kg = max(2, min(args.steps, 5))
-        barrier()
-        g0.record()
-        for _ in range(kg):
-            g = step_gather()
-            del g
-        g1.record()
-        barrier()
-        msg = g0.elapsed_time(g1)
-        tg = torch.tensor([msg], device=dev, dtype=torch.float64)
-        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
-        msg = float(tg.item()) / kg
-        gather_res = {"value": world * ncol / (msg * 1e-3), "unit": "columns/s", "ms_per_step": msg, "steps": kg,
-                      "chunks": 4, "dst": 0, "bytes_into_root_per_step": (world - 1) * ncol * (6 * NLAY + 4) * 8,
-                      "root_block_equals_ungathered_step": same,
-                      "note": "step in 4 column chunks; chunk i's ncclGather (NCCL stream) overlaps chunk i+1's kernels; "
-                              "includes packing and the assembly of the (rows, N*ncol) arrays on rank 0"}
 
     res = None
     if rank == 0:
-        # ---- roofline of the dominant kernel group (the 16 band kernels of a pass)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -346,25 +423,29 @@ def main():
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
         fp64_peak = api.fp64_peak()
-        flops_per_col = 606259.0      # op-counting oracle, DESIGN.md section "Algorithmic work"
+        flops_per_col = flops.get("C3", 606259.0)   # op-counting oracle (tools/count_flops.py)
         bytes_per_col = (37 * NLAY + 19 + 6 * NLAY + 4) * 8.0   # API words in + out, SURVEY 8(d)
         cols_per_s_band = ncol / (ms_band * 1e-3)
+        two = args.band_kernel == 4 and args.precision == 64
         roof = {
             "bound": "fp64",
-            "kernel": ("band_kernel<1..16,CLD_MASK,0>" if args.band_kernel == 2 else "gband_kernel<1..16,CLD_MASK>") +
-                      " (16 launches per pass of %d columns)" % args.chunk,
+            "kernel": ("taumol_kernel + 16 rtrnmc_kernel<B,1,CLD_MASK,0> per pass of %d columns (timed one after the other)"
+                       if two else "band_kernel<1..16,CLD_MASK,0> (16 launches per pass of %d columns)") % args.chunk,
             "achieved": flops_per_col * cols_per_s_band / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
             "frac": flops_per_col * cols_per_s_band / 1e12 / fp64_peak,
             "peak_source": "DFMA microbenchmark run in this process (rrtmg_lw_b200_fp64_peak)",
             "flops_per_column": flops_per_col, "band_kernels_ms_per_step": ms_band, "all_kernels_ms_per_step": ms_all,
-            "per_band_ms_per_step": [round(x, 3) for x in ms_bands],
+            "per_stage_ms_per_step": [round(x, 3) for x in stages],
+            "stages": (["taumol"] + ["sweep band %d" % b for b in range(1, 17)]) if two else ["band %d" % b for b in range(1, 17)],
+            "note": "the reference arithmetic is not FMA-contracted (-fmad=false up to the table indices): 0.5 of the DFMA "
+                    "peak is the ceiling of a bit-faithful kernel",
             "traffic": None,
             "hbm": {"achieved": bytes_per_col * cols_per_s_band / 1e9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": bytes_per_col * cols_per_s_band / 1e9 / hbm_peak, "bytes_per_column": bytes_per_col,
                     "peak_source": hbm_src},
         }
-        # DRAM bytes of the same 16 launches from the committed ncu capture (profiles/traffic.json: bytes per
-        # column of dram__bytes_read.sum + dram__bytes_write.sum over bands 1..16), scaled to this step
+        # DRAM bytes of the same launches from the committed ncu capture (profiles/traffic.json, regenerated from the
+        # capture's CSV by tools/traffic_json.py), scaled to this step
         prof = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(prof):
             try:
@@ -372,18 +453,19 @@ def main():
                 if tj.get("band_kernel") == args.band_kernel:
                     roof["traffic"] = tj["dram_bytes_per_column"] * ncol
                     roof["traffic_note"] = tj.get("note")
-                    # what the band kernels actually pull through DRAM (scratch included) against the same peak
                     roof["hbm"]["traffic_gbs"] = roof["traffic"] / (ms_band * 1e-3) / 1e9
                     roof["hbm"]["traffic_frac"] = roof["hbm"]["traffic_gbs"] / hbm_peak
             except (OSError, ValueError, KeyError):
                 pass
         res = {
             "metric": "columns/sec", "value": value, "unit": "columns/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64" if args.precision == 64 else "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "columns_per_gpu": ncol, "layers": NLAY, "chunk_columns": args.chunk,
                        "entry": "rrtmg_lw_b200_rrtmg_lw_mcica (device pointers)", "l2": "inputs (>=20 GB) larger than L2",
                        "fma": "off (-fmad=false)", "band_kernel": args.band_kernel,
+                       "multi_gpu": ("column blocks per rank; value INCLUDES the NCCL gather of all outputs into rank 0"
+                                     if world > 1 else "single GPU: nothing to gather"),
                        "precision": "fp64" if args.precision == 64 else
                                     "optional fp32 mode: float band kernels, double flux accumulators (tolerance 0.05 W m-2 / 0.01 K/day)"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof,
@@ -392,6 +474,8 @@ def main():
             res["gather"] = gather_res
 
     # ---- e2e: same metric through the C ABI with HOST (pinned) buffers, H2D + D2H inside the timed region
+    b = wl.b
+    out = wl.out
     ne = min(args.e2e_cols, ncol)
     names = ["play", "plev", "tlay", "tlev", "tsfc", "h2ovmr", "o3vmr", "co2vmr", "ch4vmr", "n2ovmr", "o2vmr",
              "cfc11vmr", "cfc12vmr", "cfc22vmr", "ccl4vmr", "emis", "cldfrac", "ciwp", "clwp", "rei", "rel", "tauaer"]
@@ -441,9 +525,75 @@ def main():
         res["e2e"] = {"value": world * ne * ke / te, "unit": "columns/s", "h2d_bytes_per_step": h2d,
                       "d2h_bytes_per_step": d2h, "columns_per_step": ne, "steps": ke,
                       "note": "host pinned buffers -> rrtmg_lw_b200_rrtmg_lw_mcica(HOST) -> host; result fluxes read back"}
+        wl.step()
+        torch.cuda.synchronize()
         # sanity of the timed outputs
         res["checks"] = {"toa_up_mean": float(out["uflx"][-1].mean()), "sfc_down_mean": float(out["dflx"][0].mean()),
                          "host_equals_device": bool(np.array_equal(ho["uflx"], out["uflx"][:, :ne].cpu().numpy()))}
+    del hb, tauc_h, ho
+
+    # ------------------------------------------------------------------ the other BASELINE.json configurations
+    # device-timed like the headline (same events, barrier, max over ranks); each with its own op-counted flops/column.
+    # C2 and C4 run as per-rank replicas (weak, like C3); C5 is ONE 1440 x 720 grid block-partitioned over the ranks
+    # (strong scaling), outputs gathered into rank 0 inside the timed step when N > 1.
+    extras = {}
+    if not args.no_extra_configs and args.precision == 64:
+        del wl, out, b
+        send = recv = None
+        torch.cuda.empty_cache()
+
+        def run_extra(name, w2, k, note, gather=False):
+            f = w2.step
+            if gather and world > 1:
+                rbuf = torch.empty((world, w2.R, w2.ncol), dtype=torch.float64, device=dev) if rank == 0 else None
+
+                def f():
+                    w2.step()
+                    dist.gather(w2.pack, [rbuf[r] for r in range(world)] if rank == 0 else None, dst=0)
+            msx = timed(torch, dist, world, dev, f, k, 2) / k
+            api.set_timing(True)
+            w2.step()
+            torch.cuda.synchronize()
+            mb, ma = api.last_timing()
+            api.set_timing(False)
+            if rank == 0:
+                tot = world * w2.ncol
+                fl = flops.get(name)
+                extras[name] = {"value": tot / (msx * 1e-3), "unit": "columns/s", "ms_per_step": msx, "columns": tot,
+                                "layers": w2.nlay, "steps": k, "config": note, "flops_per_column": fl,
+                                "band_kernels_ms_per_step": mb,
+                                "fp64_frac_band_kernels": (fl * w2.ncol / (mb * 1e-3) / 1e12 / fp64_peak) if fl else None,
+                                "toa_up_mean": float(w2.out["uflx"][-1].mean())}
+
+        api.set_option("release_scratch", 1)
+        api.set_chunk(262144)
+        w2 = Workload(api, driver, dev, 65536, NLAY, 0, 0, False, rank, clear=True)
+        run_extra("C2", w2, 5, "clear sky, rrtmg_lw() strict entry, idrv=0, 65 536 columns x 72 layers per GPU (weak)")
+        del w2
+        torch.cuda.empty_cache()
+        w2 = Workload(api, driver, dev, ncol, NLAY, 5, 1, True, rank)
+        run_extra("C4", w2, 3, "icld=5 exponential-random overlap, idcor=1 alpha (get_alpha on device), 16-band aerosol "
+                  "tau, idrv=1; %d columns x 72 layers per GPU (weak)" % ncol)
+        del w2
+        torch.cuda.empty_cache()
+        api.set_option("release_scratch", 1)
+        api.set_chunk(131072)
+        n5 = 1440 * 720
+        per = -(-n5 // world)
+        n5_loc = max(0, min(per, n5 - rank * per))
+        w2 = Workload(api, driver, dev, n5_loc, 137, 2, 0, False, 100 + rank)
+        run_extra("C5", w2, 2, "global 0.25 degree grid 1440 x 720 = 1 036 800 columns x 137 layers, McICA cloudy, "
+                  "block-partitioned over %d GPU(s) (STRONG scaling)%s" % (world, "; outputs gathered into rank 0 inside "
+                  "the timed step" if world > 1 else ""), gather=True)
+        if rank == 0:
+            extras["C5"]["columns"] = n5
+            extras["C5"]["value"] = n5 / (extras["C5"]["ms_per_step"] * 1e-3)
+            extras["C5"]["scaling"] = "strong"
+        del w2
+        torch.cuda.empty_cache()
+    if rank == 0:
+        if extras:
+            res["other_configs"] = extras
         if world == 1 and not args.no_cpu_baseline:
             os.sched_setaffinity(0, all_cpus)  # the CPU baseline uses every host core again
             from oracle import orc

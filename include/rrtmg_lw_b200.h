@@ -149,6 +149,13 @@ int rrtmg_lw_b200_set_chunk(int max_columns);
  *   0 = one sweep kernel per band.
  * "band_lo" / "band_hi": band range istart..iend of the following runs (default 1..16): only those bands enter the
  *   flux sums, as in the column-mode program's per-band output (src/rrtmg_lw.1col.f90:463-467); two-phase path.
+ * "concurrency": 1 (default) = independent kernels of a pass run on side streams of the library (McICA generator and
+ *   cloud optics beside taumol, the sweep kernels beside each other), forked from and joined to the caller's stream;
+ *   0 = everything on the caller's stream.
+ * "out_ld": column extent of the OUTPUT arrays of the following device-pointer calls when it differs from ld (0 =
+ *   same as ld): a call on a column sub-range of a resident batch (inputs offset, ld = the batch's extent) can write
+ *   its fluxes straight into a packed, chunk-sized send buffer.  out_ld >= ncol.
+ * "release_scratch": frees the library-owned scratch now (any value); the next call re-allocates what it needs.
  * "host_chunk": columns per staged pass of a host-pointer call (default 32768); passes alternate between two
  *   staging arenas so the H2D copy of pass k+1 and the D2H copy of pass k-1 overlap the kernels of pass k.
  * "precision": 64 (default) or 32 = the optional FP32 mode of BASELINE.json's north star: float band kernels

@@ -40,6 +40,7 @@ struct Ctx {
     cudaStream_t side[NSIDE] = {};
     cudaEvent_t e_fork = nullptr, e_colprep = nullptr, e_t = nullptr, e_cld = nullptr, e_side[NSIDE] = {};
     int concurrency = 1;      // set_option("concurrency", 0) keeps every kernel on the caller's stream
+    long out_ld = 0;          // set_option("out_ld", n): column extent of the OUTPUT arrays of device-pointer calls (0 = ld)
     long cap_cols = 0;
     int cap_lay = 0;
     unsigned have = 0;        // ScratchPiece bits allocated at the current capacity
@@ -732,7 +733,7 @@ extern "C" int rrtmg_lw_b200_rrtmg_lw(int ncol, int ld, int nlay, int* icld, int
         in.cldfmcl = cldfmcl; in.taucmcl = taucmcl; in.ciwpmcl = ciwpmcl; in.clwpmcl = clwpmcl;
         in.reicmcl = reicmcl; in.relqmcl = relqmcl;
         in.ld = ld; in.nlay = nlay;
-        ColOut out{uflx, dflx, hr, uflxc, dflxc, hrc, duflx_dt, duflxc_dt, ld};
+        ColOut out{uflx, dflx, hr, uflxc, dflxc, hrc, duflx_dt, duflxc_dt, G.out_ld > 0 ? G.out_ld : (long)ld};
         return run_device(MODE_STRICT, ncol, nlay, *icld, idrv, inflglw, iceflglw, liqflglw, 0, 0, in, out, st);
     }
     // host pointers: staged, pipelined passes
@@ -793,7 +794,7 @@ extern "C" int rrtmg_lw_b200_rrtmg_lw_mcica(int ncol, int ld, int nlay, int icld
         in.cfc22 = cfc22vmr; in.ccl4 = ccl4vmr; in.emis = emis; in.tauaer = tauaer;
         in.cldfrac = cldfrac; in.ciwp = ciwp; in.clwp = clwp; in.rei = rei; in.rel = rel; in.tauc = tauc; in.alpha = alpha;
         in.ld = ld; in.nlay = nlay;
-        ColOut out{uflx, dflx, hr, uflxc, dflxc, hrc, duflx_dt, duflxc_dt, ld};
+        ColOut out{uflx, dflx, hr, uflxc, dflxc, hrc, duflx_dt, duflxc_dt, G.out_ld > 0 ? G.out_ld : (long)ld};
         return run_device(MODE_FUSED, ncol, nlay, icld_overlap, idrv, inflglw, iceflglw, liqflglw, permuteseed, irng, in,
                           out, st);
     }
@@ -1017,6 +1018,17 @@ extern "C" int rrtmg_lw_b200_set_option(const char* name, int value) {
     if (std::strcmp(name, "band_kernel") == 0) {
         if (value != 2 && value != 4) return RRTMG_LW_ERR_ARG;
         G.band_kernel = value;
+        return RRTMG_LW_OK;
+    }
+    if (std::strcmp(name, "release_scratch") == 0) {
+        // give the library-owned scratch back to the device (it is re-allocated by the next call that needs it)
+        cudaDeviceSynchronize();
+        free_scratch();
+        return RRTMG_LW_OK;
+    }
+    if (std::strcmp(name, "out_ld") == 0) {
+        if (value < 0) return RRTMG_LW_ERR_ARG;
+        G.out_ld = value;
         return RRTMG_LW_OK;
     }
     if (std::strcmp(name, "concurrency") == 0) {
