@@ -136,6 +136,12 @@ int rrtmg_lw_b200_debug_stages(int icol, int* ints6, double* facs, double* taug,
  * count (0 = unknown name); copies min(count, cap) doubles when out != NULL. */
 long rrtmg_lw_b200_get_table(const char* name, double* out, long cap);
 
+/* Multi-GPU from one host process: the library keeps one context (tables, scratch, streams, options) per
+ * CUDA device.  rrtmg_lw_b200_set_device(d) makes the following calls of this process run on device d (and makes d
+ * the thread's current CUDA device); d = -1 (default) follows whatever device is current when an entry is called, so
+ * one-process-per-GPU hosts need not call it.  Each device is initialised with its own rrtmg_lw_b200_ini call. */
+int rrtmg_lw_b200_set_device(int device);
+
 /* Upper bound of columns processed per internal pass of a device-pointer call (default 262144; scratch is
  * sized to min(ncol, max_columns): about 1.3 KB per (column, layer) on the default two-phase path). */
 int rrtmg_lw_b200_set_chunk(int max_columns);

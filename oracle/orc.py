@@ -155,6 +155,24 @@ def count_ops(kdata_blob, b, icld=0, idrv=0, irng=0, alpha=None, default_real_ki
     return d
 
 
+BRANCH_ADJFAC_SITES = ("taumol:550 b3 lower n2o", "taumol:736 b3 upper n2o", "taumol:1355 b6 co2", "taumol:1483 b7 lower co2",
+                       "taumol:1639 b7 upper co2", "taumol:1721 b8 lower co2", "taumol:1768 b8 upper co2",
+                       "taumol:1879 b9 lower n2o", "taumol:2036 b9 upper n2o", "taumol:2497 b13 co2")
+BINARY_LOWER_BANDS = (3, 4, 5, 7, 9, 12, 13, 15, 16)
+
+
+def branch_counts(reset=False):
+    """Branch-coverage counters of the oracle since the last reset (orc_common.h NBRANCH), decoded:
+    eta[band][corner][branch] (branch 0: specparm < 0.125, 1: > 0.875, 2: linear), half[band][0 lower | 1 upper]
+    (layers evaluated), adjfac[10] (sites in source order), cloudy[3], clear[2]."""
+    n = lib().orc_branch_counts(None, 0, 0)
+    raw = (C.c_longlong * n)()
+    lib().orc_branch_counts(raw, n, 1 if reset else 0)
+    v = np.array(list(raw), dtype=np.int64)
+    return dict(eta=v[0:96].reshape(16, 2, 3), half=v[96:128].reshape(16, 2), adjfac=v[128:138], cloudy=v[138:141],
+                clear=v[141:143])
+
+
 def mt_stream(seed, n):
     ints = np.zeros(n, dtype=np.uint32); reals = np.zeros(n)
     lib().orc_mt_stream(seed, n, ints.ctypes.data_as(C.POINTER(C.c_uint)), _p(reals))

@@ -4,6 +4,8 @@
 #include <cstdlib>
 
 #include "orc_common.h"
+#include <atomic>
+
 #include "orc_api.h"
 
 namespace orc {
@@ -222,6 +224,22 @@ extern "C" long orc_get_table(const char* name, double* out, long cap) {
     }
     if (out) for (long i = 0; i < cnt && i < cap; ++i) out[i] = src[i];
     return cnt;
+}
+
+// branch-coverage counters (orc_common.h NBRANCH): copies them out and optionally resets them
+static std::atomic<long long> g_branch[orc::NBRANCH];
+namespace orc {
+thread_local int g_cur_band = 0;
+void branch_hit(int idx, long long n) {
+    if (idx >= 0 && idx < NBRANCH) g_branch[idx].fetch_add(n, std::memory_order_relaxed);
+}
+}  // namespace orc
+extern "C" int orc_branch_counts(long long* out, int cap, int reset) {
+    for (int i = 0; i < orc::NBRANCH; ++i) {
+        if (out && i < cap) out[i] = g_branch[i].load();
+        if (reset) g_branch[i].store(0);
+    }
+    return orc::NBRANCH;
 }
 
 // op-counting build only (liborc_count.so): counters of the calling thread since the last reset

@@ -159,6 +159,19 @@ struct Column {
     double& LG(std::vector<double>& v, int l, int ig) { return v[(l - 1) + nlayers * (ig - 1)]; }
 };
 
+// Branch-coverage counters of the oracle (test infrastructure for the parity suite): how often each data-dependent branch
+// of the reference algorithm was taken since the last reset, summed over all threads.  tests/ assert that the batches
+// the CUDA path is compared on really exercise every branch.  Layout (orc_branch_counts):
+//   [0, 96)   eta interpolation, taumol.f90:569-598 and twins: band (1..16) x corner (ind0 / ind1) x branch
+//             (specparm < 0.125, specparm > 0.875, linear): index ((band-1)*2 + corner)*3 + branch
+//   [96, 128) atmosphere halves: (band-1)*2 + (0 lower: lay <= laytrop, 1 upper)   -- layers evaluated
+//   [128,138) adjfac sites taken (rat > threshold), in source order taumol.f90:550,736,1355,1483,1639,1721,1768,1879,2036,2497
+//   [138,141) cloudy-layer sub-branches of rtrnmc.f90:358-425 (odtot < 0.06, odepth <= 0.06, else)
+//   [141,143) clear-layer branches rtrnmc.f90:429-440 (odepth <= 0.06, table)
+constexpr int NBRANCH = 143;
+void branch_hit(int idx, long long n = 1);
+extern thread_local int g_cur_band;  // set by the taugbN being evaluated (for the shared eta_fac helper)
+
 // status codes shared by oracle entry points (mirror the reference's STOP sites)
 enum {
     ORC_OK = 0,

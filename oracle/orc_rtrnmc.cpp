@@ -76,6 +76,7 @@ void rtrnmc(Column& c, int istart, int iend, int iout, int idrv, bool dump_itr) 
                     double odtot = odepth + c.LG(odcld, lev, igc);
                     double cf = c.CLD(c.cldfmc, igc, lev), ef = c.LG(efclfrac, lev, igc);
                     if (odtot < 0.06) {
+                        branch_hit(138);
                         atrans[lev] = odepth - 0.5 * odepth * odepth;
                         double odepth_rec = rec_6 * odepth;
                         double gassrc = plfrac * (blay + dplankdn * odepth_rec) * atrans[lev];
@@ -89,6 +90,7 @@ void rtrnmc(Column& c, int istart, int iend, int iout, int idrv, bool dump_itr) 
                         bbugas[lev] = plfrac * (blay + dplankup * odepth_rec);
                         bbutot[lev] = plfrac * (blay + dplankup * odtot_rec);
                     } else if (odepth <= 0.06) {
+                        branch_hit(139);
                         atrans[lev] = odepth - 0.5 * odepth * odepth;
                         double odepth_rec = rec_6 * odepth;
                         double gassrc = plfrac * (blay + dplankdn * odepth_rec) * atrans[lev];
@@ -106,6 +108,7 @@ void rtrnmc(Column& c, int istart, int iend, int iout, int idrv, bool dump_itr) 
                         bbugas[lev] = plfrac * (blay + dplankup * odepth_rec);
                         bbutot[lev] = plfrac * (blay + tfactot * dplankup);
                     } else {
+                        branch_hit(140);
                         double tblind = odepth / (bpade + odepth);
                         int itgas = (int)(tblint * tblind + 0.5);
                         d0 = itgas;
@@ -129,11 +132,13 @@ void rtrnmc(Column& c, int istart, int iend, int iout, int idrv, bool dump_itr) 
                     }
                 } else {
                     if (odepth <= 0.06) {
+                        branch_hit(141);
                         atrans[lev] = odepth - 0.5 * odepth * odepth;
                         odepth = rec_6 * odepth;
                         bbd = plfrac * (blay + dplankdn * odepth);
                         bbugas[lev] = plfrac * (blay + dplankup * odepth);
                     } else {
+                        branch_hit(142);
                         double tblind = odepth / (bpade + odepth);
                         int itr = (int)(tblint * tblind + 0.5);
                         d0 = itr;

@@ -19,6 +19,9 @@ struct Ctx {
     const double *absa, *absb, *selfref, *forref, *fracrefa, *fracrefb;
     int nra, nrb;  // rows of absa / absb
     Ctx(Column& c_, int band) : c(c_), B(G.band[band - 1]), b(band) {
+        g_cur_band = band;
+        branch_hit(96 + (band - 1) * 2, c_.laytrop);
+        branch_hit(96 + (band - 1) * 2 + 1, c_.nlayers - c_.laytrop);
         goff = band == 1 ? 0 : G.ngs[band - 2];
         ng = G.ngc[band - 1];
         absa = B.a("absa"); absb = B.a("absb"); selfref = B.a("selfref"); forref = B.a("forref");
@@ -60,10 +63,12 @@ inline Spec spec(double colA, double rat, double colB, double mult) {
 
 // eta weights for one (p,T) corner pair, taumol.f90:569-598 (and its twins)
 struct Fac { int br; double f0, f1, f2, g0, g1, g2; };  // f* multiply row block 0, g* row block +nsp
-inline Fac eta_fac(double specparm, double fs, double facA, double facB) {
+inline Fac eta_fac(double specparm, double fs, double facA, double facB, int corner) {
     Fac w;
+    const int site = ((g_cur_band - 1) * 2 + corner) * 3;
     if (specparm < 0.125) {
         w.br = 0;
+        branch_hit(site);
         double p = fs - 1;
         double p2 = p * p;
         double p4 = p2 * p2;  // p**4
@@ -74,6 +79,7 @@ inline Fac eta_fac(double specparm, double fs, double facA, double facB) {
         w.g0 = fk0 * facB; w.g1 = fk1 * facB; w.g2 = fk2 * facB;
     } else if (specparm > 0.875) {
         w.br = 1;
+        branch_hit(site + 1);
         double p = -fs;
         double p2 = p * p;
         double p4 = p2 * p2;
@@ -84,6 +90,7 @@ inline Fac eta_fac(double specparm, double fs, double facA, double facB) {
         w.g0 = fk0 * facB; w.g1 = fk1 * facB; w.g2 = fk2 * facB;
     } else {
         w.br = 2;
+        branch_hit(site + 2);
         w.f0 = (1. - fs) * facA; w.g0 = (1. - fs) * facB;
         w.f1 = fs * facA; w.g1 = fs * facB;
         w.f2 = w.g2 = 0.;
@@ -151,11 +158,12 @@ inline double key8b(const Ctx& x, const Spec& s, const Spec& s1, int ind0, int i
                       fac111 * x.Bk(ind1 + 6, ig));
 }
 // gas-amount adjustment with pow, e.g. taumol.f90:547-554
-inline double adjcol(double col, double coldry, double e20, double chiref, double thresh, double base, double expo,
-                     double chiref2) {
+inline double adjcol(int site, double col, double coldry, double e20, double chiref, double thresh, double base,
+                     double expo, double chiref2) {
     double chi = col / coldry;
     double rat = e20 * chi / chiref;
     if (rat > thresh) {
+        branch_hit(128 + site);
         double adjfac = base + std::pow(rat - base, expo);
         return adjfac * chiref2 * coldry * 1.e-20;
     }
@@ -245,13 +253,13 @@ void taugb3(Column& c) {
         Spec s = spec(colh2o, c.rat_h2oco2[lay - 1], colco2, 8.);
         Spec s1 = spec(colh2o, c.rat_h2oco2_1[lay - 1], colco2, 8.);
         Spec sm = spec(colh2o, refrat_m_a, colco2, 8.);
-        double adjcoln2o = adjcol(c.coln2o[lay - 1], c.coldry[lay - 1], 1.e20, G.chi(4, jp + 1), 1.5, 0.5, 0.65,
+        double adjcoln2o = adjcol(0, c.coln2o[lay - 1], c.coldry[lay - 1], 1.e20, G.chi(4, jp + 1), 1.5, 0.5, 0.65,
                                   G.chi(4, jp + 1));
         Spec sp = spec(colh2o, refrat_planck_a, colco2, 8.);
         int ind0, ind1;
         ind_lo(jp, jt, jt1, G.nspa[2], s.js, s1.js, ind0, ind1);
-        Fac w0 = eta_fac(s.parm, s.fs, fac00, fac10);
-        Fac w1 = eta_fac(s1.parm, s1.fs, fac01, fac11);
+        Fac w0 = eta_fac(s.parm, s.fs, fac00, fac10, 0);
+        Fac w1 = eta_fac(s1.parm, s1.fs, fac01, fac11, 1);
         for (int ig = 1; ig <= x.ng; ++ig) {
             double tauself = tauself_(x, c, lay, ig);
             double taufor = taufor_(x, c, lay, ig);
@@ -269,7 +277,7 @@ void taugb3(Column& c) {
         Spec s1 = spec(colh2o, c.rat_h2oco2_1[lay - 1], colco2, 4.);
         Spec sm = spec(colh2o, refrat_m_b, colco2, 4.);
         // :734 "1.e20" is a default-kind literal here (T1)
-        double adjcoln2o = adjcol(c.coln2o[lay - 1], c.coldry[lay - 1], lit(1.e20), G.chi(4, jp + 1), 1.5, 0.5, 0.65,
+        double adjcoln2o = adjcol(1, c.coln2o[lay - 1], c.coldry[lay - 1], lit(1.e20), G.chi(4, jp + 1), 1.5, 0.5, 0.65,
                                   G.chi(4, jp + 1));
         Spec sp = spec(colh2o, refrat_planck_b, colco2, 4.);
         int ind0, ind1;
@@ -296,8 +304,8 @@ void taugb4(Column& c) {
         Spec sp = spec(colh2o, refrat_planck_a, colco2, 8.);
         int ind0, ind1;
         ind_lo(jp, jt, jt1, G.nspa[3], s.js, s1.js, ind0, ind1);
-        Fac w0 = eta_fac(s.parm, s.fs, fac00, fac10);
-        Fac w1 = eta_fac(s1.parm, s1.fs, fac01, fac11);
+        Fac w0 = eta_fac(s.parm, s.fs, fac00, fac10, 0);
+        Fac w1 = eta_fac(s1.parm, s1.fs, fac01, fac11, 1);
         for (int ig = 1; ig <= x.ng; ++ig) {
             double tauself = tauself_(x, c, lay, ig);
             double taufor = taufor_(x, c, lay, ig);
@@ -342,8 +350,8 @@ void taugb5(Column& c) {
         Spec sp = spec(colh2o, refrat_planck_a, colco2, 8.);
         int ind0, ind1;
         ind_lo(jp, jt, jt1, G.nspa[4], s.js, s1.js, ind0, ind1);
-        Fac w0 = eta_fac(s.parm, s.fs, fac00, fac10);
-        Fac w1 = eta_fac(s1.parm, s1.fs, fac01, fac11);
+        Fac w0 = eta_fac(s.parm, s.fs, fac00, fac10, 0);
+        Fac w1 = eta_fac(s1.parm, s1.fs, fac01, fac11, 1);
         for (int ig = 1; ig <= x.ng; ++ig) {
             double tauself = tauself_(x, c, lay, ig);
             double taufor = taufor_(x, c, lay, ig);
@@ -378,7 +386,7 @@ void taugb6(Column& c) {
     for (int lay = 1; lay <= c.laytrop; ++lay) {
         LAYVARS
         double adjcolco2 =
-            adjcol(c.colco2[lay - 1], c.coldry[lay - 1], 1.e20, G.chi(2, jp + 1), 3.0, 2.0, 0.77, G.chi(2, jp + 1));
+            adjcol(2, c.colco2[lay - 1], c.coldry[lay - 1], 1.e20, G.chi(2, jp + 1), 3.0, 2.0, 0.77, G.chi(2, jp + 1));
         int ind0, ind1;
         ind_lo(jp, jt, jt1, G.nspa[5], 1, 1, ind0, ind1);
         for (int ig = 1; ig <= x.ng; ++ig) {
@@ -413,13 +421,13 @@ void taugb7(Column& c) {
         Spec s1 = spec(colh2o, c.rat_h2oo3_1[lay - 1], colo3, 8.);
         Spec sm = spec(colh2o, refrat_m_a, colo3, 8.);
         // :1481 default-kind "1.e20" (T1)
-        double adjcolco2 = adjcol(c.colco2[lay - 1], c.coldry[lay - 1], lit(1.e20), G.chi(2, jp + 1), 3.0, 3.0, 0.79,
+        double adjcolco2 = adjcol(3, c.colco2[lay - 1], c.coldry[lay - 1], lit(1.e20), G.chi(2, jp + 1), 3.0, 3.0, 0.79,
                                   G.chi(2, jp + 1));
         Spec sp = spec(colh2o, refrat_planck_a, colo3, 8.);
         int ind0, ind1;
         ind_lo(jp, jt, jt1, G.nspa[6], s.js, s1.js, ind0, ind1);
-        Fac w0 = eta_fac(s.parm, s.fs, fac00, fac10);
-        Fac w1 = eta_fac(s1.parm, s1.fs, fac01, fac11);
+        Fac w0 = eta_fac(s.parm, s.fs, fac00, fac10, 0);
+        Fac w1 = eta_fac(s1.parm, s1.fs, fac01, fac11, 1);
         for (int ig = 1; ig <= x.ng; ++ig) {
             double tauself = tauself_(x, c, lay, ig);
             double taufor = taufor_(x, c, lay, ig);
@@ -434,7 +442,7 @@ void taugb7(Column& c) {
     for (int lay = c.laytrop + 1; lay <= c.nlayers; ++lay) {
         LAYVARS
         // :1637 default-kind "1.e20" (T1); base 2.0 in the upper atmosphere
-        double adjcolco2 = adjcol(c.colco2[lay - 1], c.coldry[lay - 1], lit(1.e20), G.chi(2, jp + 1), 3.0, 2.0, 0.79,
+        double adjcolco2 = adjcol(4, c.colco2[lay - 1], c.coldry[lay - 1], lit(1.e20), G.chi(2, jp + 1), 3.0, 2.0, 0.79,
                                   G.chi(2, jp + 1));
         int ind0, ind1;
         ind_up(jp, jt, jt1, G.nspb[6], 1, 1, ind0, ind1);
@@ -457,7 +465,7 @@ void taugb8(Column& c) {
     for (int lay = 1; lay <= c.laytrop; ++lay) {
         LAYVARS
         double adjcolco2 =
-            adjcol(c.colco2[lay - 1], c.coldry[lay - 1], 1.e20, G.chi(2, jp + 1), 3.0, 2.0, 0.65, G.chi(2, jp + 1));
+            adjcol(5, c.colco2[lay - 1], c.coldry[lay - 1], 1.e20, G.chi(2, jp + 1), 3.0, 2.0, 0.65, G.chi(2, jp + 1));
         int ind0, ind1;
         ind_lo(jp, jt, jt1, G.nspa[7], 1, 1, ind0, ind1);
         for (int ig = 1; ig <= x.ng; ++ig) {
@@ -475,7 +483,7 @@ void taugb8(Column& c) {
     for (int lay = c.laytrop + 1; lay <= c.nlayers; ++lay) {
         LAYVARS
         double adjcolco2 =
-            adjcol(c.colco2[lay - 1], c.coldry[lay - 1], 1.e20, G.chi(2, jp + 1), 3.0, 2.0, 0.65, G.chi(2, jp + 1));
+            adjcol(6, c.colco2[lay - 1], c.coldry[lay - 1], 1.e20, G.chi(2, jp + 1), 3.0, 2.0, 0.65, G.chi(2, jp + 1));
         int ind0, ind1;
         ind_up(jp, jt, jt1, G.nspb[7], 1, 1, ind0, ind1);
         for (int ig = 1; ig <= x.ng; ++ig) {
@@ -502,13 +510,13 @@ void taugb9(Column& c) {
         Spec s = spec(colh2o, c.rat_h2och4[lay - 1], colch4, 8.);
         Spec s1 = spec(colh2o, c.rat_h2och4_1[lay - 1], colch4, 8.);
         Spec sm = spec(colh2o, refrat_m_a, colch4, 8.);
-        double adjcoln2o = adjcol(c.coln2o[lay - 1], c.coldry[lay - 1], 1.e20, G.chi(4, jp + 1), 1.5, 0.5, 0.65,
+        double adjcoln2o = adjcol(7, c.coln2o[lay - 1], c.coldry[lay - 1], 1.e20, G.chi(4, jp + 1), 1.5, 0.5, 0.65,
                                   G.chi(4, jp + 1));
         Spec sp = spec(colh2o, refrat_planck_a, colch4, 8.);
         int ind0, ind1;
         ind_lo(jp, jt, jt1, G.nspa[8], s.js, s1.js, ind0, ind1);
-        Fac w0 = eta_fac(s.parm, s.fs, fac00, fac10);
-        Fac w1 = eta_fac(s1.parm, s1.fs, fac01, fac11);
+        Fac w0 = eta_fac(s.parm, s.fs, fac00, fac10, 0);
+        Fac w1 = eta_fac(s1.parm, s1.fs, fac01, fac11, 1);
         for (int ig = 1; ig <= x.ng; ++ig) {
             double tauself = tauself_(x, c, lay, ig);
             double taufor = taufor_(x, c, lay, ig);
@@ -521,7 +529,7 @@ void taugb9(Column& c) {
     }
     for (int lay = c.laytrop + 1; lay <= c.nlayers; ++lay) {
         LAYVARS
-        double adjcoln2o = adjcol(c.coln2o[lay - 1], c.coldry[lay - 1], 1.e20, G.chi(4, jp + 1), 1.5, 0.5, 0.65,
+        double adjcoln2o = adjcol(8, c.coln2o[lay - 1], c.coldry[lay - 1], 1.e20, G.chi(4, jp + 1), 1.5, 0.5, 0.65,
                                   G.chi(4, jp + 1));
         int ind0, ind1;
         ind_up(jp, jt, jt1, G.nspb[8], 1, 1, ind0, ind1);
@@ -605,8 +613,8 @@ void taugb12(Column& c) {
         Spec sp = spec(colh2o, refrat_planck_a, colco2, 8.);
         int ind0, ind1;
         ind_lo(jp, jt, jt1, G.nspa[11], s.js, s1.js, ind0, ind1);
-        Fac w0 = eta_fac(s.parm, s.fs, fac00, fac10);
-        Fac w1 = eta_fac(s1.parm, s1.fs, fac01, fac11);
+        Fac w0 = eta_fac(s.parm, s.fs, fac00, fac10, 0);
+        Fac w1 = eta_fac(s1.parm, s1.fs, fac01, fac11, 1);
         for (int ig = 1; ig <= x.ng; ++ig) {
             double tauself = tauself_(x, c, lay, ig);
             double taufor = taufor_(x, c, lay, ig);
@@ -638,13 +646,13 @@ void taugb13(Column& c) {
         Spec sm = spec(colh2o, refrat_m_a, coln2o, 8.);
         // :2494-2501  ratco2 uses 3.55e-4_rb, adjcolco2 the default-kind 3.55e-4 (T1)
         double adjcolco2 =
-            adjcol(c.colco2[lay - 1], c.coldry[lay - 1], 1.e20, 3.55e-4, 3.0, 2.0, 0.68, lit(3.55e-4));
+            adjcol(9, c.colco2[lay - 1], c.coldry[lay - 1], 1.e20, 3.55e-4, 3.0, 2.0, 0.68, lit(3.55e-4));
         Spec smco = spec(colh2o, refrat_m_a3, coln2o, 8.);
         Spec sp = spec(colh2o, refrat_planck_a, coln2o, 8.);
         int ind0, ind1;
         ind_lo(jp, jt, jt1, G.nspa[12], s.js, s1.js, ind0, ind1);
-        Fac w0 = eta_fac(s.parm, s.fs, fac00, fac10);
-        Fac w1 = eta_fac(s1.parm, s1.fs, fac01, fac11);
+        Fac w0 = eta_fac(s.parm, s.fs, fac00, fac10, 0);
+        Fac w1 = eta_fac(s1.parm, s1.fs, fac01, fac11, 1);
         for (int ig = 1; ig <= x.ng; ++ig) {
             double tauself = tauself_(x, c, lay, ig);
             double taufor = taufor_(x, c, lay, ig);
@@ -706,8 +714,8 @@ void taugb15(Column& c) {
         int ind0, ind1;
         ind_lo(jp, jt, jt1, G.nspa[14], s.js, s1.js, ind0, ind1);
         double scalen2 = c.colbrd[lay - 1] * c.scaleminor[lay - 1];
-        Fac w0 = eta_fac(s.parm, s.fs, fac00, fac10);
-        Fac w1 = eta_fac(s1.parm, s1.fs, fac01, fac11);
+        Fac w0 = eta_fac(s.parm, s.fs, fac00, fac10, 0);
+        Fac w1 = eta_fac(s1.parm, s1.fs, fac01, fac11, 1);
         for (int ig = 1; ig <= x.ng; ++ig) {
             double tauself = tauself_(x, c, lay, ig);
             double taufor = taufor_(x, c, lay, ig);
@@ -737,8 +745,8 @@ void taugb16(Column& c) {
         Spec sp = spec(colh2o, refrat_planck_a, colch4, 8.);
         int ind0, ind1;
         ind_lo(jp, jt, jt1, G.nspa[15], s.js, s1.js, ind0, ind1);
-        Fac w0 = eta_fac(s.parm, s.fs, fac00, fac10);
-        Fac w1 = eta_fac(s1.parm, s1.fs, fac01, fac11);
+        Fac w0 = eta_fac(s.parm, s.fs, fac00, fac10, 0);
+        Fac w1 = eta_fac(s1.parm, s1.fs, fac01, fac11, 1);
         for (int ig = 1; ig <= x.ng; ++ig) {
             double tauself = tauself_(x, c, lay, ig);
             double taufor = taufor_(x, c, lay, ig);

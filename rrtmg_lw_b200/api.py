@@ -60,6 +60,7 @@ SIGNATURES = {
     "rrtmg_lw_b200_get_table": (C.c_long, [C.c_char_p, _dp, C.c_long]),
     "rrtmg_lw_b200_set_chunk": (C.c_int, [C.c_int]),
     "rrtmg_lw_b200_set_option": (C.c_int, [C.c_char_p, C.c_int]),
+    "rrtmg_lw_b200_set_device": (C.c_int, [C.c_int]),
     "rrtmg_lw_b200_kiss_jump_selftest": (C.c_int, []),
     "rrtmg_lw_b200_launch_count": (C.c_long, [C.c_int]),
     "rrtmg_lw_b200_set_timing": (C.c_int, [C.c_int]),
@@ -230,6 +231,13 @@ def sync():
         e = RrtmgLwError(rc, "device status (column %d, layer %d)" % (col.value, lay.value))
         e.col, e.lay = col.value, lay.value
         raise e
+
+
+def set_device(device):
+    """Bind the following calls of this process to CUDA device ``device`` (-1: follow the current device)."""
+    rc = lib().rrtmg_lw_b200_set_device(int(device))
+    if rc:
+        raise RrtmgLwError(rc, "set_device")
 
 
 def set_chunk(n):

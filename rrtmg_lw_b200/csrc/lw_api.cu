@@ -75,9 +75,28 @@ struct Ctx {
     float ms_bands[NBND + 2] = {};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t evb[NBND + 3] = {};
-    std::mutex mu;
 };
-Ctx G;
+// One context per CUDA device: tables, scratch, streams and options belong to the device they were created on.
+// rrtmg_lw_b200_set_device(d) binds the calling process's following calls to device d (one host process can drive
+// several GPUs by switching between them); without it the library follows the caller's current device.
+constexpr int LW_MAX_DEVICES = 16;
+Ctx g_ctx[LW_MAX_DEVICES];
+int g_cur = 0;        // context of the call in progress
+int g_explicit = -1;  // device chosen with set_device, -1 = follow cudaGetDevice
+std::mutex g_mu;
+#define G (g_ctx[g_cur])
+void select_ctx() {
+    int d = 0;
+    if (g_explicit >= 0) {
+        d = g_explicit;
+        int cur = -1;
+        if (cudaGetDevice(&cur) == cudaSuccess && cur != d) cudaSetDevice(d);
+    } else if (cudaGetDevice(&d) != cudaSuccess) {
+        d = 0;
+    }
+    g_cur = (d >= 0 && d < LW_MAX_DEVICES) ? d : 0;
+}
+#define LW_ENTER() std::lock_guard<std::mutex> lk(g_mu); select_ctx()
 
 #define CK(x)                                                                            \
     do {                                                                                 \
@@ -520,7 +539,7 @@ static std::vector<double> g_kstage;
 static std::vector<char> g_khave;
 
 extern "C" int rrtmg_lw_b200_kdata_put(int band, const char* name, const double* data, long n) {
-    std::lock_guard<std::mutex> lk(G.mu);
+    LW_ENTER();
     if (!name || !data) return RRTMG_LW_ERR_ARG;
     if (g_kstage.empty()) {
         g_kstage.assign(RRTMG_LW_KDATA_DOUBLES, 0.0);
@@ -542,7 +561,7 @@ extern "C" int rrtmg_lw_b200_kdata_put(int band, const char* name, const double*
 }
 
 extern "C" int rrtmg_lw_b200_ini(double cpdair, const double* kdata, long nkdata, int default_real_kind) {
-    std::lock_guard<std::mutex> lk(G.mu);
+    LW_ENTER();
     if (!kdata && nkdata == 0) {
         if (g_khave.empty()) return RRTMG_LW_ERR_ARG;
         for (char h : g_khave)
@@ -711,7 +730,7 @@ extern "C" int rrtmg_lw_b200_rrtmg_lw(int ncol, int ld, int nlay, int* icld, int
                                       const double* tauaer, double* uflx, double* dflx, double* hr, double* uflxc,
                                       double* dflxc, double* hrc, double* duflx_dt, double* duflxc_dt, int memspace,
                                       void* stream) {
-    std::lock_guard<std::mutex> lk(G.mu);
+    LW_ENTER();
     if (!G.inited) return RRTMG_LW_ERR_NOT_INIT;
     if (!icld || !check_common(ncol, ld, nlay)) return RRTMG_LW_ERR_ARG;
     if (*icld < 0 || *icld > 3) *icld = 2;  // rad.f90:470
@@ -771,7 +790,7 @@ extern "C" int rrtmg_lw_b200_rrtmg_lw_mcica(int ncol, int ld, int nlay, int icld
                                             const double* alpha, const double* tauaer, double* uflx, double* dflx,
                                             double* hr, double* uflxc, double* dflxc, double* hrc, double* duflx_dt,
                                             double* duflxc_dt, int memspace, void* stream) {
-    std::lock_guard<std::mutex> lk(G.mu);
+    LW_ENTER();
     if (!G.inited) return RRTMG_LW_ERR_NOT_INIT;
     if (!check_common(ncol, ld, nlay)) return RRTMG_LW_ERR_ARG;
     if (icld_overlap < 0 || icld_overlap > 5) return RRTMG_LW_ERR_FLAG;  // 'MCICA_SUBCOL_LW: INVALID ICLD'
@@ -828,7 +847,7 @@ extern "C" int rrtmg_lw_b200_mcica_subcol_lw(int iplon, int ncol, int ld, int nl
                                              double* clwpmcl, double* reicmcl, double* relqmcl, double* taucmcl,
                                              int memspace, void* stream) {
     (void)iplon;
-    std::lock_guard<std::mutex> lk(G.mu);
+    LW_ENTER();
     if (!G.inited) return RRTMG_LW_ERR_NOT_INIT;
     if (icld == 0) return RRTMG_LW_OK;  // mcica:257
     if (icld < 0 || icld > 5) return RRTMG_LW_ERR_FLAG;
@@ -908,7 +927,7 @@ extern "C" int rrtmg_lw_b200_get_alpha(int iplon, int ncol, int ld, int nlayers,
                                        const double* dz, const double* lat, int juldat, const double* cldfrac,
                                        double* alpha, int memspace, void* stream) {
     (void)iplon;
-    std::lock_guard<std::mutex> lk(G.mu);
+    LW_ENTER();
     if (!G.inited) return RRTMG_LW_ERR_NOT_INIT;
     if (!check_common(ncol, ld, nlayers) || !dz || !lat || !cldfrac || !alpha) return RRTMG_LW_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
@@ -937,20 +956,20 @@ extern "C" int rrtmg_lw_b200_get_alpha(int iplon, int ncol, int ld, int nlayers,
 }
 
 extern "C" int rrtmg_lw_b200_sync(int* col, int* lay) {
-    std::lock_guard<std::mutex> lk(G.mu);
+    LW_ENTER();
     if (cudaDeviceSynchronize() != cudaSuccess) return RRTMG_LW_ERR_CUDA;
     return decode_status(col, lay);
 }
 
 extern "C" int rrtmg_lw_b200_last_error(int* col, int* lay) {
-    std::lock_guard<std::mutex> lk(G.mu);
+    LW_ENTER();
     if (col) *col = (int)G.last_err_col;
     if (lay) *lay = G.last_err_lay;
     return RRTMG_LW_OK;
 }
 
 extern "C" int rrtmg_lw_b200_debug_capture(int col_plus1) {
-    std::lock_guard<std::mutex> lk(G.mu);
+    LW_ENTER();
     G.dbg = col_plus1 > 0;
     G.dbg_col = col_plus1 - 1;
     return RRTMG_LW_OK;
@@ -958,7 +977,7 @@ extern "C" int rrtmg_lw_b200_debug_capture(int col_plus1) {
 
 extern "C" int rrtmg_lw_b200_debug_stages(int icol, int* ints6, double* facs, double* taug, double* fracs, int* itr,
                                           double* scal, unsigned char* mask) {
-    std::lock_guard<std::mutex> lk(G.mu);
+    LW_ENTER();
     if (!G.inited || !G.dbg || G.dbg_nlay <= 0) return RRTMG_LW_ERR_NOT_INIT;
     if (icol != G.dbg_col) return RRTMG_LW_ERR_ARG;
     const int nlay = G.dbg_nlay;
@@ -985,7 +1004,7 @@ extern "C" int rrtmg_lw_b200_debug_stages(int icol, int* ints6, double* facs, do
 }
 
 extern "C" long rrtmg_lw_b200_get_table(const char* name, double* out, long cap) {
-    std::lock_guard<std::mutex> lk(G.mu);
+    LW_ENTER();
     if (!G.inited || !name) return 0;
     const std::string n(name);
     const double* src = nullptr;
@@ -1005,15 +1024,27 @@ extern "C" long rrtmg_lw_b200_get_table(const char* name, double* out, long cap)
     return cnt;
 }
 
+extern "C" int rrtmg_lw_b200_set_device(int device) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (device < -1 || device >= LW_MAX_DEVICES) return RRTMG_LW_ERR_ARG;
+    if (device >= 0) {
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess || device >= n) return RRTMG_LW_ERR_CUDA;
+        if (cudaSetDevice(device) != cudaSuccess) return RRTMG_LW_ERR_CUDA;
+    }
+    g_explicit = device;
+    return RRTMG_LW_OK;
+}
+
 extern "C" int rrtmg_lw_b200_set_chunk(int max_columns) {
-    std::lock_guard<std::mutex> lk(G.mu);
+    LW_ENTER();
     if (max_columns < 32) return RRTMG_LW_ERR_ARG;
     G.chunk = max_columns;
     return RRTMG_LW_OK;
 }
 
 extern "C" int rrtmg_lw_b200_set_option(const char* name, int value) {
-    std::lock_guard<std::mutex> lk(G.mu);
+    LW_ENTER();
     if (!name) return RRTMG_LW_ERR_ARG;
     if (std::strcmp(name, "band_kernel") == 0) {
         if (value != 2 && value != 4) return RRTMG_LW_ERR_ARG;
@@ -1074,34 +1105,34 @@ extern "C" int rrtmg_lw_b200_set_option(const char* name, int value) {
 }
 
 extern "C" long rrtmg_lw_b200_launch_count(int reset) {
-    std::lock_guard<std::mutex> lk(G.mu);
+    LW_ENTER();
     const long v = G.launches;
     if (reset) G.launches = 0;
     return v;
 }
 
 extern "C" int rrtmg_lw_b200_set_timing(int enable) {
-    std::lock_guard<std::mutex> lk(G.mu);
+    LW_ENTER();
     G.timing = enable != 0;
     return RRTMG_LW_OK;
 }
 
 extern "C" int rrtmg_lw_b200_last_timing(float* ms_band, float* ms_all) {
-    std::lock_guard<std::mutex> lk(G.mu);
+    LW_ENTER();
     if (ms_band) *ms_band = G.ms_band;
     if (ms_all) *ms_all = G.ms_all;
     return RRTMG_LW_OK;
 }
 
 extern "C" int rrtmg_lw_b200_last_band_timing(float* ms16) {
-    std::lock_guard<std::mutex> lk(G.mu);
+    LW_ENTER();
     if (!ms16) return RRTMG_LW_ERR_ARG;
     for (int k = 0; k < NBND; ++k) ms16[k] = G.ms_bands[k];
     return RRTMG_LW_OK;
 }
 
 extern "C" int rrtmg_lw_b200_last_stage_timing(float* ms, int cap) {
-    std::lock_guard<std::mutex> lk(G.mu);
+    LW_ENTER();
     if (!ms || cap < 0) return -1;
     for (int k = 0; k < G.nstage && k < cap; ++k) ms[k] = G.ms_bands[k];
     return G.nstage;
@@ -1122,7 +1153,7 @@ extern "C" const char* rrtmg_lw_b200_strerror(int code) {
 }
 
 extern "C" int rrtmg_lw_b200_fp64_peak(double* tflops) {
-    std::lock_guard<std::mutex> lk(G.mu);
+    LW_ENTER();
     if (!tflops) return RRTMG_LW_ERR_ARG;
     return measure_fp64_peak(tflops, 5) ? RRTMG_LW_ERR_CUDA : RRTMG_LW_OK;
 }
@@ -1132,7 +1163,7 @@ extern "C" int rrtmg_lw_b200_kiss_jump_selftest(void) { return kiss_jump_selftes
 extern "C" const char* rrtmg_lw_b200_version(void) { return "rrtmg_lw_b200 0.1 (sm_100a)"; }
 
 extern "C" void rrtmg_lw_b200_finalize(void) {
-    std::lock_guard<std::mutex> lk(G.mu);
+    LW_ENTER();
     free_scratch();
     free_mt_buffers();
     for (float* p : G.f32_allocs) cudaFree(p);
@@ -1151,5 +1182,8 @@ extern "C" void rrtmg_lw_b200_finalize(void) {
         for (int k = 0; k < 2; ++k) { cudaEventDestroy(G.e_in[k]); cudaEventDestroy(G.e_done[k]); cudaEventDestroy(G.e_out[k]); }
         G.s_in = G.s_out = nullptr;
     }
+    for (auto& q : G.side) { if (q) cudaStreamDestroy(q); q = nullptr; }
+    for (cudaEvent_t* e : {&G.e_fork, &G.e_colprep, &G.e_t, &G.e_cld}) { if (*e) cudaEventDestroy(*e); *e = nullptr; }
+    for (auto& e : G.e_side) { if (e) cudaEventDestroy(e); e = nullptr; }
     G.inited = false;
 }

@@ -39,10 +39,12 @@ static void launch_b(int cld, int idrv, const ColIn& in, const ColOut& out, cons
     const size_t smem = Ring<B>::BYTES + pad;
 #define LW_GO(CLD, IDRV)                                                                                  \
     do {                                                                                                  \
-        static bool attr_set = false;                                                                     \
-        if (!attr_set) {                                                                                  \
+        static unsigned attr_set = 0u; /* bit d = done on device d (the attribute is per device) */      \
+        int dev_ = 0;                                                                                     \
+        cudaGetDevice(&dev_);                                                                             \
+        if (!((attr_set >> dev_) & 1u)) {                                                                 \
             cudaFuncSetAttribute(band_kernel<B, CLD, IDRV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            attr_set = true;                                                                              \
+            attr_set |= 1u << dev_;                                                                       \
         }                                                                                                 \
         band_kernel<B, CLD, IDRV><<<blocks, threads, smem, st>>>(in, out, s, r);                          \
     } while (0)
@@ -61,10 +63,12 @@ static void launch_b32(int cld, int idrv, const ColInF& in, const ColOut& out, c
     const size_t smem = p32::Ring<B>::BYTES;
 #define LW_GO(CLD, IDRV)                                                                                  \
     do {                                                                                                  \
-        static bool attr_set = false;                                                                     \
-        if (!attr_set) {                                                                                  \
+        static unsigned attr_set = 0u; /* bit d = done on device d (the attribute is per device) */      \
+        int dev_ = 0;                                                                                     \
+        cudaGetDevice(&dev_);                                                                             \
+        if (!((attr_set >> dev_) & 1u)) {                                                                 \
             cudaFuncSetAttribute(p32::band_kernel<B, CLD, IDRV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            attr_set = true;                                                                              \
+            attr_set |= 1u << dev_;                                                                       \
         }                                                                                                 \
         p32::band_kernel<B, CLD, IDRV><<<blocks, threads, smem, st>>>(in, out, s, r);                     \
     } while (0)

@@ -501,9 +501,19 @@ __global__ void __launch_bounds__(128) mcica_finish_kernel(ColIn in, Scratch s, 
     if (i < r.ncol) finish_column(in, s, r, i);
 }
 
-static MtState* g_mt_state = nullptr;
-static unsigned* g_mt_buf = nullptr;
-static size_t g_mt_buf_words = 0;
+// generator state / word buffer and the KISS jump table live on the device that uses them (one set per device)
+constexpr int LWK_MAX_DEVICES = 16;
+static inline int cur_dev() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= LWK_MAX_DEVICES) d = 0;
+    return d;
+}
+static MtState* g_mt_state_d[LWK_MAX_DEVICES] = {};
+static unsigned* g_mt_buf_d[LWK_MAX_DEVICES] = {};
+static size_t g_mt_buf_words_d[LWK_MAX_DEVICES] = {};
+#define g_mt_state g_mt_state_d[cur_dev()]
+#define g_mt_buf g_mt_buf_d[cur_dev()]
+#define g_mt_buf_words g_mt_buf_words_d[cur_dev()]
 
 void free_mt_buffers() {
     if (g_mt_state) cudaFree(g_mt_state);
@@ -699,10 +709,16 @@ KissMap kiss_power(unsigned long long n) {
     }
     return res;
 }
+static inline int cur_dev_kj() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 16) d = 0;
+    return d;
+}
 struct KissJumpCache {
     KissJump* dev = nullptr;
     long key_seed = -1, key_draws = -1;
-} g_kj;
+} g_kj_d[16];
+#define g_kj g_kj_d[cur_dev_kj()]
 }  // namespace
 
 // Host-only check of the jump algebra against plain stepping: returns the number of mismatching

@@ -228,7 +228,10 @@ __device__ __forceinline__ void cloud_point(const SweepTab& tb, double st, bool 
     const double rec_6 = 0.166667;
     const double odg = big ? ldg1_if(tb.tau_tbl + itr, on && big) : st;
     const double odtot = odg + odc;
-    const bool tsmall = odtot < 0.06;
+    // the series only where the reference takes it: odtot < 0.06 with the gas optical depth itself (branch 1,
+    // rtrnmc.f90:361-376); once the gas part has gone through the lookup (odepth > 0.06, :397-425) the total is looked
+    // up too, whatever tau_tbl(itgas) + odcld comes to
+    const bool tsmall = !big && odtot < 0.06;
     const double tblind = div_fast(odtot, bpade + odtot);
     const int ittot = tbl_index(tblind);
     const double2 et = ldg2_if(tb.exptfn + ittot, on && !tsmall);

@@ -48,10 +48,12 @@ static void launch_g(int cld, int idrv, const ColIn& in, const ColOut& out, cons
 #define LW_GO(CLD, IDRV)                                                                                         \
     do {                                                                                                         \
         auto kern = rtrnmc_kernel<B0, NB, CLD, IDRV, sweep_minb(NGG, CLD, IDRV)>;                                \
-        static bool attr_set = false;                                                                            \
-        if (!attr_set) {                                                                                         \
+        static unsigned attr_set = 0u; /* bit d = done on device d (the attribute is per device) */             \
+        int dev_ = 0;                                                                                            \
+        cudaGetDevice(&dev_);                                                                                    \
+        if (!((attr_set >> dev_) & 1u)) {                                                                        \
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                  \
-            attr_set = true;                                                                                     \
+            attr_set |= 1u << dev_;                                                                              \
         }                                                                                                        \
         kern<<<blocks, threads, smem, st>>>(in, out, s, r, tb);                                                    \
     } while (0)

@@ -74,7 +74,11 @@ def _t_profile(p: torch.Tensor) -> torch.Tensor:
 
 
 def make_batch(ncol: int, nlay: int = 72, cloudy: bool = False, aerosol: bool = False, seed: int = 20261017,
-               device="cpu", stress_co2: bool = False, col_offset: int = 0) -> Batch:
+               device="cpu", stress_co2: bool = False, col_offset: int = 0, gas_spread: float = 0.0) -> Batch:
+    """Synthetic GCM batch of SURVEY 8(d).  ``stress_co2`` triples CO2 / doubles N2O (the ``adjfac`` pow paths);
+    ``gas_spread`` > 0 multiplies every absorber by an independent 10**(gas_spread * N(0,1)) per (layer, column)
+    (clipped to [1e-3, 50]), which drives the binary-species interpolation parameter through all three eta branches
+    of every band (taumol.f90:569-598) -- a coverage batch for the parity tests, not a physical atmosphere."""
     dev = torch.device(device)
     g = torch.Generator(device=dev)
     g.manual_seed(seed + 7919 * col_offset)
@@ -101,6 +105,15 @@ def make_batch(ncol: int, nlay: int = 72, cloudy: bool = False, aerosol: bool = 
     ones = torch.ones(nlay, ncol, dtype=f64, device=dev)
     co2 = (1.2e-3 if stress_co2 else 4.0e-4) * ones
     n2o = (6.0e-7 if stress_co2 else 3.2e-7) * ones
+    ch4 = 1.8e-6 * ones
+    if gas_spread > 0.0:
+        def spread(x, cap):
+            return (x * torch.pow(torch.tensor(10.0, dtype=f64, device=dev), gas_spread * N(nlay, ncol)).clamp(1.0e-3, 50.0)).clamp_max(cap)
+        h2o = spread(h2o, 0.04)
+        o3 = spread(o3, 1.0e-3)
+        co2 = spread(co2, 0.05)
+        n2o = spread(n2o, 1.0e-3)
+        ch4 = spread(ch4, 1.0e-3)
     emis = 0.96 + 0.04 * U(NBND, ncol)
     if aerosol:
         tauaer = 0.01 * U(NBND, nlay, ncol) * (play > 500.0).to(f64)[None]
@@ -108,7 +121,7 @@ def make_batch(ncol: int, nlay: int = 72, cloudy: bool = False, aerosol: bool = 
         tauaer = torch.zeros(NBND, nlay, ncol, dtype=f64, device=dev)
 
     b = Batch(ncol=ncol, nlay=nlay, play=play.contiguous(), plev=plev.contiguous(), tlay=tlay, tlev=tlev, tsfc=tsfc,
-              h2ovmr=h2o, o3vmr=o3, co2vmr=co2, ch4vmr=1.8e-6 * ones, n2ovmr=n2o, o2vmr=0.209 * ones,
+              h2ovmr=h2o, o3vmr=o3, co2vmr=co2, ch4vmr=ch4, n2ovmr=n2o, o2vmr=0.209 * ones,
               cfc11vmr=2.3e-10 * ones, cfc12vmr=5.2e-10 * ones, cfc22vmr=2.3e-10 * ones, ccl4vmr=8.0e-11 * ones,
               emis=emis, tauaer=tauaer.contiguous())
     if cloudy:
@@ -137,7 +150,7 @@ def make_batch(ncol: int, nlay: int = 72, cloudy: bool = False, aerosol: bool = 
         b.lat = -90.0 + 180.0 * U(ncol)
         # hydrostatic thickness (m): dz = R_d T / g * ln(p_bot / p_top)
         b.dz = 287.05 * tlay / 9.8066 * torch.log(plev[:-1] / plev[1:])
-    b.meta = dict(seed=seed, cloudy=cloudy, aerosol=aerosol, stress_co2=stress_co2)
+    b.meta = dict(seed=seed, cloudy=cloudy, aerosol=aerosol, stress_co2=stress_co2, gas_spread=gas_spread)
     return b
 
 

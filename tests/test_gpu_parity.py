@@ -456,3 +456,78 @@ def test_empty_and_invalid_calls_are_refused(gpu):
         with pytest.raises(api.RrtmgLwError) as e:
             api.rrtmg_lw_mcica(ncol, nlay, 2, 0, 1, 0, *at, 2, 3, 1, *cl, None, c(b.tauaer), *outs, None, None)
         assert e.value.code == 7
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# integer bit-exactness on many columns and branch coverage of the batches the CUDA path is compared on
+COVERAGE_BATCHES = {
+    "cloudy72": dict(ncol=256, nlay=72, cloudy=True, aerosol=True),
+    "cloudy137": dict(ncol=96, nlay=137, cloudy=True),
+    "stress72": dict(ncol=256, nlay=72, cloudy=True, stress_co2=True),
+    "spread72": dict(ncol=256, nlay=72, cloudy=True, gas_spread=1.2),
+}
+
+
+@pytest.mark.parametrize("name", sorted(COVERAGE_BATCHES))
+def test_stage_dumps_bit_exact_on_32_columns(gpu, oracle, name):
+    """jp / jt / jt1 / indself / indfor / indminor, laytrop, the McICA mask and the rtrnmc table indices itr / itgas /
+    ittot (rtrnmc.f90:386, 404, 412, 435) of cloudy layers, bit for bit, on 32 columns spread over a cloudy 72-layer,
+    a cloudy 137-layer, a stress-gas (pow paths) and a gas-spread (all eta branches) batch; Planck fractions equal,
+    gas optical depths to libm rounding."""
+    kw = dict(COVERAGE_BATCHES[name])
+    b = synth.make_batch(**kw)
+    mc = oracle.mcica_subcol_lw(b, 2, permuteseed=1, irng=0)
+    cols = np.unique(np.linspace(0, b.ncol - 1, 32).astype(int))
+    assert len(cols) == 32
+    cloudy_layers_seen = 0
+    try:
+        for col in cols:
+            col = int(col)
+            gpu.debug_capture(col)
+            driver.run_fused(b, icld=2, idrv=0, device="cuda:0")
+            gpu.sync()
+            d = gpu.debug_stages(col, b.nlay, want_mask=True)
+            s = oracle.column_stages(b, col, icld=2, inflglw=2, iceflglw=3, liqflglw=1, mc=mc)
+            assert s["rc"] == 0
+            assert np.array_equal(s["ints6"], d["ints6"]), (name, col, "setcoef integers")
+            assert s["laytrop"] == d["laytrop"], (name, col)
+            mask_ref = (mc["cldfmcl"][:, col, :] == 1.0).T.astype(np.uint8)       # (140, nlay)
+            assert np.array_equal(mask_ref, d["mask"]), (name, col, "McICA mask")
+            if not np.array_equal(s["itr"], d["itr"]):
+                w = np.argwhere(s["itr"] != d["itr"])
+                g_, l_, k_ = (int(x) for x in w[0])
+                raise AssertionError((name, col, "itr / itgas / ittot", len(w), "first at (g, layer, which)", (g_, l_, k_),
+                                      "oracle", s["itr"][g_, l_].tolist(), "gpu", d["itr"][g_, l_].tolist(),
+                                      "cloud bit", int(mask_ref[g_, l_]), "layer cloudy", int(mask_ref[:, l_].max())))
+            assert np.array_equal(s["fracs"], d["fracs"]), (name, col, "Planck fractions")
+            rel = np.abs(s["taug"] - d["taug"]) / np.maximum(np.abs(s["taug"]), 1e-300)
+            assert rel.max() < 1e-12, (name, col, rel.max())   # libm log / pow rounding only
+            cloudy_layers_seen += int((mask_ref.sum(0) > 0).sum())
+            assert (s["itr"][:, :, 1] >= 0).sum() > 0 or mask_ref.sum() == 0
+    finally:
+        gpu.debug_capture(None)
+    assert cloudy_layers_seen >= 100   # ittot really was compared in cloudy layers
+
+
+def test_parity_batches_cover_every_branch(gpu, oracle):
+    """The batches of this suite, run through the oracle with its branch counters armed and through the CUDA path
+    (fluxes within 1e-6 / heating rates within 1e-6), exercise every data-dependent branch of the reference >= 100
+    times: the three eta branches of both (p, T) corners of every binary-species band (taumol.f90:569-598), both
+    atmosphere halves of every band, all ten adjfac sites (:550, 736, 1355, 1483, 1639, 1721, 1768, 1879, 2036, 2497),
+    the three cloudy-layer sub-branches (rtrnmc.f90:358-425) and both clear-layer branches (:429-440)."""
+    oracle.branch_counts(reset=True)
+    for name in sorted(COVERAGE_BATCHES):
+        kw = dict(COVERAGE_BATCHES[name])
+        b = synth.make_batch(**kw)
+        mc = oracle.mcica_subcol_lw(b, 2, permuteseed=1, irng=0)
+        ref = oracle.rrtmg_lw(b, icld=2, idrv=1, inflglw=2, iceflglw=3, liqflglw=1, mc=mc, nthreads=8)
+        assert ref["rc"] == 0
+        got = driver.run_fused(b, icld=2, idrv=1, device="cuda:0")
+        gpu.sync()
+        _check(got, ref, 1, what="coverage batch " + name)
+    c = oracle.branch_counts(reset=True)
+    for band in oracle.BINARY_LOWER_BANDS:
+        assert (c["eta"][band - 1] >= 100).all(), ("eta branches of band", band, c["eta"][band - 1].tolist())
+    assert (c["half"] >= 100).all(), c["half"].tolist()
+    assert (c["adjfac"] >= 100).all(), dict(zip(oracle.BRANCH_ADJFAC_SITES, c["adjfac"].tolist()))
+    assert (c["cloudy"] >= 100).all() and (c["clear"] >= 100).all(), (c["cloudy"], c["clear"])

@@ -208,3 +208,66 @@ def test_netcdf_ingest_round_trip(tmp_path):
     # selfrefo(Tself, ig): count (Tself, 16, 1, 1)
     assert np.array_equal(v["H20SelfAbsorptionCoefficients"][:][0, 0].T, arrs[(1, "selfrefo")])
     f.close()
+
+
+def test_kdata_layout_matches_the_reference_modules():
+    """include/rrtmg_lw_kdata_layout.h (shared by the product's and the oracle's 16 -> 140 g-point reduction) against
+    the reference's own declarations: the unreduced arrays of modules/rrlw_kgNN.f90 (the ones dimensioned with noN)
+    are exactly the rows of the layout, with the same leading extent (product of all dims other than the g-point
+    axis) and g-point position (last, except the (g, eta) Planck-fraction arrays where it is first); the `weighted`
+    flag is set exactly for the arrays whose accumulation in rrtmg_lw_init.f90's cmbgbN multiplies by rwgt
+    (absorption coefficients), not for the ones it just sums (Planck fractions)."""
+    import os
+    import re
+    ref = "/root/reference"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.isdir(os.path.join(ref, "modules")):
+        pytest.skip("reference tree not mounted")
+    hdr = open(os.path.join(root, "include", "rrtmg_lw_kdata_layout.h")).read()
+    rows = re.findall(r'\{\s*(\d+)\s*,\s*"(\w+)"\s*,\s*(\d+)\s*,\s*(\d)\s*,\s*(\d)\s*\}', hdr)
+    layout = {(int(b), n): (int(lead), int(gfirst), int(w)) for b, n, lead, gfirst, w in rows}
+    assert len(layout) == len(rows) == 115
+    init = open(os.path.join(ref, "src", "rrtmg_lw_init.f90")).read().lower()
+    init = re.sub(r"&\s*\n\s*&?", " ", init)          # join continuation lines
+    seen = 0
+    for band in range(1, 17):
+        mod = open(os.path.join(ref, "modules", "rrlw_kg%02d.f90" % band)).read().lower()
+        mod = re.sub(r"!.*", "", mod)
+        body = re.search(r"subroutine cmbgb%d\b(.*?)end subroutine cmbgb%d\b" % (band, band), init, re.S).group(1)
+        body = re.sub(r"!.*", "", body)
+        declared = {}
+        for name, dims in re.findall(r"(\w+)\s*\(([^()]*\bno%d\b[^()]*)\)" % band, mod):
+            if name != "dimension":
+                declared[name] = [d.strip() for d in dims.split(",")]
+        # the other spelling: real(kind=rb), dimension(no6) :: fracrefao, cfc11adjo, cfc12o
+        for dims, names in re.findall(r"dimension\s*\(([^()]*\bno%d\b[^()]*)\)[ \t]*::[ \t]*([\w \t,]+)" % band, mod):
+            for name in names.split(","):
+                if name.strip():
+                    declared[name.strip()] = [d.strip() for d in dims.split(",")]
+        in_layout = {n for (b, n) in layout if b == band}
+        assert set(declared) == in_layout, (band, sorted(set(declared) ^ in_layout))
+        for name, dims in declared.items():
+            ext, gpos = [], None
+            for k, d in enumerate(dims):
+                if d == "no%d" % band:
+                    ext.append(16)
+                    gpos = k
+                elif ":" in d:
+                    lo, hi = d.split(":")
+                    ext.append(int(hi) - int(lo) + 1)
+                else:
+                    ext.append(int(d))
+            other = 1
+            for k, e in enumerate(ext):
+                if k != gpos:
+                    other *= e
+            lead, gfirst, weighted = layout[(band, name)]
+            assert lead == other, (band, name, lead, ext)
+            if len(ext) > 1:   # a one-dimensional (g only) array is the same blob either way
+                assert gfirst == (1 if (gpos == 0) else 0), (band, name, dims, gfirst)
+            stmts = [st for st in body.split("\n") if re.search(r"\b%s\s*\(" % re.escape(name), st)]
+            assert stmts, (band, name, "never read in cmbgb%d" % band)
+            uses_rwgt = any("rwgt" in st for st in stmts)
+            assert weighted == (1 if uses_rwgt else 0), (band, name, "weighted flag", weighted, stmts[:2])
+            seen += 1
+    assert seen == 115
