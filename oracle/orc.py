@@ -60,6 +60,12 @@ def _np(t):
     return np.ascontiguousarray(t, dtype=np.float64)
 
 
+def set_band_range(istart=1, iend=16):
+    """Band range of the following runs (per-band output blocks of the column-mode program)."""
+    rc = lib().orc_set_band_range(int(istart), int(iend))
+    assert rc == 0, rc
+
+
 def rrtmg_lw(b, icld=0, idrv=0, inflglw=0, iceflglw=0, liqflglw=0, mc=None, nthreads=1):
     """Run the oracle on a synth.Batch.  mc = dict(cldfmcl, taucmcl, ciwpmcl, clwpmcl, reicmcl, relqmcl)
     with the (nlay, ncol, 140) / (nlay, ncol) layouts.  Returns dict of outputs + rc + icld."""

@@ -83,8 +83,11 @@ static void inatm(const In& in, int iplon, int iaer, Column& c) {
 }
 
 // body of "do iplon" in rrtmg_lw, src/rrtmg_lw_rad.f90:486-571
+// band range of the following runs (the column-mode program's istart / iend / iout of a per-band output block,
+// src/rrtmg_lw.1col.f90:463-467): set by orc_set_band_range, 1..16 by default
+static int g_istart = 1, g_iend = 16;
 static int column(const In& in, int iplon, Column& c, bool dump) {
-    const int istart = 1, iend = 16, iout = 0, iaer = 10;
+    const int istart = g_istart, iend = g_iend, iout = (g_istart == 1 && g_iend == 16) ? 0 : g_istart, iaer = 10;
     inatm(in, iplon, iaer, c);
     int rc = cldprmc(c);
     if (rc != ORC_OK) return rc;
@@ -98,6 +101,12 @@ static int column(const In& in, int iplon, Column& c, bool dump) {
 }  // namespace orc
 
 using namespace orc;
+
+extern "C" int orc_set_band_range(int istart, int iend) {
+    if (istart < 1 || iend > 16 || istart > iend) return ORC_ERR_FLAG;
+    orc::g_istart = istart; orc::g_iend = iend;
+    return ORC_OK;
+}
 
 extern "C" int orc_ini(double cpdair, const double* st, const double* kdata, int drk) {
     if (drk != 4 && drk != 8) return ORC_ERR_FLAG;

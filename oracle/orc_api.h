@@ -15,6 +15,10 @@ extern "C" {
 
 int orc_ini(double cpdair, const double* static_tables, const double* kdata, int default_real_kind);
 
+/* band range istart..iend of the following orc_rrtmg_lw / orc_column_stages runs (1..16 by default): only those bands
+ * enter the flux sums, and band 16 alone takes the totplk16 Planck variant (src/rrtmg_lw_setcoef.f90:233-251) */
+int orc_set_band_range(int istart, int iend);
+
 int orc_rrtmg_lw(int ncol, int ld, int nlay, int* icld, int idrv, const double* play, const double* plev,
                  const double* tlay, const double* tlev, const double* tsfc, const double* h2ovmr,
                  const double* o3vmr, const double* co2vmr, const double* ch4vmr, const double* n2ovmr,

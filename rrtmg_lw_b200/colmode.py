@@ -18,8 +18,9 @@ column-mode program (they come from driving the GCM entry, not from this file):
   * the GCM ``inatm`` derives the dry-air column from the level pressures
     (``src/rrtmg_lw_rad.f90:807-809``) where column mode takes it from the file's broadening-gas
     column (:1013-1021), and sets the CO amount to zero (``rad:816``);
-  * per-band output (``iout = 99`` / ``1..16``) needs the band fluxes, which the GCM entry does not
-    return: only the broadband block (10-3250 cm-1) is produced;
+  * per-band output (``iout = 99`` / ``1..16``): every block is its own run of the library over bands
+    ``istart..iend`` (``set_option("band_lo" / "band_hi")``; band 16 alone takes the ``totplk16`` Planck variant of
+    ``src/rrtmg_lw_setcoef.f90:233-251``), :func:`run_blocks`;
   * ``iatm = 1`` (``rrtatm`` layering, N4) and ``imca = 0`` with clouds (``cldprop`` + ``rtrnmr``, N2)
     are refused with ``NotImplementedError``.
 """
@@ -329,6 +330,14 @@ class GpuBackend:
         from . import api
         return float(api.get_table("heatfac")[0])
 
+    def band_range(self, istart=1, iend=16):
+        """Bands istart..iend of the following runs (the program's istart / iend of a per-band output block,
+        src/rrtmg_lw.1col.f90:463-467); band 16 alone takes its own Planck table (setcoef.f90:233-251)."""
+        from . import api
+        api.set_option("band_lo", 1)
+        api.set_option("band_hi", int(iend))
+        api.set_option("band_lo", int(istart))
+
     def clear(self, b, idrv):
         from . import driver
         return self._np(driver.run_clear_or_strict(b, icld=0, idrv=idrv, device=self.device))
@@ -346,10 +355,52 @@ class GpuBackend:
                                          iceflglw=flags[1], liqflglw=flags[2], alpha=alpha, device=self.device))
 
 
+# band limits in cm-1, rrlw_wvn wavenum1 / wavenum2 (src/rrtmg_lw_init.f90:215-220)
+WAVENUM1 = (10., 350., 500., 630., 700., 820., 980., 1080., 1180., 1390., 1480., 1800., 2080., 2250., 2380., 2600.)
+WAVENUM2 = (350., 500., 630., 700., 820., 980., 1080., 1180., 1390., 1480., 1800., 2080., 2250., 2380., 2600., 3250.)
+
+
+def output_blocks(iout: int):
+    """(istart, iend, wn1, wn2) of every OUTPUT_RRTM block the program writes for a given ``iout``
+    (doc/rrtmg_lw_instructions.txt; src/rrtmg_lw.1col.f90:453-467, 704-711): 0 = the broadband block, n in 1..16 =
+    band n alone, 99 = the broadband block followed by the 16 bands, < 0 = nothing."""
+    if iout < 0:
+        return []
+    blocks = []
+    if iout == 0 or iout == 99:
+        blocks.append((1, 16, WAVENUM1[0], WAVENUM2[15]))
+    if 1 <= iout <= 16:
+        blocks.append((iout, iout, WAVENUM1[iout - 1], WAVENUM2[iout - 1]))
+    if iout == 99:
+        blocks += [(b, b, WAVENUM1[b - 1], WAVENUM2[b - 1]) for b in range(1, 17)]
+    return blocks
+
+
+def run_blocks(c: Case, backend, nmca: int | None = None, irng: int = 1):
+    """Every output block of the case (17 for ``iout = 99``): list of :func:`run_case` results with ``wn1`` / ``wn2`` /
+    ``istart`` / ``iend`` added.  Each block is its own run over bands istart..iend, like the program's
+    ``goto 1000`` loop, McICA sampling included."""
+    out = []
+    try:
+        for istart, iend, wn1, wn2 in output_blocks(c.iout):
+            backend.band_range(istart, iend)
+            r = run_case(c, backend, nmca=nmca, irng=irng)
+            r.update(wn1=wn1, wn2=wn2, istart=istart, iend=iend)
+            out.append(r)
+    finally:
+        backend.band_range(1, 16)
+    return out
+
+
+def format_blocks(blocks, iplon: int = 1) -> str:
+    return "".join(format_output(r, iplon=iplon, wn1=r["wn1"], wn2=r["wn2"]) for r in blocks)
+
+
 def run_case(c: Case, backend, nmca: int | None = None, irng: int = 1):
-    """The main program's loop for one atmosphere (1col:440-705): returns a dict with the level
-    arrays ``uflx, dflx, fnet`` (nlayers+1) and ``htr`` (nlayers+1, top entry 0) of the broadband block,
-    McICA-averaged over ``nmca`` samples (200 in the reference) and ``dtbound``-adjusted when idrv = 1."""
+    """The main program's loop for one atmosphere and ONE band range (1col:440-705; the backend's current
+    ``band_range``, all 16 bands by default): returns a dict with the level arrays ``uflx, dflx, fnet`` (nlayers+1)
+    and ``htr`` (nlayers+1, top entry 0), McICA-averaged over ``nmca`` samples (200 in the reference) and
+    ``dtbound``-adjusted when idrv = 1."""
     if c.imca == 0 and c.icld >= 1:
         raise NotImplementedError("imca = 0 with clouds is the cldprop + rtrnmr path (SURVEY 8(f) N2)")
     b = case_to_batch(c)

@@ -271,6 +271,7 @@ int run_device(Mode mode, int ncol, int nlay, int icld, int idrv, int inflag, in
     int rc = ensure_scratch(ncol < chunk ? ncol : chunk, nlay, need);
     if (rc) return rc;
     const int b_lo = G.band_lo, b_hi = G.band_hi;  // band range of the run (1..16 unless the band_lo / band_hi options say otherwise)
+    if (b_lo > b_hi || (!two_phase && (b_lo != 1 || b_hi != NBND))) return RRTMG_LW_ERR_ARG;  // band ranges: two-phase path only
     if (G.timing) {
         for (auto& e : G.ev)
             if (!e) CK(cudaEventCreate(&e));
@@ -287,6 +288,7 @@ int run_device(Mode mode, int ncol, int nlay, int icld, int idrv, int inflag, in
         r.icld = icld; r.irng = irng; r.permuteseed = permuteseed;
         r.fp32 = fp32 ? 1 : 0;
         r.fld_block = 1;
+        r.istart = b_lo;
         Scratch S = G.S;
         S.err_base = G.err_col0;
         S.dbg_col = (G.dbg && G.dbg_col >= c0 && G.dbg_col < c0 + r.ncol) ? (int)(G.dbg_col - c0) : -1;

@@ -88,8 +88,8 @@ struct Scratch {
 struct SweepTab {
     const double2* exptfn;        // [itr] = {exp_tbl, tfn_tbl}
     const double* tau_tbl;
-    const double* totplnk;        // (181,16)
-    const double* totplnkderiv;   // (181,16)
+    const double* totplnk;        // (181,17): column 16 (0-based) = totplk16
+    const double* totplnkderiv;   // (181,17)
     const double* fracrefa[NBND]; // padded rows (lw_tables.h NGPAD)
     const double* fracrefb[NBND];
     double delwave[NBND];
@@ -104,6 +104,7 @@ struct RunCfg {
     int inflag, iceflag, liqflag;
     int icld, irng, permuteseed;
     int fp32;        // 1 = the prep kernel writes float fields (Scratch::fldf) for the FP32-mode band kernels
+    int istart;      // first band of the run (two-phase path; 16 = band 16 alone, which then takes its own Planck table)
     int fld_block;   // layout of Scratch::fld: 0 = [field][layer][column], 1 = blocks of 128 columns,
                      // [column / 128][layer][field][column % 128] (column-lane kernel: a CTA's fields of one layer are
                      // one contiguous run, addressed as one base + compile-time offsets); pitch is a multiple of 128

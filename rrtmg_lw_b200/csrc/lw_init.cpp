@@ -95,8 +95,12 @@ void build_host_tables(double cpdair, const double* st, const double* kdata, int
     c.abscld1 = *S.abscld1;
     c.absliq0 = *S.absliq0;
 
+    // (181, 16) in the reference's order, followed by a 17th column: totplk16 / totplk16deriv, band 16 integrated over
+    // 2600-3250 cm-1 only, which setcoef uses when the run is band 16 alone (istart = 16, setcoef.f90:233-251)
     H.totplnk.assign(S.totplnk, S.totplnk + 181 * 16);
+    H.totplnk.insert(H.totplnk.end(), S.totplk16, S.totplk16 + 181);
     H.totplnkderiv.assign(S.totplnkderiv, S.totplnkderiv + 181 * 16);
+    H.totplnkderiv.insert(H.totplnkderiv.end(), S.totplk16deriv, S.totplk16deriv + 181);
     H.absice2.assign(S.absice2, S.absice2 + 43 * 16);
     H.absice3.assign(S.absice3, S.absice3 + 46 * 16);
     H.absliq1.assign(S.absliq1, S.absliq1 + 58 * 16);

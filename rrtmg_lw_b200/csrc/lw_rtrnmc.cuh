@@ -62,9 +62,18 @@ struct SweepRing {
 };
 
 // Planck function of band B at the temperature whose table position is (it, frac), setcoef.f90:173-226
+// own16: the run is band 16 alone (istart = 16): setcoef then integrates its Planck function over 2600-3250 cm-1 only
+// (totplk16, column 17 of the table) instead of 2600 cm-1 to infinity (setcoef.f90:233-251).  level0: planklev(0, 16) of
+// that variant takes the VALUE from totplk16 and the SLOPE from totplnk(:,16) (setcoef.f90:244-246).
 template <int B>
-__device__ __forceinline__ double planck_at(const double* totplnk, int it, double frac) {
+__device__ __forceinline__ double planck_at(const double* totplnk, int it, double frac, bool own16 = false, bool level0 = false) {
     const double* tp = totplnk + 181 * (B - 1);
+    if (B == 16 && own16) {
+        const double* t16 = totplnk + 181 * 16;
+        const double a = ldg(t16 + it - 1);
+        const double dbdt = level0 ? ldg(tp + it) - ldg(tp + it - 1) : ldg(t16 + it) - a;
+        return fmadd(frac, dbdt, a);
+    }
     const double a = ldg(tp + it - 1), b = ldg(tp + it);
     const double dbdt = b - a;
     return fmadd(frac, dbdt, a);
@@ -262,6 +271,8 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
     const bool dbg = live && (s.dbg_col == i);
     const int laytrop = s.laytrop[i];
     const int ctop = (CLD != CLD_NONE) ? s.ctop[i] : 0;
+    const bool own16 = (B0 + NB - 1 == 16) && r.istart == 16;
+    (void)own16;
     (void)out;
 
     // blocks of 128 columns, [column / 128][layer][...][column % 128]
@@ -367,8 +378,8 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
             constexpr int B = B0 + K;
             constexpr int NG = NGC[B - 1];
             constexpr int GO = GR::goff(K);
-            const double blay = planck_at<B>(tb.totplnk, it_lay, fr_lay);
-            const double dplankdn = planck_at<B>(tb.totplnk, it_lev, fr_lev) - blay;  // planklev(lev-1) - planklay(lev)
+            const double blay = planck_at<B>(tb.totplnk, it_lay, fr_lay, own16);
+            const double dplankdn = planck_at<B>(tb.totplnk, it_lev, fr_lev, own16, lev == 1) - blay;  // planklev(lev-1) - planklay(lev)
             double sm = 0.;
             if constexpr (pf_slot(B) >= 0) sm = st_d(stage, RG::S_PF + pf_slot(B) - GR::PF0);
             PlFrac<B> pf;
@@ -515,12 +526,12 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
             constexpr int GO = GR::goff(K);
             // surface emission, setcoef.f90:211-219 / rtrnmc.f90:465-469
             const double semiss = in.emis[ci + in.ld * (B - 1)];
-            const double* tp = tb.totplnk + 181 * (B - 1);
+            const double* tp = tb.totplnk + 181 * ((B == 16 && own16) ? 16 : B - 1);
             const double pa = ldg(tp + it_b - 1), pb = ldg(tp + it_b);
             const double plankbnd = semiss * (pa + fr_b * (pb - pa));
             double dplankbnd_dt = 0.;
             if constexpr (IDRV == 1) {
-                const double* td = tb.totplnkderiv + 181 * (B - 1);
+                const double* td = tb.totplnkderiv + 181 * ((B == 16 && own16) ? 16 : B - 1);
                 const double da = ldg(td + it_b - 1), db = ldg(td + it_b);
                 dplankbnd_dt = semiss * (da + fr_b * (db - da));
             }
@@ -591,8 +602,8 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
             constexpr int B = B0 + K;
             constexpr int NG = NGC[B - 1];
             constexpr int GO = GR::goff(K);
-            const double blay = planck_at<B>(tb.totplnk, it_lay, fr_lay);
-            const double dplankup = planck_at<B>(tb.totplnk, it_lev, fr_lev) - blay;  // planklev(lev) - planklay(lev)
+            const double blay = planck_at<B>(tb.totplnk, it_lay, fr_lay, own16);
+            const double dplankup = planck_at<B>(tb.totplnk, it_lev, fr_lev, own16) - blay;  // planklev(lev) - planklay(lev)
             double sm = 0.;
             if constexpr (pf_slot(B) >= 0) sm = st_d(stage, RG::S_PF + pf_slot(B) - GR::PF0);
             PlFrac<B> pf;

@@ -10,6 +10,9 @@ class OracleBackend:
     def heatfac(self):
         return float(self.orc.get_table("heatfac")[0])
 
+    def band_range(self, istart=1, iend=16):
+        self.orc.set_band_range(istart, iend)
+
     def clear(self, b, idrv):
         o = self.orc.rrtmg_lw(b, icld=0, idrv=idrv)
         assert o["rc"] == 0

@@ -203,3 +203,37 @@ def test_mcica_samples_are_seeded_like_the_column_mode_generator(suite):
     if os.path.exists(ref_src):
         src = open(ref_src).read()
         assert "permuteseed = ims*nsubclw" in src
+
+
+def test_iout_99_yields_the_17_blocks_of_the_goldens(suite, oracle):
+    """iout = 99: broadband block + one block per band with the band limits of rrlw_wvn (init.f90:215-220), in the
+    order and with the 'Wavenumbers' headers of the shipped 17-block outputs; the band blocks add up to the broadband
+    block (fluxes are sums over bands) except for band 16, which alone takes the totplk16 Planck table
+    (setcoef.f90:233-251) -- its block differs from its share of the broadband sum."""
+    assert [b[:2] for b in colmode.output_blocks(99)] == [(1, 16)] + [(k, k) for k in range(1, 17)]
+    assert colmode.output_blocks(0) == [(1, 16, 10.0, 3250.0)] and colmode.output_blocks(-1) == []
+    assert colmode.output_blocks(7) == [(7, 7, 980.0, 1080.0)]
+    be = OracleBackend(oracle)
+    name = "MLS-clr-idrv1"
+    c = colmode.Case(**suite[name]["case"])
+    assert c.iout == 99
+    blocks = colmode.run_blocks(c, be)
+    assert len(blocks) == 17
+    if os.path.isdir(REF_EX):
+        gold = colmode.parse_output_rrtm(open(os.path.join(REF_EX, "output_rrtm_" + name)).read())
+        assert len(gold) == 17
+        assert [(g["wn1"], g["wn2"]) for g in gold] == [(b["wn1"], b["wn2"]) for b in blocks]
+        mine = colmode.parse_output_rrtm(colmode.format_blocks(blocks))
+        assert [(g["wn1"], g["wn2"], len(g["level"])) for g in gold] == [(g["wn1"], g["wn2"], len(g["level"])) for g in mine]
+        # data-independent golden numbers, per band: surface upward flux (emissivity 1, Planck tables, dtbound-adjusted);
+        # block 17 pins the totplk16 variant (its golden differs from the 2600 cm-1 -> infinity integral)
+        for k, (g, b) in enumerate(zip(gold, blocks)):
+            assert abs(b["uflx"][0] - g["uflx"][0]) <= 1.5e-3, (k, b["uflx"][0], g["uflx"][0])
+    total = sum(b["uflx"] for b in blocks[1:16])
+    be.band_range(16, 16)
+    own16 = colmode.run_case(c, be)
+    be.band_range(1, 16)
+    np.testing.assert_array_equal(own16["uflx"], blocks[16]["uflx"])
+    # bands 1..15 are additive; band 16's share of the broadband block is the 2600 -> infinity integral, larger than block 17
+    share16 = blocks[0]["uflx"] - total
+    assert (share16 > blocks[16]["uflx"] - 1e-12).all() and share16[0] > blocks[16]["uflx"][0]

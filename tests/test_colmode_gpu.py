@@ -52,3 +52,22 @@ def test_unsupported_cases_are_refused(gpu):
     c = colmode.Case(**SUITE["MLS-cld5-imca0-icld2"]["case"])
     with pytest.raises(NotImplementedError):
         colmode.run_case(c, colmode.GpuBackend(None))
+
+
+@pytest.mark.parametrize("name", ["MLS-clr", "MLS-clr-aer12", "MLS-clr-idrv1"])
+def test_per_band_blocks_match_oracle(gpu, oracle, name):
+    """iout = 99: all 17 output blocks (broadband + one run per band, band 16 with its own Planck table) through the
+    library's band-range option equal the oracle's per-band runs to 1e-6."""
+    c = colmode.Case(**SUITE[name]["case"])
+    assert c.iout == 99
+    ref = colmode.run_blocks(c, OracleBackend(oracle))
+    got = colmode.run_blocks(c, colmode.GpuBackend("cuda:0"))
+    gpu.sync()
+    assert len(ref) == len(got) == 17
+    for k, (r, g) in enumerate(zip(ref, got)):
+        assert (r["istart"], r["iend"]) == (g["istart"], g["iend"])
+        for key in ("uflx", "dflx", "fnet", "htr"):
+            err = float(np.abs(g[key] - r[key]).max())
+            assert err <= 1e-6, (name, "block", k, key, err)
+    text = colmode.format_blocks(got)
+    assert text.count("Wavenumbers:") == 17
