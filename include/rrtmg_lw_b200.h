@@ -10,6 +10,7 @@
  *   mcica_subcol_lw(iplon,ncol,...) src/mcica_subcol_gen_lw.f90:183   rrtmg_lw_b200_mcica_subcol_lw
  *   get_alpha(iplon,ncol,...)       src/mcica_subcol_gen_lw.f90:68    rrtmg_lw_b200_get_alpha
  *   [mcica_subcol_lw -> rrtmg_lw fused, sub-columns never materialised] rrtmg_lw_b200_rrtmg_lw_mcica
+ *   rrtmg_lw(ncol,nlay,icld,...)    src/rrtmg_lw_rad.nomcica.f90:99   rrtmg_lw_b200_rrtmg_lw_nomcica
  *
  * Conventions
  *   - Every array keeps the reference's Fortran layout, passed as a plain pointer:
@@ -81,6 +82,24 @@ int rrtmg_lw_b200_rrtmg_lw(int ncol, int ld, int nlay, int* icld, int idrv,
                            const double* tauaer, double* uflx, double* dflx, double* hr, double* uflxc,
                            double* dflxc, double* hrc, double* duflx_dt, double* duflxc_dt,
                            int memspace, void* stream);
+
+/* Replaces rrtmg_lw of the NON-McICA build (src/rrtmg_lw_rad.nomcica.f90:99-588), argument for argument:
+ * grid-mean cloud arrays cldfr, cicewp, cliqwp, reice, reliq (ncol,nlay) and taucld (16,ncol,nlay);
+ * cldprop (src/rrtmg_lw_cldprop.f90) then rtrn (random overlap, *icld == 1, src/rrtmg_lw_rtrn.f90) or
+ * rtrnmr (maximum-random overlap, *icld == 0, 2, 3, src/rrtmg_lw_rtrnmr.f90).  icld is inout (clamped to 2 when
+ * outside [0,3], :458).  The cloud arrays are read only when *icld >= 1.  Radius errors of cldprop
+ * (:212,217,228,244,272) come back as RRTMG_LW_ERR_ICE_RADIUS / RRTMG_LW_ERR_LIQ_RADIUS. */
+int rrtmg_lw_b200_rrtmg_lw_nomcica(int ncol, int ld, int nlay, int* icld, int idrv,
+                                   const double* play, const double* plev, const double* tlay, const double* tlev,
+                                   const double* tsfc, const double* h2ovmr, const double* o3vmr,
+                                   const double* co2vmr, const double* ch4vmr, const double* n2ovmr,
+                                   const double* o2vmr, const double* cfc11vmr, const double* cfc12vmr,
+                                   const double* cfc22vmr, const double* ccl4vmr, const double* emis, int inflglw,
+                                   int iceflglw, int liqflglw, const double* cldfr, const double* taucld,
+                                   const double* cicewp, const double* cliqwp, const double* reice,
+                                   const double* reliq, const double* tauaer, double* uflx, double* dflx, double* hr,
+                                   double* uflxc, double* dflxc, double* hrc, double* duflx_dt, double* duflxc_dt,
+                                   int memspace, void* stream);
 
 /* Replaces mcica_subcol_lw (src/mcica_subcol_gen_lw.f90:183-291); irng is inout (:442).
  * iplon is accepted and ignored, as in the reference.  icld in [0,5]; alpha read for icld 4/5.

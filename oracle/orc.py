@@ -92,6 +92,25 @@ def rrtmg_lw(b, icld=0, idrv=0, inflglw=0, iceflglw=0, liqflglw=0, mc=None, nthr
     return out
 
 
+def rrtmg_lw_nomcica(b, icld=2, idrv=0, inflglw=2, iceflglw=3, liqflglw=1, nthreads=1):
+    """The non-McICA GCM entry (rrtmg_lw_rad.nomcica.f90: cldprop + rtrn / rtrnmr) on a cloudy synth.Batch."""
+    ncol, nlay = b.ncol, b.nlay
+    out = {k: np.zeros((nlay + 1, ncol)) for k in ("uflx", "dflx", "uflxc", "dflxc", "duflx_dt", "duflxc_dt")}
+    out["hr"] = np.zeros((nlay, ncol)); out["hrc"] = np.zeros((nlay, ncol))
+    ic = C.c_int(icld)
+    keep = [_np(x) for x in (b.play, b.plev, b.tlay, b.tlev, b.tsfc, b.h2ovmr, b.o3vmr, b.co2vmr, b.ch4vmr, b.n2ovmr,
+                             b.o2vmr, b.cfc11vmr, b.cfc12vmr, b.cfc22vmr, b.ccl4vmr, b.emis)]
+    cl = [_np(x) for x in (b.cldfrac, b.tauc, b.ciwp, b.clwp, b.rei, b.rel)]
+    ta = _np(b.tauaer)
+    rc = lib().orc_rrtmg_lw_nomcica(ncol, ncol, nlay, C.byref(ic), idrv, *[_p(x) for x in keep], inflglw, iceflglw,
+                                    liqflglw, *[_p(x) for x in cl], _p(ta), _p(out["uflx"]), _p(out["dflx"]),
+                                    _p(out["hr"]), _p(out["uflxc"]), _p(out["dflxc"]), _p(out["hrc"]),
+                                    _p(out["duflx_dt"]), _p(out["duflxc_dt"]), nthreads)
+    out["rc"] = rc
+    out["icld"] = ic.value
+    return out
+
+
 def column_stages(b, icol, icld=0, idrv=0, inflglw=0, iceflglw=0, liqflglw=0, mc=None):
     ncol, nlay = b.ncol, b.nlay
     d = np.zeros((1,))

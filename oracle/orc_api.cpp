@@ -162,6 +162,85 @@ extern "C" int orc_rrtmg_lw(int ncol, int ld, int nlay, int* icld, int idrv, con
     return status;
 }
 
+// rrtmg_lw of src/rrtmg_lw_rad.nomcica.f90:99-588: grid-mean cloud properties, cldprop + rtrn (icld = 1, random
+// overlap) or rtrnmr (icld = 0, 2, 3: maximum-random overlap).  cldfr, cicewp, cliqwp, reice, reliq (ncol, nlay);
+// taucld (nbndlw, ncol, nlay).
+namespace orc {
+int cldprop(int nlayers, int inflag, int iceflag, int liqflag, const double* cldfrac, const double* tauc,
+            const double* ciwp, const double* clwp, const double* rei, const double* rel, int& ncbands,
+            std::vector<double>& taucloud);
+void rtrn_nomcica(Column& c, bool maxrand, const double* cldfrac, int ncbands, const std::vector<double>& taucloud,
+                  int istart, int iend, int iout, int idrv);
+}
+extern "C" int orc_rrtmg_lw_nomcica(int ncol, int ld, int nlay, int* icld, int idrv, const double* play, const double* plev,
+                                    const double* tlay, const double* tlev, const double* tsfc, const double* h2ovmr,
+                                    const double* o3vmr, const double* co2vmr, const double* ch4vmr, const double* n2ovmr,
+                                    const double* o2vmr, const double* cfc11vmr, const double* cfc12vmr,
+                                    const double* cfc22vmr, const double* ccl4vmr, const double* emis, int inflglw,
+                                    int iceflglw, int liqflglw, const double* cldfr, const double* taucld,
+                                    const double* cicewp, const double* cliqwp, const double* reice, const double* reliq,
+                                    const double* tauaer, double* uflx, double* dflx, double* hr, double* uflxc,
+                                    double* dflxc, double* hrc, double* duflx_dt, double* duflxc_dt, int nthreads) {
+    if (!G.inited) return ORC_ERR_NOT_INIT;
+    if (*icld < 0 || *icld > 3) *icld = 2;  // rad.nomcica.f90:458
+    const int icld_run = *icld;
+    int icld_v = 0;  // inatm below copies no McICA arrays
+    const double *cldfmcl = nullptr, *taucmcl = nullptr, *ciwpmcl = nullptr, *clwpmcl = nullptr, *reicmcl = nullptr,
+                 *relqmcl = nullptr;
+    In in;
+    FILL_IN(in)
+    int status = ORC_OK;
+    if (nthreads < 1) nthreads = 1;
+#pragma omp parallel num_threads(nthreads)
+    {
+        Column c;
+        // cfpad: one element of slack either side -- rtrnmr reads cldfrac(lev+1) at the top layer and cldfrac(lev-1) at
+        // layer 1 when it fills faccmb* (rtrnmr.f90:420-423,498-501); those values never reach an output
+        std::vector<double> cfpad(nlay + 2, 0.);
+        double* cf = cfpad.data() + 1;
+        std::vector<double> ci(nlay), cl(nlay), re(nlay), rl(nlay), tc((size_t)NBND * nlay), taucloud;
+#pragma omp for schedule(dynamic, 16)
+        for (int iplon = 1; iplon <= ncol; ++iplon) {
+            const int istart = g_istart, iend = g_iend, iout = (g_istart == 1 && g_iend == 16) ? 0 : g_istart, iaer = 10;
+            inatm(in, iplon, iaer, c);
+            for (int l = 1; l <= nlay; ++l) {
+                if (icld_run >= 1) {
+                    cf[l - 1] = in.at2(cldfr, iplon, l); ci[l - 1] = in.at2(cicewp, iplon, l);
+                    cl[l - 1] = in.at2(cliqwp, iplon, l); re[l - 1] = in.at2(reice, iplon, l);
+                    rl[l - 1] = in.at2(reliq, iplon, l);
+                    for (int n = 1; n <= NBND; ++n)
+                        tc[(n - 1) + NBND * (l - 1)] = taucld[(n - 1) + NBND * ((size_t)(iplon - 1) + (size_t)ld * (l - 1))];
+                } else {
+                    cf[l - 1] = ci[l - 1] = cl[l - 1] = re[l - 1] = rl[l - 1] = 0.;
+                    for (int n = 1; n <= NBND; ++n) tc[(n - 1) + NBND * (l - 1)] = 0.;
+                }
+            }
+            int ncbands = 1;
+            int rc = cldprop(nlay, icld_run >= 1 ? inflglw : 0, iceflglw, liqflglw, cf, tc.data(), ci.data(), cl.data(),
+                             re.data(), rl.data(), ncbands, taucloud);
+            if (rc != ORC_OK) {
+#pragma omp critical
+                if (status == ORC_OK) status = rc;
+                continue;
+            }
+            setcoef(c, istart, idrv);
+            taumol(c);
+            for (int k = 1; k <= c.nlayers; ++k)
+                for (int ig = 1; ig <= NGPT; ++ig) c.LG(c.taut, k, ig) = c.LG(c.taug, k, ig) + c.TAUA(k, G.ngb[ig - 1]);
+            rtrn_nomcica(c, icld_run != 1, cf, ncbands, taucloud, istart, iend, iout, idrv);
+            auto O = [&](double* a, int k) -> double& { return a[(size_t)(iplon - 1) + (size_t)ld * k]; };
+            for (int k = 0; k <= nlay; ++k) {
+                O(uflx, k) = c.totuflux[k]; O(dflx, k) = c.totdflux[k];
+                O(uflxc, k) = c.totuclfl[k]; O(dflxc, k) = c.totdclfl[k];
+            }
+            for (int k = 0; k <= nlay - 1; ++k) { O(hr, k) = c.htr[k]; O(hrc, k) = c.htrc[k]; }
+            if (idrv == 1 && duflx_dt && duflxc_dt)
+                for (int k = 0; k <= nlay; ++k) { O(duflx_dt, k) = c.dtotuflux_dt[k]; O(duflxc_dt, k) = c.dtotuclfl_dt[k]; }
+        }
+    }
+    return status;
+}
+
 extern "C" int orc_column_stages(int icol, int ncol, int ld, int nlay, int icld_v, int idrv, const double* play,
                                  const double* plev, const double* tlay, const double* tlev, const double* tsfc,
                                  const double* h2ovmr, const double* o3vmr, const double* co2vmr,

@@ -29,6 +29,18 @@ int orc_rrtmg_lw(int ncol, int ld, int nlay, int* icld, int idrv, const double* 
                  double* hr, double* uflxc, double* dflxc, double* hrc, double* duflx_dt, double* duflxc_dt,
                  int nthreads);
 
+/* rrtmg_lw of src/rrtmg_lw_rad.nomcica.f90:99-108 (no McICA): cldfr, cicewp, cliqwp, reice, reliq (ncol, nlay);
+ * taucld (nbndlw, ncol, nlay); icld = 1 -> rtrn (random overlap), else rtrnmr (maximum-random) */
+int orc_rrtmg_lw_nomcica(int ncol, int ld, int nlay, int* icld, int idrv, const double* play, const double* plev,
+                         const double* tlay, const double* tlev, const double* tsfc, const double* h2ovmr,
+                         const double* o3vmr, const double* co2vmr, const double* ch4vmr, const double* n2ovmr,
+                         const double* o2vmr, const double* cfc11vmr, const double* cfc12vmr, const double* cfc22vmr,
+                         const double* ccl4vmr, const double* emis, int inflglw, int iceflglw, int liqflglw,
+                         const double* cldfr, const double* taucld, const double* cicewp, const double* cliqwp,
+                         const double* reice, const double* reliq, const double* tauaer, double* uflx, double* dflx,
+                         double* hr, double* uflxc, double* dflxc, double* hrc, double* duflx_dt, double* duflxc_dt,
+                         int nthreads);
+
 int orc_mcica_subcol_lw(int ncol, int ld, int nlay, int icld, int permuteseed, int* irng, const double* play,
                         const double* cldfrac, const double* ciwp, const double* clwp, const double* rei,
                         const double* rel, const double* tauc, const double* alpha, double* cldfmcl,

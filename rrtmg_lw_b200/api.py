@@ -49,6 +49,8 @@ SIGNATURES = {
     "rrtmg_lw_b200_ini": (C.c_int, [C.c_double, _dp, C.c_long, C.c_int]),
     "rrtmg_lw_b200_rrtmg_lw": (C.c_int, [C.c_int, C.c_int, C.c_int, _ip, C.c_int] + [_dp] * 16 + [C.c_int] * 3 +
                                [_dp] * 15 + [C.c_int, C.c_void_p]),
+    "rrtmg_lw_b200_rrtmg_lw_nomcica": (C.c_int, [C.c_int, C.c_int, C.c_int, _ip, C.c_int] + [_dp] * 16 + [C.c_int] * 3 +
+                                       [_dp] * 15 + [C.c_int, C.c_void_p]),
     "rrtmg_lw_b200_rrtmg_lw_mcica": (C.c_int, [C.c_int] * 7 + [_dp] * 16 + [C.c_int] * 3 + [_dp] * 16 +
                                      [C.c_int, C.c_void_p]),
     "rrtmg_lw_b200_mcica_subcol_lw": (C.c_int, [C.c_int] * 6 + [_ip] + [_dp] * 14 + [C.c_int, C.c_void_p]),
@@ -180,6 +182,26 @@ def rrtmg_lw(ncol, nlay, icld, idrv, play, plev, tlay, tlev, tsfc, h2ovmr, o3vmr
                                       int(inflglw), int(iceflglw), int(liqflglw), *p[16:], space, _stream(space))
     if rc:
         raise RrtmgLwError(rc, "rrtmg_lw")
+    return ic.value
+
+
+def rrtmg_lw_nomcica(ncol, nlay, icld, idrv, play, plev, tlay, tlev, tsfc, h2ovmr, o3vmr, co2vmr, ch4vmr, n2ovmr, o2vmr,
+                     cfc11vmr, cfc12vmr, cfc22vmr, ccl4vmr, emis, inflglw, iceflglw, liqflglw, cldfr, taucld, cicewp,
+                     cliqwp, reice, reliq, tauaer, uflx, dflx, hr, uflxc, dflxc, hrc, duflx_dt=None, duflxc_dt=None,
+                     ld=None):
+    """Replaces ``rrtmg_lw`` of ``src/rrtmg_lw_rad.nomcica.f90:99-108`` (grid-mean clouds, no McICA: random overlap
+    for icld = 1, maximum-random otherwise).  Returns the (possibly clamped) icld."""
+    arrs = [play, plev, tlay, tlev, tsfc, h2ovmr, o3vmr, co2vmr, ch4vmr, n2ovmr, o2vmr, cfc11vmr, cfc12vmr, cfc22vmr,
+            ccl4vmr, emis, cldfr, taucld, cicewp, cliqwp, reice, reliq, tauaer, uflx, dflx, hr, uflxc, dflxc,
+            hrc, duflx_dt, duflxc_dt]
+    space = _space(arrs)
+    ic = C.c_int(int(icld))
+    p = [_ptr(a) for a in arrs]
+    rc = lib().rrtmg_lw_b200_rrtmg_lw_nomcica(int(ncol), int(ld or ncol), int(nlay), C.byref(ic), int(idrv), *p[:16],
+                                              int(inflglw), int(iceflglw), int(liqflglw), *p[16:], space,
+                                              _stream(space))
+    if rc:
+        raise RrtmgLwError(rc, "rrtmg_lw_nomcica")
     return ic.value
 
 

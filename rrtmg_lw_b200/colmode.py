@@ -21,8 +21,9 @@ column-mode program (they come from driving the GCM entry, not from this file):
   * per-band output (``iout = 99`` / ``1..16``): every block is its own run of the library over bands
     ``istart..iend`` (``set_option("band_lo" / "band_hi")``; band 16 alone takes the ``totplk16`` Planck variant of
     ``src/rrtmg_lw_setcoef.f90:233-251``), :func:`run_blocks`;
-  * ``iatm = 1`` (``rrtatm`` layering, N4) and ``imca = 0`` with clouds (``cldprop`` + ``rtrnmr``, N2)
-    are refused with ``NotImplementedError``.
+  * ``imca = 0`` with clouds is the non-McICA path (``cldprop`` + ``rtrn`` for icld = 1 / ``rtrnmr`` otherwise,
+    ``src/rrtmg_lw.1col.f90:498,557-572``): one run of the library's ``rrtmg_lw_nomcica`` entry;
+  * ``iatm = 1`` (``rrtatm`` layering, N4) is refused with ``NotImplementedError``.
 """
 from __future__ import annotations
 
@@ -349,6 +350,11 @@ class GpuBackend:
         api.get_alpha(1, 1, b.nlay, icld, idcor, decorr_con, cv(b.dz), cv(b.lat), juldat, cv(b.cldfrac), alpha)
         return alpha
 
+    def nomcica(self, b, icld, idrv, flags):
+        from . import driver
+        return self._np(driver.run_nomcica(b, icld=icld, idrv=idrv, inflglw=flags[0], iceflglw=flags[1],
+                                           liqflglw=flags[2], device=self.device))
+
     def mcica(self, b, icld, idrv, permuteseed, irng, flags, alpha):
         from . import driver
         return self._np(driver.run_fused(b, icld=icld, idrv=idrv, permuteseed=permuteseed, irng=irng, inflglw=flags[0],
@@ -401,8 +407,6 @@ def run_case(c: Case, backend, nmca: int | None = None, irng: int = 1):
     ``band_range``, all 16 bands by default): returns a dict with the level arrays ``uflx, dflx, fnet`` (nlayers+1)
     and ``htr`` (nlayers+1, top entry 0), McICA-averaged over ``nmca`` samples (200 in the reference) and
     ``dtbound``-adjusted when idrv = 1."""
-    if c.imca == 0 and c.icld >= 1:
-        raise NotImplementedError("imca = 0 with clouds is the cldprop + rtrnmr path (SURVEY 8(f) N2)")
     b = case_to_batch(c)
     L = c.nlayers
     n = 1 if c.imca == 0 else (NMCA if nmca is None else nmca)
@@ -416,6 +420,9 @@ def run_case(c: Case, backend, nmca: int | None = None, irng: int = 1):
             # the column-mode generator seeds every sample with permuteseed = ims * nsubclw
             # (src/mcica_subcol_gen_lw.1col.f90:251, nsubclw = ngptlw = 140)
             o = backend.mcica(b, c.icld, c.idrv, ims * NGPT, irng, (c.inflag, c.iceflag, c.liqflag), alpha)
+        elif c.icld >= 1:
+            # grid-mean clouds, no sub-columns: cldprop + rtrn (icld = 1) / rtrnmr (1col:498, 557-572)
+            o = backend.nomcica(b, c.icld, c.idrv, (c.inflag, c.iceflag, c.liqflag))
         else:
             o = backend.clear(b, c.idrv)
         uflx = np.asarray(o["uflx"], dtype=np.float64).reshape(L + 1).copy()

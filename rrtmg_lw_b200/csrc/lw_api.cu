@@ -128,6 +128,7 @@ enum ScratchPiece {
     SP_CLDB = 4,     // two-phase path, McICA mask entry: per-band cloud optical depth of cloudy layers
     SP_GCLD = 8,     // two-phase path, strict rrtmg_lw() entry with clouds: per-g efclfrac / odcld
     SP_FP32IN = 16,  // FP32 mode: float copies of the caller arrays
+    SP_GRID = 32,    // non-McICA entry: cloud fraction, overlap factors, band cloud optical depths per layer
 };
 
 int ensure_scratch(long cols, int nlay, unsigned need) {
@@ -188,6 +189,9 @@ int ensure_scratch(long cols, int nlay, unsigned need) {
     if (miss & SP_GCLD) {
         if (A(&S.gcld, (size_t)2 * NGPT * plane)) return RRTMG_LW_ERR_CUDA;
     }
+    if (miss & SP_GRID) {
+        if (A(&S.gridcld, (size_t)GC_NREC * plane)) return RRTMG_LW_ERR_CUDA;
+    }
     if (miss & SP_FP32IN) {
         if (A(&S.inf, (size_t)(40 * (size_t)(nlay + 1) + 32) * P)) return RRTMG_LW_ERR_CUDA;
     }
@@ -243,7 +247,7 @@ bool launch_sweep(int b0, int nb, int cld, int idrv, const ColIn& in, const ColO
 // default band groups of the sweep kernels: {first band, bands}
 const int kSweepGroups[][2] = {{1, 2}, {3, 1}, {4, 1}, {5, 1}, {6, 2}, {8, 2}, {10, 3}, {13, 4}};
 
-enum Mode { MODE_STRICT = 0, MODE_FUSED = 1 };
+enum Mode { MODE_STRICT = 0, MODE_FUSED = 1, MODE_GRID = 2 };  // MODE_GRID: the non-McICA entry (lw_gridcloud.cuh)
 
 int ensure_side_streams() {
     if (G.side[0]) return 0;
@@ -259,14 +263,16 @@ int run_device(Mode mode, int ncol, int nlay, int icld, int idrv, int inflag, in
     if (nlay < 4 && mode == MODE_FUSED && icld > 0 && irng == 0) return RRTMG_LW_ERR_ARG;  // KISS seeds need 4 layers
     if (nlay < 1 || nlay > LW_MAXLAY) return RRTMG_LW_ERR_ARG;
     const int chunk = G.chunk;
-    const int cld = icld == 0 ? CLD_NONE : (mode == MODE_FUSED ? CLD_MASK : CLD_ARRAYS);
+    const int cld = icld == 0 ? CLD_NONE : (mode == MODE_FUSED ? CLD_MASK : (mode == MODE_GRID ? CLD_GRID : CLD_ARRAYS));
     // optional FP32 mode: float band kernels for clear sky and the fused McICA entry (fused band kernels only; the
     // strict entry with per-g cloud arrays stays FP64)
-    const bool fp32 = G.precision == 32 && cld != CLD_ARRAYS;
-    const bool two_phase = G.band_kernel == 4 && !fp32;  // the FP32 mode lives in the fused band kernels
+    const bool fp32 = G.precision == 32 && cld != CLD_ARRAYS && mode != MODE_GRID;
+    // the FP32 mode lives in the fused band kernels; the non-McICA entry exists on the two-phase path only
+    const bool two_phase = (G.band_kernel == 4 && !fp32) || mode == MODE_GRID;
     unsigned need = two_phase ? SP_TWOPHASE : SP_FUSED;
     if (two_phase && cld == CLD_MASK) need |= SP_CLDB;
     if (two_phase && cld == CLD_ARRAYS) need |= SP_GCLD;
+    if (cld == CLD_GRID) need |= SP_GRID;
     if (fp32) need |= SP_FP32IN;
     int rc = ensure_scratch(ncol < chunk ? ncol : chunk, nlay, need);
     if (rc) return rc;
@@ -332,6 +338,7 @@ int run_device(Mode mode, int ncol, int nlay, int icld, int idrv, int inflag, in
                 if (conc) CK(cudaEventRecord(G.e_cld, qm));
             }
             if (cld == CLD_ARRAYS) { launch_cldflags(in, S, r, st); G.launches += 2; }
+            if (cld == CLD_GRID) { launch_gridcloud_prep(in, S, r, icld != 1, st); G.launches++; }  // needs colprep's secdiff
             if (G.timing) CK(cudaEventRecord(G.ev[1], st));
             if (G.timing) CK(cudaEventRecord(G.evb[nstage++], st));
             launch_taumol(in, S, r, st); G.launches++;
@@ -352,9 +359,10 @@ int run_device(Mode mode, int ncol, int nlay, int icld, int idrv, int inflag, in
                 if (G.timing) CK(cudaEventRecord(G.evb[nstage++], st));
                 slots |= 1u << (b0 - 1);
                 G.launches++;
+                if (cld == CLD_GRID) return launch_gridcloud_sweep(b0, icld != 1, idrv, in, S, r, G.sweep_tab, q);
                 return launch_sweep(b0, nb, cld, idrv, in, out, S, r, q);
             };
-            if (G.sweep_groups && b_lo == 1 && b_hi == NBND) {
+            if (G.sweep_groups && cld != CLD_GRID && b_lo == 1 && b_hi == NBND) {
                 for (const auto& g : kSweepGroups)
                     if (!sweep(g[0], g[1])) return RRTMG_LW_ERR_ARG;
             } else {
@@ -716,6 +724,7 @@ extern "C" int rrtmg_lw_b200_ini(double cpdair, const double* kdata, long nkdata
     CK(upload_constants_stu3(H.ct, dp, rr, &cf));
     CK(upload_constants_stu4(H.ct, dp, rr, &cf));
     CK(upload_constants_stu5(H.ct, dp, rr, &cf));
+    CK(upload_constants_stu6(H.ct, dp, rr, &cf));
     CK(cudaDeviceSynchronize());
     G.inited = true;
     return RRTMG_LW_OK;
@@ -840,6 +849,65 @@ extern "C" int rrtmg_lw_b200_rrtmg_lw_mcica(int ncol, int ld, int nlay, int icld
     const HostOut ho{uflx, dflx, hr, uflxc, dflxc, hrc, duflx_dt, duflxc_dt};
     return host_pipeline(MODE_FUSED, ncol, ld, nlay, icld_overlap, idrv, inflglw, iceflglw, liqflglw, permuteseed, irng,
                          per_col, stage_in, ho, st);
+}
+
+// rrtmg_lw of src/rrtmg_lw_rad.nomcica.f90:99-108: grid-mean cloud arrays, cldprop + rtrn (icld = 1) / rtrnmr (else)
+extern "C" int rrtmg_lw_b200_rrtmg_lw_nomcica(int ncol, int ld, int nlay, int* icld, int idrv, const double* play,
+                                              const double* plev, const double* tlay, const double* tlev,
+                                              const double* tsfc, const double* h2ovmr, const double* o3vmr,
+                                              const double* co2vmr, const double* ch4vmr, const double* n2ovmr,
+                                              const double* o2vmr, const double* cfc11vmr, const double* cfc12vmr,
+                                              const double* cfc22vmr, const double* ccl4vmr, const double* emis,
+                                              int inflglw, int iceflglw, int liqflglw, const double* cldfr,
+                                              const double* taucld, const double* cicewp, const double* cliqwp,
+                                              const double* reice, const double* reliq, const double* tauaer,
+                                              double* uflx, double* dflx, double* hr, double* uflxc, double* dflxc,
+                                              double* hrc, double* duflx_dt, double* duflxc_dt, int memspace,
+                                              void* stream) {
+    LW_ENTER();
+    if (!G.inited) return RRTMG_LW_ERR_NOT_INIT;
+    if (!icld || !check_common(ncol, ld, nlay)) return RRTMG_LW_ERR_ARG;
+    if (*icld < 0 || *icld > 3) *icld = 2;  // rad.nomcica.f90:458
+    if (idrv != 0 && idrv != 1) return RRTMG_LW_ERR_ARG;
+    if (idrv == 1 && (!duflx_dt || !duflxc_dt)) return RRTMG_LW_ERR_ARG;
+    const bool cloudy = *icld >= 1;
+    if (!play || !plev || !tlay || !tlev || !tsfc || !h2ovmr || !o3vmr || !co2vmr || !ch4vmr || !n2ovmr || !o2vmr ||
+        !cfc11vmr || !cfc12vmr || !cfc22vmr || !ccl4vmr || !emis || !tauaer || !uflx || !dflx || !hr || !uflxc ||
+        !dflxc || !hrc)
+        return RRTMG_LW_ERR_ARG;
+    if (cloudy && (!cldfr || !taucld || !cicewp || !cliqwp || !reice || !reliq)) return RRTMG_LW_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    reset_timing();
+    if (memspace == RRTMG_LW_DEVICE) {
+        ColIn in{};
+        in.play = play; in.plev = plev; in.tlay = tlay; in.tlev = tlev; in.tsfc = tsfc; in.h2o = h2ovmr; in.o3 = o3vmr;
+        in.co2 = co2vmr; in.ch4 = ch4vmr; in.n2o = n2ovmr; in.o2 = o2vmr; in.cfc11 = cfc11vmr; in.cfc12 = cfc12vmr;
+        in.cfc22 = cfc22vmr; in.ccl4 = ccl4vmr; in.emis = emis; in.tauaer = tauaer;
+        in.cldfrac = cldfr; in.ciwp = cicewp; in.clwp = cliqwp; in.rei = reice; in.rel = reliq; in.tauc = taucld;
+        in.ld = ld; in.nlay = nlay;
+        ColOut out{uflx, dflx, hr, uflxc, dflxc, hrc, duflx_dt, duflxc_dt, G.out_ld > 0 ? G.out_ld : (long)ld};
+        return run_device(MODE_GRID, ncol, nlay, *icld, idrv, inflglw, iceflglw, liqflglw, 0, 0, in, out, st);
+    }
+    const size_t per_col = (size_t)12 * nlay + 2 * (nlay + 1) + 1 + 16 + 16 * (size_t)nlay +
+                           (cloudy ? (size_t)5 * nlay + 16 * (size_t)nlay : 0) + 6 * (size_t)(nlay + 1) + 2 * (size_t)nlay;
+    auto stage_in = [&](Stager& sg, ColIn& in, long c0, int nc) -> int {
+        double* d;
+#define IN2(field, src, rows) if (sg.in(src, &d, 1, ld, c0, nc, rows)) return RRTMG_LW_ERR_CUDA; in.field = d;
+        IN2(play, play, nlay) IN2(plev, plev, nlay + 1) IN2(tlay, tlay, nlay) IN2(tlev, tlev, nlay + 1) IN2(tsfc, tsfc, 1)
+        IN2(h2o, h2ovmr, nlay) IN2(o3, o3vmr, nlay) IN2(co2, co2vmr, nlay) IN2(ch4, ch4vmr, nlay) IN2(n2o, n2ovmr, nlay)
+        IN2(o2, o2vmr, nlay) IN2(cfc11, cfc11vmr, nlay) IN2(cfc12, cfc12vmr, nlay) IN2(cfc22, cfc22vmr, nlay)
+        IN2(ccl4, ccl4vmr, nlay) IN2(emis, emis, 16) IN2(tauaer, tauaer, (long)16 * nlay)
+        if (cloudy) {
+            IN2(cldfrac, cldfr, nlay) IN2(ciwp, cicewp, nlay) IN2(clwp, cliqwp, nlay) IN2(rei, reice, nlay)
+            IN2(rel, reliq, nlay)
+            if (sg.in(taucld, &d, 16, ld, c0, nc, nlay)) return RRTMG_LW_ERR_CUDA;
+            in.tauc = d;
+        }
+#undef IN2
+        return 0;
+    };
+    const HostOut ho{uflx, dflx, hr, uflxc, dflxc, hrc, duflx_dt, duflxc_dt};
+    return host_pipeline(MODE_GRID, ncol, ld, nlay, *icld, idrv, inflglw, iceflglw, liqflglw, 0, 0, per_col, stage_in, ho, st);
 }
 
 extern "C" int rrtmg_lw_b200_mcica_subcol_lw(int iplon, int ncol, int ld, int nlay, int icld, int permuteseed, int* irng,

@@ -45,7 +45,18 @@ enum Field {
 };
 
 // cloud treatment of the band kernel
-enum CloudMode { CLD_NONE = 0, CLD_MASK = 1, CLD_ARRAYS = 2 };
+enum CloudMode { CLD_NONE = 0, CLD_MASK = 1, CLD_ARRAYS = 2, CLD_GRID = 3 };  // CLD_GRID: lw_gridcloud.cuh kernels
+
+// per-(column, layer) record written by gridcloud_prep_kernel: [layer][GC_NREC][pitch] doubles
+enum GridCloudRec {
+    GC_CLDFRAC = 0,
+    GC_FLAGS,      // bit 0 icldlyr, bit 1 istcld(lev), bit 2 istcldd(lev)  (as a double holding a small integer)
+    GC_FACCLR1, GC_FACCLR2, GC_FACCLD1, GC_FACCLD2, GC_FACCMB1, GC_FACCMB2,        // index lev+1 of the reference (upward)
+    GC_FACCLR1D, GC_FACCLR2D, GC_FACCLD1D, GC_FACCLD2D, GC_FACCMB1D, GC_FACCMB2D,  // index lev-1 of the reference (downward)
+    GC_ODCLD,                  // 16 bands: secdiff(ib) * taucloud(lay, ib), ib = ipat(band, ncbands)
+    GC_EFCL = GC_ODCLD + 16,   // 16 bands: (1 - exp(-odcld)) * cldfrac  (rtrn only)
+    GC_NREC = GC_EFCL + 16
+};
 
 struct Scratch {
     double* fld;        // NFIELD x nlay x pitch
@@ -73,6 +84,8 @@ struct Scratch {
     double* cldb;       // [pitch / 128][nlay][16][2][128] : {odcld, 1 - exp(-odcld)} of a band's cloudy sub-columns (CLD_MASK)
     double* fluxP;      // [pitch / 128][nlay + 1][16][6][128] : level-flux band sums, one slot per sweep launch (first band)
     double* gcld;       // 2 x 140 x nlay x pitch : efclfrac, odcld per g-point (strict rrtmg_lw() entry only)
+    double* gridcld;    // nlay x GC_NREC x pitch : cloud fraction, overlap factors, band cloud optical depths of the
+                        // non-McICA entry (lw_gridcloud.cuh)
     // debug capture of one column
     int dbg_col;        // chunk-relative column or -1
     double *dbg_taug, *dbg_fracs;  // (140, nlay)

@@ -58,4 +58,9 @@ void launch_taumol(const ColIn&, const Scratch&, const RunCfg&, cudaStream_t);
 LW_DECL_STU(1) LW_DECL_STU(2) LW_DECL_STU(3) LW_DECL_STU(4) LW_DECL_STU(5)
 #undef LW_DECL_STU
 cudaError_t upload_constants_stu0(const ConstTab&, const DevPtrs&, const double (*refrat)[5], const ConstTabF*);
+// non-McICA path (lw_gridcloud.cuh, STU 6): cldprop + overlap factors, then one rtrn / rtrnmr sweep kernel per band
+cudaError_t upload_constants_stu6(const ConstTab&, const DevPtrs&, const double (*refrat)[5], const ConstTabF*);
+void launch_gridcloud_prep(const ColIn&, const Scratch&, const RunCfg&, int maxran, cudaStream_t);
+bool launch_gridcloud_sweep(int band, int maxran, int idrv, const ColIn&, const Scratch&, const RunCfg&, const SweepTab&,
+                            cudaStream_t);
 }  // namespace lw

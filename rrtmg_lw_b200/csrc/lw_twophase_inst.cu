@@ -3,13 +3,17 @@
 //   STU 0: column scalars + the (column, layer) taumol kernel
 //   STU 1-3: the default band groups of the sweep kernel
 //   STU 4-5: single-band sweep kernels (band-range runs, e.g. the per-band output blocks of the column-mode harness)
+//   STU 6: the non-McICA path (lw_gridcloud.cuh): cldprop + overlap factors, rtrn / rtrnmr sweeps
 #include <cstdlib>
 
 #include "lw_rtrnmc.cuh"
+#if LW_STU == 6
+#include "lw_gridcloud.cuh"
+#endif
 #include "lw_launch.h"
 
 #ifndef LW_STU
-#error "compile with -DLW_STU=0..5"
+#error "compile with -DLW_STU=0..6"
 #endif
 
 #define LW_CAT2(a, b) a##b
@@ -26,6 +30,32 @@ cudaError_t LW_CAT(upload_constants_stu, LW_STU)(const ConstTab& c, const DevPtr
 void launch_taumol(const ColIn& in, const Scratch& s, const RunCfg& r, cudaStream_t st) {
     const dim3 grid((unsigned)((r.ncol + TAUMOL_THREADS - 1) / TAUMOL_THREADS), (unsigned)r.nlay);
     taumol_kernel<0xffffu, LW_TAUMOL_MINB><<<grid, TAUMOL_THREADS, 0, st>>>(in, s, r);
+}
+#elif LW_STU == 6
+void launch_gridcloud_prep(const ColIn& in, const Scratch& s, const RunCfg& r, int maxran, cudaStream_t st) {
+    gridcloud_prep_kernel<<<(r.ncol + 127) / 128, 128, 0, st>>>(in, s, r, maxran);
+}
+template <int B>
+static void launch_gc(int maxran, int idrv, const ColIn& in, const Scratch& s, const RunCfg& r, const SweepTab& tb,
+                      cudaStream_t st) {
+    const int blocks = (r.ncol + 127) / 128;
+    if (maxran) {
+        if (idrv) gridcloud_sweep_kernel<B, 1, 1><<<blocks, 128, 0, st>>>(in, s, r, tb);
+        else gridcloud_sweep_kernel<B, 1, 0><<<blocks, 128, 0, st>>>(in, s, r, tb);
+    } else {
+        if (idrv) gridcloud_sweep_kernel<B, 0, 1><<<blocks, 128, 0, st>>>(in, s, r, tb);
+        else gridcloud_sweep_kernel<B, 0, 0><<<blocks, 128, 0, st>>>(in, s, r, tb);
+    }
+}
+bool launch_gridcloud_sweep(int band, int maxran, int idrv, const ColIn& in, const Scratch& s, const RunCfg& r,
+                            const SweepTab& tb, cudaStream_t st) {
+    switch (band) {
+#define LW_CASE(B) case B: launch_gc<B>(maxran, idrv, in, s, r, tb, st); return true;
+        LW_CASE(1) LW_CASE(2) LW_CASE(3) LW_CASE(4) LW_CASE(5) LW_CASE(6) LW_CASE(7) LW_CASE(8) LW_CASE(9) LW_CASE(10)
+        LW_CASE(11) LW_CASE(12) LW_CASE(13) LW_CASE(14) LW_CASE(15) LW_CASE(16)
+#undef LW_CASE
+    }
+    return false;
 }
 #else
 

@@ -68,6 +68,20 @@ def run_fused(b, icld=2, idrv=0, permuteseed=1, irng=0, inflglw=2, iceflglw=3, l
     return out
 
 
+def run_nomcica(b, icld=2, idrv=0, inflglw=2, iceflglw=3, liqflglw=1, device=None, out=None):
+    """rrtmg_lw() of the non-McICA build (grid-mean clouds; rtrn for icld = 1, rtrnmr otherwise) on a Batch."""
+    c = _conv(b, device)
+    a = atm_args(b, c)
+    cl = [c(x) for x in (b.cldfrac, b.tauc, b.ciwp, b.clwp, b.rei, b.rel)]
+    ta = c(b.tauaer)
+    if out is None:
+        out = _outputs(b.nlay, b.ncol, like=a[0] if device is not None else None)
+    out["icld"] = api.rrtmg_lw_nomcica(b.ncol, b.nlay, icld, idrv, *a, inflglw, iceflglw, liqflglw, *cl, ta,
+                                       out["uflx"], out["dflx"], out["hr"], out["uflxc"], out["dflxc"], out["hrc"],
+                                       out["duflx_dt"], out["duflxc_dt"])
+    return out
+
+
 def run_mcica_subcol(b, icld, permuteseed=1, irng=0, alpha=None, device=None):
     c = _conv(b, device)
     args = [c(x) for x in (b.play, b.cldfrac, b.ciwp, b.clwp, b.rei, b.rel, b.tauc)]

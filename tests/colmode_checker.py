@@ -1,5 +1,5 @@
-"""CPU checker with the three methods rrtmg_lw_b200.colmode.run_case asks of a backend
-(clear / get_alpha / mcica), answered by the oracle.  Test infrastructure only."""
+"""CPU checker with the methods rrtmg_lw_b200.colmode.run_case asks of a backend
+(clear / get_alpha / mcica / nomcica), answered by the oracle.  Test infrastructure only."""
 import numpy as np
 
 
@@ -20,6 +20,11 @@ class OracleBackend:
 
     def get_alpha(self, b, icld, idcor, decorr_con, juldat):
         return self.orc.get_alpha(b, icld, idcor=idcor, decorr_con=decorr_con, juldat=juldat)
+
+    def nomcica(self, b, icld, idrv, flags):
+        o = self.orc.rrtmg_lw_nomcica(b, icld=icld, idrv=idrv, inflglw=flags[0], iceflglw=flags[1], liqflglw=flags[2])
+        assert o["rc"] == 0
+        return o
 
     def mcica(self, b, icld, idrv, permuteseed, irng, flags, alpha):
         mc = self.orc.mcica_subcol_lw(b, icld, permuteseed=permuteseed, irng=irng, alpha=alpha)

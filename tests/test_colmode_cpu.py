@@ -140,10 +140,6 @@ def test_driver_loop_over_the_oracle_pins_the_goldens_surface_flux(suite, oracle
     be = OracleBackend(oracle)
     for n, d in _supported(suite).items():
         c = colmode.Case(**d["case"])
-        if c.imca == 0 and c.icld >= 1:
-            with pytest.raises(NotImplementedError):
-                colmode.run_case(c, be)
-            continue
         r = colmode.run_case(c, be, nmca=None if n == "MLS-cld7-imca1-icld5-idcor1" else 6)
         g = d["golden"]
         assert r["nmca"] == (1 if c.imca == 0 else (200 if n == "MLS-cld7-imca1-icld5-idcor1" else 6))

@@ -17,7 +17,7 @@ from rrtmg_lw_b200 import colmode  # noqa: E402
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SUITE = json.load(open(os.path.join(ROOT, "tests", "golden", "std_atm_cases.json")))
-RUNNABLE = [n for n, d in SUITE.items() if d["case"] is not None and not (d["case"]["imca"] == 0 and d["case"]["icld"] >= 1)]
+RUNNABLE = [n for n, d in SUITE.items() if d["case"] is not None]
 
 
 @pytest.mark.parametrize("name", RUNNABLE)
@@ -48,10 +48,22 @@ def test_full_200_sample_mcica_average(gpu, oracle):
         assert float(np.abs(got[k] - ref[k]).max()) <= 1e-6, k
 
 
-def test_unsupported_cases_are_refused(gpu):
+def test_non_mcica_cloudy_case_all_17_blocks(gpu, oracle):
+    """MLS-cld5-imca0-icld2 (iout = 99): cldprop + rtrnmr through the library's rrtmg_lw_nomcica entry, broadband block
+    and the 16 per-band runs, against the oracle's restatement; and with icld switched to 1 (rtrn)."""
+    import dataclasses
     c = colmode.Case(**SUITE["MLS-cld5-imca0-icld2"]["case"])
-    with pytest.raises(NotImplementedError):
-        colmode.run_case(c, colmode.GpuBackend(None))
+    assert (c.imca, c.icld, c.iout) == (0, 2, 99)
+    for case in (c, dataclasses.replace(c, icld=1)):
+        ref = colmode.run_blocks(case, OracleBackend(oracle))
+        got = colmode.run_blocks(case, colmode.GpuBackend("cuda:0"))
+        gpu.sync()
+        assert len(ref) == len(got) == 17
+        for k, (r, g) in enumerate(zip(ref, got)):
+            for key in ("uflx", "dflx", "fnet", "htr"):
+                err = float(np.abs(g[key] - r[key]).max())
+                assert err <= 1e-6, (case.icld, "block", k, key, err)
+        assert float(np.abs(got[0]["dflx"] - colmode.run_case(dataclasses.replace(case, icld=0), colmode.GpuBackend("cuda:0"))["dflx"]).max()) > 1.0
 
 
 @pytest.mark.parametrize("name", ["MLS-clr", "MLS-clr-aer12", "MLS-clr-idrv1"])

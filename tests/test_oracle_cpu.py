@@ -271,3 +271,47 @@ def test_kdata_layout_matches_the_reference_modules():
             assert weighted == (1 if uses_rwgt else 0), (band, name, "weighted flag", weighted, stmts[:2])
             seen += 1
     assert seen == 115
+
+
+def test_nomcica_oracle_pinned_against_the_mcica_path(oracle):
+    """The non-McICA restatement (oracle/orc_nomcica.cpp: cldprop + rtrn / rtrnmr) has no golden vector of its own in
+    the reference tree, so it is tied to the McICA restatement, which has: (1) without clouds it must reproduce the
+    clear run bit for bit; (2) with OVERCAST cloudy layers (cldfrac = 1) random overlap, maximum-random overlap and
+    McICA (every sub-column cloudy, same band optical depths) are the same physical problem: rtrn, which shares the
+    efclfrac form of the cloudy update with rtrnmc, must agree to rounding, and rtrnmr, which takes the cloudy stream's
+    transmittance from the table entry of the TOTAL optical depth instead (rtrnmr.f90:600-603), to the table's
+    resolution; (3) with fractional clouds the McICA sample mean must scatter around the maximum-random result."""
+    from rrtmg_lw_b200 import synth
+    b = synth.make_batch(48, 40, cloudy=True, aerosol=True)
+    # (1)
+    z = synth.make_batch(48, 40, cloudy=True, aerosol=True)
+    z.cldfrac[:] = 0.0
+    clear = oracle.rrtmg_lw(z, icld=0, idrv=1)
+    for icld in (0, 1, 2):
+        r = oracle.rrtmg_lw_nomcica(z, icld=icld, idrv=1)
+        assert r["rc"] == 0
+        for k in ("uflx", "dflx", "uflxc", "dflxc", "hr", "hrc", "duflx_dt", "duflxc_dt"):
+            assert np.array_equal(r[k], clear[k]), (icld, k)
+    # (2)
+    o = synth.make_batch(48, 40, cloudy=True, aerosol=True)
+    o.cldfrac[:] = (o.cldfrac > 0).double()
+    mc = oracle.mcica_subcol_lw(o, 2, permuteseed=1, irng=0)
+    assert mc["cldfmcl"].sum() > 0 and set(np.unique(mc["cldfmcl"])) <= {0.0, 1.0}
+    ref = oracle.rrtmg_lw(o, icld=2, idrv=1, inflglw=2, iceflglw=3, liqflglw=1, mc=mc)
+    for icld in (1, 2):
+        r = oracle.rrtmg_lw_nomcica(o, icld=icld, idrv=1, inflglw=2, iceflglw=3, liqflglw=1)
+        for k in ("uflx", "dflx", "uflxc", "dflxc", "duflx_dt", "duflxc_dt"):
+            assert np.abs(r[k] - ref[k]).max() < (1e-9 if icld == 1 else 0.05), (icld, k, np.abs(r[k] - ref[k]).max())
+        assert np.abs(ref["dflx"] - ref["dflxc"]).max() > 10.0
+    # (3)
+    mr = oracle.rrtmg_lw_nomcica(b, icld=2, inflglw=2, iceflglw=3, liqflglw=1)
+    acc = np.zeros_like(mr["dflx"])
+    n = 24
+    for seed in range(n):
+        mc = oracle.mcica_subcol_lw(b, 2, permuteseed=seed * 140, irng=0)
+        acc += oracle.rrtmg_lw(b, icld=2, inflglw=2, iceflglw=3, liqflglw=1, mc=mc)["dflx"]
+    cloud_effect = np.abs(mr["dflx"][0] - mr["dflxc"][0])
+    bias = np.abs(acc[0] / n - mr["dflx"][0])
+    sel = cloud_effect > 5.0
+    assert sel.sum() > 5
+    assert np.median(bias[sel] / cloud_effect[sel]) < 0.1
