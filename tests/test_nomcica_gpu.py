@@ -107,7 +107,7 @@ def test_nomcica_host_call_chunks_and_clear_limit(gpu, oracle):
     try:
         got = driver.run_nomcica(b, icld=2, idrv=1)
     finally:
-        gpu.set_chunk(0)
+        gpu.set_chunk(262144)
     _check(got, ref, 1, what="host")
     dev = driver.run_nomcica(b, icld=2, idrv=1, device="cuda:0")
     gpu.sync()
