@@ -106,8 +106,8 @@ int rrtmg_lw_b200_rrtmg_lw_nomcica(int ncol, int ld, int nlay, int* icld, int id
  * irng = 0: KISS, one stream per column seeded from the column's four lowest pressures (needs nlay >= 4).
  * irng = 1: Mersenne Twister (src/mcica_random_numbers.f90), ONE stream per call in the order
  *           (sub-column, column, layer) seeded with permuteseed -- reproduced exactly, including for calls
- *           that the library processes in several column passes; a compatibility path (one CTA advances
- *           the generator), use irng = 0 for throughput. */
+ *           that the library processes in several column passes.  140 generator CTAs (one per sub-column) each
+ *           reach their place in the stream with a GF(2) polynomial jump-ahead and emit their run in parallel. */
 int rrtmg_lw_b200_mcica_subcol_lw(int iplon, int ncol, int ld, int nlay, int icld, int permuteseed, int* irng,
                                   const double* play, const double* cldfrac, const double* ciwp,
                                   const double* clwp, const double* rei, const double* rel, const double* tauc,
@@ -177,6 +177,9 @@ int rrtmg_lw_b200_set_chunk(int max_columns);
  * "concurrency": 1 (default) = independent kernels of a pass run on side streams of the library (McICA generator and
  *   cloud optics beside taumol, the sweep kernels beside each other), forked from and joined to the caller's stream;
  *   0 = everything on the caller's stream.
+ * "kiss_sparse": 1 (default) = the KISS generator (irng = 0, icld 1 / 2) stops at the highest layer with a cloud
+ *   fraction and steps over the draws of cloud-free layers with closed-form jumps (those draws cannot reach the
+ *   mask); 0 = every number of the reference's stream is drawn.  The masks are bit-identical either way.
  * "out_ld": column extent of the OUTPUT arrays of the following device-pointer calls when it differs from ld (0 =
  *   same as ld): a call on a column sub-range of a resident batch (inputs offset, ld = the batch's extent) can write
  *   its fluxes straight into a packed, chunk-sized send buffer.  out_ld >= ncol.
@@ -196,6 +199,11 @@ int rrtmg_lw_b200_set_option(const char* name, int value);
  * McICA kernel (src/mcica_subcol_gen_lw.f90:731-741 stepped n times == one jump); returns the number
  * of mismatches (0 = ok).  Needs no CUDA device. */
 int rrtmg_lw_b200_kiss_jump_selftest(void);
+/* Host-only self test of the Mersenne-Twister jump-ahead of the irng = 1 path (src/mcica_random_numbers.f90:134-152
+ * stepped n times == the GF(2) polynomial jump by n, for several n up to 10^6): builds the jump table (characteristic
+ * polynomial by Berlekamp-Massey, x^(2^b) mod phi by squaring) and returns the number of mismatching state words
+ * (0 = ok, -1 = the table could not be built).  Needs no CUDA device. */
+int rrtmg_lw_b200_mt_jump_selftest(void);
 /* Number of kernels launched by this library since the last call with reset != 0. */
 long rrtmg_lw_b200_launch_count(int reset);
 /* CUDA-event time (ms) spent in the band kernels / all kernels of the last HOST- or DEVICE-mode

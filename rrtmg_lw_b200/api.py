@@ -64,6 +64,7 @@ SIGNATURES = {
     "rrtmg_lw_b200_set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "rrtmg_lw_b200_set_device": (C.c_int, [C.c_int]),
     "rrtmg_lw_b200_kiss_jump_selftest": (C.c_int, []),
+    "rrtmg_lw_b200_mt_jump_selftest": (C.c_int, []),
     "rrtmg_lw_b200_launch_count": (C.c_long, [C.c_int]),
     "rrtmg_lw_b200_set_timing": (C.c_int, [C.c_int]),
     "rrtmg_lw_b200_last_timing": (C.c_int, [_fp, _fp]),

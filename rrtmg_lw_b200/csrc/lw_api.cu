@@ -1132,6 +1132,11 @@ extern "C" int rrtmg_lw_b200_set_option(const char* name, int value) {
         G.out_ld = value;
         return RRTMG_LW_OK;
     }
+    if (std::strcmp(name, "kiss_sparse") == 0) {
+        if (value != 0 && value != 1) return RRTMG_LW_ERR_ARG;
+        set_kiss_sparse(value);
+        return RRTMG_LW_OK;
+    }
     if (std::strcmp(name, "concurrency") == 0) {
         if (value != 0 && value != 1) return RRTMG_LW_ERR_ARG;
         G.concurrency = value;
@@ -1229,6 +1234,7 @@ extern "C" int rrtmg_lw_b200_fp64_peak(double* tflops) {
 }
 
 extern "C" int rrtmg_lw_b200_kiss_jump_selftest(void) { return kiss_jump_selftest(); }
+extern "C" int rrtmg_lw_b200_mt_jump_selftest(void) { return mt_jump_selftest(); }
 
 extern "C" const char* rrtmg_lw_b200_version(void) { return "rrtmg_lw_b200 0.1 (sm_100a)"; }
 

@@ -278,6 +278,12 @@ struct Kiss {
         const int kiss = (int)(s1 + s2 + (s3 << 16) + s4);
         return (double)kiss * 2.328306e-10 + 0.5;
     }
+    __device__ __forceinline__ void step() {  // advance without forming the number
+        s1 = 69069u * s1 + 1327217885u;
+        s2 ^= s2 << 13; s2 ^= s2 >> 17; s2 ^= s2 << 5;
+        s3 = 18000u * (s3 & 65535u) + (s3 >> 16);
+        s4 = 30903u * (s4 & 65535u) + (s4 >> 16);
+    }
 };
 
 // per-layer cloud flag (icldlyr, bit 31 of mask word 4), column cloud top, and the validation of the cloud-optics
@@ -384,11 +390,12 @@ __global__ void __launch_bounds__(128) mcica_kiss_kernel(ColIn in, Scratch s, Ru
 // Mersenne-Twister path (irng = 1).  The reference draws ONE global stream in the order
 // (sub-column, column, layer) [two draws per point for icld 4/5, one per (sub-column, column) for icld 3]
 // from new_RandomNumberSequence(seed = permuteseed) (mcica:478, 523-530, 586-595; MT19937 itself
-// src/mcica_random_numbers.f90:116-185).  Here one CTA regenerates the 624-word state in three
-// data-parallel phases and emits the tempered words of one sub-column's run of a column chunk at a time
-// (the words between two runs of a chunk are stepped over, not stored); a column-parallel kernel then
-// applies the overlap recurrence and sets that sub-column's bit in the packed cloud mask.  This is the
-// reference-faithful compatibility path, not a throughput path.
+// src/mcica_random_numbers.f90:116-185).  The 140 sub-column runs of a column block are generated side by side:
+// generator CTA sc starts (sc * ncol_of_the_call + first column) * draws_per_column words into the stream, a position
+// it reaches with the GF(2) jump-ahead of lw_mtjump.cpp (mt_jump_kernel), regenerates the 624-word state in three
+// data-parallel phases per period and emits the tempered words of its run tile by tile; a (column, sub-column)-parallel
+// kernel applies the overlap recurrence and sets the sub-column's bit in the packed cloud mask.  The words are the
+// reference's, bit for bit; what changes is that 140 CTAs advance 140 copies of the stream instead of one.
 struct MtState {
     unsigned mt[624];
     int cur;
@@ -403,9 +410,14 @@ __device__ __forceinline__ unsigned mt_twist(unsigned u, unsigned v) {
     const unsigned mix = (u & 0x80000000u) | (v & 0x7fffffffu);
     return (mix >> 1) ^ ((v & 1u) ? 0x9908b0dfu : 0u);
 }
-__global__ void __launch_bounds__(256) mt_fill_kernel(MtState* st, unsigned* __restrict__ out, long skip, long emit) {
+// CTA q advances generator state st[q] and writes its next `emit` tempered words to out + q * out_stride (after
+// stepping over `skip` words)
+__global__ void __launch_bounds__(256) mt_fill_kernel(MtState* st, unsigned* __restrict__ out, long out_stride, long skip,
+                                                      long emit) {
     __shared__ unsigned mt[624];
     const int t = threadIdx.x;
+    st += blockIdx.x;
+    out += (long)blockIdx.x * out_stride;
     for (int k = t; k < 624; k += 256) mt[k] = st->mt[k];
     int cur = st->cur;
     __syncthreads();
@@ -448,6 +460,48 @@ __global__ void __launch_bounds__(256) mt_fill_kernel(MtState* st, unsigned* __r
     for (int k = t; k < 624; k += 256) st->mt[k] = mt[k];
     if (t == 0) st->cur = cur;
 }
+// Jump-ahead: out[q] = the state n0 + q * stride words after the freshly seeded state *seed (lw_mtjump.cpp).  For every
+// set bit b of the distance: expand the current window to the next 19937 + 623 raw words, then word j of the new window
+// is the XOR of x[i + j] over the set coefficients i of x^(2^b) mod phi.  One CTA per target state.
+constexpr int MTJ_DEG = 19937;
+constexpr int MTJ_XS = MTJ_DEG + 624;  // raw words a pass needs
+__global__ void __launch_bounds__(640) mt_jump_kernel(const MtState* __restrict__ seed, MtState* __restrict__ out,
+                                                      const unsigned* __restrict__ pow2, unsigned long long n0,
+                                                      unsigned long long stride) {
+    extern __shared__ unsigned xs[];  // MTJ_XS words
+    const int t = threadIdx.x;
+    const unsigned long long n = n0 + (unsigned long long)blockIdx.x * stride;
+    for (int k = t; k < 624; k += blockDim.x) xs[k] = seed->mt[k];
+    __syncthreads();
+    for (int b = 0; b < MTJ_NPOW && (n >> b) != 0ull; ++b) {
+        if (!((n >> b) & 1ull)) continue;  // uniform over the CTA
+        // x[k + 624] = x[k + 397] ^ twist(x[k], x[k + 1]): 227 words per step are independent of each other
+        for (int base = 0; base < MTJ_DEG; base += 227) {
+            const int k = base + t;
+            if (t < 227 && k < MTJ_DEG) xs[k + 624] = xs[k + 397] ^ mt_twist(xs[k], xs[k + 1]);
+            __syncthreads();
+        }
+        const unsigned* g = pow2 + (size_t)b * 624;
+        unsigned y = 0u;
+        if (t < 624) {
+            for (int w = 0; w < 624; ++w) {
+                const unsigned gw = __ldg(g + w);  // uniform
+                if (gw == 0u) continue;
+                const unsigned* x = xs + w * 32 + t;
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if ((gw >> i) & 1u) y ^= x[i];
+            }
+        }
+        __syncthreads();
+        if (t < 624) xs[t] = y;
+        __syncthreads();
+    }
+    MtState* o = out + blockIdx.x;
+    for (int k = t; k < 624; k += blockDim.x) o->mt[k] = xs[k];
+    if (t == 0) o->cur = 624;
+}
+
 // getRandomReal, random_numbers:276-295: for a negative INT32 the sum localInt + 2.0**32 is evaluated in the
 // default real kind (float under plain gfortran), then divided by the kind-rb 2**32 - 1
 __device__ __forceinline__ double mt_real(unsigned w) {
@@ -459,18 +513,22 @@ __device__ __forceinline__ double mt_real(unsigned w) {
     }
     return (double)li / denom;
 }
-// one thread = one column of the chunk, sub-column sc: its draws are buf[(i * nlay + l) * d (+1)]
-__global__ void __launch_bounds__(128) mcica_mt_apply_kernel(ColIn in, Scratch s, RunCfg r, const unsigned* __restrict__ buf, int sc) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= r.ncol) return;
+// one thread = one column of the tile [t0, t0 + tn) of the chunk and sub-column sc = blockIdx.y: its draws are
+// buf[sc * stride + ((i - t0) * nlay + l) * d (+1)]; the chunk's mask words were zeroed beforehand
+__global__ void __launch_bounds__(128) mcica_mt_apply_kernel(ColIn in, Scratch s, RunCfg r, const unsigned* __restrict__ buf,
+                                                             long stride, int t0, int tn) {
+    const int it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= tn) return;
+    const int i = t0 + it;
+    const int sc = blockIdx.y;
+    buf += (long)sc * stride;
     const long ci = r.c0 + i;
     const int nlay = r.nlay, icld = r.icld;
     const long P = s.pitch;
     const double cldmin = 1.0e-20;
     const unsigned bit = 1u << (sc & 31);
-    const bool fresh = (sc & 31) == 0;
     const int d = icld >= 4 ? 2 : 1;
-    const unsigned* q = icld == 3 ? buf + i : buf + (long)i * nlay * d;
+    const unsigned* q = icld == 3 ? buf + it : buf + (long)it * nlay * d;
     double prev = 0., cfm = 0.;
     const double rmax = icld == 3 ? mt_real(q[0]) : 0.;
     for (int l = 0; l < nlay; ++l) {
@@ -490,10 +548,7 @@ __global__ void __launch_bounds__(128) mcica_mt_apply_kernel(ColIn in, Scratch s
         }
         prev = x;
         cfm = cf;
-        unsigned* mw = s.mask + ((long)l * 5 + (sc >> 5)) * P + i;
-        unsigned m = fresh ? 0u : *mw;
-        if (x >= 1. - cf) m |= bit;
-        *mw = m;
+        if (x >= 1. - cf) atomicOr(s.mask + ((long)l * 5 + (sc >> 5)) * P + i, bit);
     }
 }
 __global__ void __launch_bounds__(128) mcica_finish_kernel(ColIn in, Scratch s, RunCfg r) {
@@ -508,39 +563,71 @@ static inline int cur_dev() {
     if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= LWK_MAX_DEVICES) d = 0;
     return d;
 }
-static MtState* g_mt_state_d[LWK_MAX_DEVICES] = {};
-static unsigned* g_mt_buf_d[LWK_MAX_DEVICES] = {};
-static size_t g_mt_buf_words_d[LWK_MAX_DEVICES] = {};
-#define g_mt_state g_mt_state_d[cur_dev()]
-#define g_mt_buf g_mt_buf_d[cur_dev()]
-#define g_mt_buf_words g_mt_buf_words_d[cur_dev()]
+struct MtBuffers {
+    MtState* seed = nullptr;    // the freshly seeded state of the call
+    MtState* run = nullptr;     // NGPT states, one per sub-column generator
+    unsigned* pow2 = nullptr;   // MTJ_NPOW x 624 words: x^(2^b) mod phi
+    unsigned* buf = nullptr;    // NGPT x buf_stride tempered words of the current tile
+    size_t buf_words = 0;
+    bool jump_attr = false;
+};
+static MtBuffers g_mt_d[LWK_MAX_DEVICES];
+#define g_mt g_mt_d[cur_dev()]
 
 void free_mt_buffers() {
-    if (g_mt_state) cudaFree(g_mt_state);
-    if (g_mt_buf) cudaFree(g_mt_buf);
-    g_mt_state = nullptr; g_mt_buf = nullptr; g_mt_buf_words = 0;
+    MtBuffers& m = g_mt;
+    if (m.seed) cudaFree(m.seed);
+    if (m.run) cudaFree(m.run);
+    if (m.pow2) cudaFree(m.pow2);
+    if (m.buf) cudaFree(m.buf);
+    m = MtBuffers{};
 }
 
+#ifndef LW_MT_TILE_WORDS
+#define LW_MT_TILE_WORDS (48L << 20)  // words of the tile buffer (192 MB): 140 sub-column runs of a column tile
+#endif
+
 // Masks of chunk columns [mt_c0, mt_c0 + r.ncol) of a call over mt_ncol columns; returns the number of kernel
-// launches, or -1 when a buffer cannot be allocated.
+// launches, or -1 when a buffer cannot be allocated or the jump table cannot be built.
 int launch_mcica_mt(const ColIn& in, const Scratch& s, const RunCfg& r, long mt_ncol, long mt_c0, cudaStream_t st) {
     const long per_col = r.icld == 3 ? 1 : (r.icld >= 4 ? 2L * r.nlay : (long)r.nlay);  // draws per (sub-column, column)
-    const size_t need = (size_t)per_col * r.ncol;
-    if (!g_mt_state && cudaMalloc((void**)&g_mt_state, sizeof(MtState)) != cudaSuccess) return -1;
-    if (need > g_mt_buf_words) {
-        cudaStreamSynchronize(st);
-        if (g_mt_buf) cudaFree(g_mt_buf);
-        g_mt_buf = nullptr; g_mt_buf_words = 0;
-        if (cudaMalloc((void**)&g_mt_buf, need * sizeof(unsigned)) != cudaSuccess) return -1;
-        g_mt_buf_words = need;
+    MtBuffers& m = g_mt;
+    if (!m.seed && cudaMalloc((void**)&m.seed, sizeof(MtState)) != cudaSuccess) return -1;
+    if (!m.run && cudaMalloc((void**)&m.run, NGPT * sizeof(MtState)) != cudaSuccess) return -1;
+    if (!m.pow2) {
+        const uint32_t* h = mt_jump_pow2_table();
+        if (!h) return -1;
+        if (cudaMalloc((void**)&m.pow2, (size_t)MTJ_NPOW * 624 * sizeof(unsigned)) != cudaSuccess) return -1;
+        if (cudaMemcpy(m.pow2, h, (size_t)MTJ_NPOW * 624 * sizeof(unsigned), cudaMemcpyHostToDevice) != cudaSuccess) return -1;
     }
-    mt_seed_kernel<<<1, 1, 0, st>>>(g_mt_state, (unsigned)r.permuteseed);
-    int launches = 1;
-    for (int sc = 0; sc < NGPT; ++sc) {
-        // the chunk's run of sub-column sc starts (sc * mt_ncol + mt_c0) * per_col words into the stream
-        const long skip = sc == 0 ? mt_c0 * per_col : (mt_ncol - r.ncol) * per_col;
-        mt_fill_kernel<<<1, 256, 0, st>>>(g_mt_state, g_mt_buf, skip, (long)need);
-        mcica_mt_apply_kernel<<<nblk(r.ncol, 128), 128, 0, st>>>(in, s, r, g_mt_buf, sc);
+    // column tile: all 140 runs of it fit the buffer
+    long tile = LW_MT_TILE_WORDS / (NGPT * per_col);
+    tile = tile < 128 ? 128 : (tile / 128) * 128;
+    if (tile > r.ncol) tile = r.ncol;
+    const size_t stride = (size_t)tile * per_col;
+    const size_t need = stride * NGPT;
+    if (need > m.buf_words) {
+        cudaStreamSynchronize(st);
+        if (m.buf) cudaFree(m.buf);
+        m.buf = nullptr; m.buf_words = 0;
+        if (cudaMalloc((void**)&m.buf, need * sizeof(unsigned)) != cudaSuccess) return -1;
+        m.buf_words = need;
+    }
+    const size_t jsmem = (size_t)MTJ_XS * sizeof(unsigned);
+    if (!m.jump_attr) {
+        if (cudaFuncSetAttribute(mt_jump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jsmem) != cudaSuccess) return -1;
+        m.jump_attr = true;
+    }
+    cudaMemsetAsync(s.mask, 0, (size_t)r.nlay * 5 * s.pitch * sizeof(unsigned), st);
+    mt_seed_kernel<<<1, 1, 0, st>>>(m.seed, (unsigned)r.permuteseed);
+    // generator sc starts at the chunk's first column of sub-column sc
+    mt_jump_kernel<<<NGPT, 640, jsmem, st>>>(m.seed, m.run, m.pow2, (unsigned long long)(mt_c0 * per_col),
+                                             (unsigned long long)(mt_ncol * per_col));
+    int launches = 3;
+    for (long t0 = 0; t0 < r.ncol; t0 += tile) {
+        const int tn = (int)((r.ncol - t0) < tile ? (r.ncol - t0) : tile);
+        mt_fill_kernel<<<NGPT, 256, 0, st>>>(m.run, m.buf, (long)stride, 0L, (long)tn * per_col);
+        mcica_mt_apply_kernel<<<dim3((unsigned)nblk(tn, 128), NGPT), 128, 0, st>>>(in, s, r, m.buf, (long)stride, (int)t0, tn);
         launches += 2;
     }
     mcica_finish_kernel<<<nblk(r.ncol, 128), 128, 0, st>>>(in, s, r);
@@ -566,9 +653,34 @@ struct KissJump {
     unsigned m2[NGPT][32];         // columns of the xorshift matrix power
 };
 constexpr unsigned KISS_M3 = 18000u * 65536u - 1u, KISS_M4 = 30903u * 65536u - 1u;
+// n-step jumps for n = 1 .. LW_MAXLAY (seed-independent, built once per device): a run of n cloud-free layers draws n
+// numbers that cannot reach the mask (icld 1: every layer's draw is compared with 1 - cldfrac = 1 only; icld 2: the
+// value a clear layer hands upward is never kept, as prev > 1 - 0 cannot hold), so the stream is stepped over them
+struct KissRun {
+    unsigned a1[LW_MAXLAY + 1], c1[LW_MAXLAY + 1];
+    unsigned p3[LW_MAXLAY + 1], p4[LW_MAXLAY + 1];  // a^(n-1) mod m
+    unsigned m2[LW_MAXLAY + 1][32];
+};
+#ifndef LW_KISS_JUMP_MIN
+#define LW_KISS_JUMP_MIN 8  // shorter clear runs are stepped draw by draw (a jump costs about as much as 6 steps)
+#endif
+__device__ __forceinline__ void kiss_jump(Kiss& k, const KissRun* __restrict__ R, int n) {
+    k.s1 = R->a1[n] * k.s1 + R->c1[n];
+    unsigned y = 0;
+    const unsigned z2 = k.s2;
+#pragma unroll 8
+    for (int b = 0; b < 32; ++b) y ^= ((z2 >> b) & 1u) ? R->m2[n][b] : 0u;
+    k.s2 = y;
+    unsigned t3 = 18000u * (k.s3 & 65535u) + (k.s3 >> 16);
+    unsigned t4 = 30903u * (k.s4 & 65535u) + (k.s4 >> 16);
+    if (t3 != KISS_M3) t3 = (unsigned)(((unsigned long long)R->p3[n] * t3) % KISS_M3);
+    if (t4 != KISS_M4) t4 = (unsigned)(((unsigned long long)R->p4[n] * t4) % KISS_M4);
+    k.s3 = t3; k.s4 = t4;
+}
 
-__global__ void __launch_bounds__(160) mcica_kiss_par_kernel(ColIn in, Scratch s, RunCfg r, const KissJump* __restrict__ J) {
-    extern __shared__ unsigned mk_words[];  // nlay x 5 mask words, then 1 word: cloud top
+__global__ void __launch_bounds__(160) mcica_kiss_par_kernel(ColIn in, Scratch s, RunCfg r, const KissJump* __restrict__ J,
+                                                             const KissRun* __restrict__ R) {
+    extern __shared__ unsigned mk_words[];  // nlay x 5 mask words, 1 word: cloud top, 1 word: highest layer with cldfrac > 0
     const int i = blockIdx.x;
     const long ci = r.c0 + i;
     const int nlay = r.nlay;
@@ -584,7 +696,19 @@ __global__ void __launch_bounds__(160) mcica_kiss_par_kernel(ColIn in, Scratch s
         for (int k = threadIdx.x; k < nlay * 5; k += blockDim.x) s.mask[(long)k * P + i] = 0u;
         return;
     }
-    if (threadIdx.x == 0) mk_words[nlay * 5] = 0u;
+    if (threadIdx.x == 0) { mk_words[nlay * 5] = 0u; mk_words[nlay * 5 + 1] = 0u; }
+    __syncthreads();
+    // icld 1 / 2: layers above the highest one with a cloud fraction draw nothing that matters, and (R given) runs of
+    // cloud-free layers below it are jumped over
+    const bool sparse = (icld == 1 || icld == 2) && R != nullptr;
+    if (sparse) {
+        unsigned top = 0u;
+        for (int l = threadIdx.x; l < nlay; l += blockDim.x)
+            if (in.cldfrac[ci + in.ld * l] >= cldmin) top = (unsigned)(l + 1);
+        if (top) atomicMax(&mk_words[nlay * 5 + 1], top);
+        __syncthreads();
+    }
+    const int lend = sparse ? (int)mk_words[nlay * 5 + 1] : nlay;
     Kiss k;
     if (act) {
         const double p3 = in.play[ci + 2 * in.ld] * 1.e2, p4 = in.play[ci + 3 * in.ld] * 1.e2;
@@ -613,9 +737,21 @@ __global__ void __launch_bounds__(160) mcica_kiss_par_kernel(ColIn in, Scratch s
     double rmax = 0.;
     if (icld == 3 && act) rmax = k.next();
     double cfm = 0.;
-    for (int l = 0; l < nlay; ++l) {
+    int l = 0;
+    while (l < lend) {
         double cf = in.cldfrac[ci + in.ld * l];
         if (cf < cldmin) cf = 0.;
+        if (sparse && cf == 0.) {  // uniform over the CTA: a run of n cloud-free layers
+            int n = 1;
+            while (l + n < lend && in.cldfrac[ci + in.ld * (l + n)] < cldmin) ++n;
+            if (n >= LW_KISS_JUMP_MIN) kiss_jump(k, R, n);
+            else for (int j = 0; j < n; ++j) k.step();
+            if (lane == 0) for (int j = 0; j < n; ++j) mk_words[(l + j) * 5 + w] = 0u;
+            prev = 0.;  // any value < 1: the layer above a clear one never keeps it
+            cfm = 0.;
+            l += n;
+            continue;
+        }
         double x;
         if (icld == 3) {
             x = rmax;
@@ -632,7 +768,9 @@ __global__ void __launch_bounds__(160) mcica_kiss_par_kernel(ColIn in, Scratch s
         cfm = cf;
         const unsigned word = __ballot_sync(0xffffffffu, act && (x >= 1. - cf));
         if (lane == 0) mk_words[l * 5 + w] = word;
+        ++l;
     }
+    if (lane == 0) for (int q = lend; q < nlay; ++q) mk_words[q * 5 + w] = 0u;
     __syncthreads();
     // per-layer cloud flag (icldlyr), column cloud top, cldprmc input validation, mask write-out
     for (int l = threadIdx.x; l < nlay; l += blockDim.x) {
@@ -784,6 +922,28 @@ static const KissJump* kiss_jump_table(int permuteseed, long draws, cudaStream_t
     cudaStreamSynchronize(st);
     g_kj.key_seed = permuteseed; g_kj.key_draws = draws;
     return g_kj.dev;
+}
+
+// seed-independent n-step jump table of the sparse path, one per device
+static const KissRun* kiss_run_table(cudaStream_t st) {
+    static KissRun* dev[16] = {};
+    KissRun*& d = dev[cur_dev_kj()];
+    if (d) return d;
+    static KissRun h;
+    KissMap cur = kiss_identity();          // n - 1 steps
+    const KissMap one = kiss_one();
+    for (int n = 1; n <= LW_MAXLAY; ++n) {
+        h.p3[n] = (unsigned)cur.p3; h.p4[n] = (unsigned)cur.p4;
+        cur = kiss_compose(one, cur);       // n steps
+        h.a1[n] = cur.a1; h.c1[n] = cur.c1;
+        for (int b = 0; b < 32; ++b) h.m2[n][b] = cur.m2[b];
+    }
+    h.a1[0] = 1u; h.c1[0] = 0u; h.p3[0] = 1u; h.p4[0] = 1u;
+    for (int b = 0; b < 32; ++b) h.m2[0][b] = 1u << b;
+    if (cudaMalloc((void**)&d, sizeof(KissRun)) != cudaSuccess) { d = nullptr; return nullptr; }
+    if (cudaMemcpyAsync(d, &h, sizeof(KissRun), cudaMemcpyHostToDevice, st) != cudaSuccess) return nullptr;
+    cudaStreamSynchronize(st);
+    return d;
 }
 
 // Cloud flags for the strict rrtmg_lw() entry: one warp scans the 140 sub-column fractions of a
@@ -996,12 +1156,15 @@ void launch_cldoptics(const ColIn& in, const Scratch& s, const RunCfg& r, cudaSt
 void launch_prep(const ColIn& in, const Scratch& s, const RunCfg& r, cudaStream_t st) {
     prep_kernel<<<nblk(r.ncol, 128), 128, 0, st>>>(in, s, r);
 }
+int g_kiss_sparse = 1;  // set_option("kiss_sparse", 0) draws every number (the round-1 kernel), for A/B timing
+void set_kiss_sparse(int on) { g_kiss_sparse = on; }
 void launch_mcica_kiss(const ColIn& in, const Scratch& s, const RunCfg& r, cudaStream_t st) {
     const long draws = r.icld == 3 ? 1 : (r.icld >= 4 ? 2L * r.nlay : (long)r.nlay);
     const KissJump* J = kiss_jump_table(r.permuteseed, draws, st);
     if (!J) { mcica_kiss_kernel<<<nblk(r.ncol, 128), 128, 0, st>>>(in, s, r); return; }
-    const size_t smem = ((size_t)r.nlay * 5 + 1) * sizeof(unsigned);
-    mcica_kiss_par_kernel<<<r.ncol, 160, smem, st>>>(in, s, r, J);
+    const size_t smem = ((size_t)r.nlay * 5 + 2) * sizeof(unsigned);
+    const KissRun* R = g_kiss_sparse ? kiss_run_table(st) : nullptr;
+    mcica_kiss_par_kernel<<<r.ncol, 160, smem, st>>>(in, s, r, J, R);
 }
 // dst[e + w*(i + ldd*k)] = (float) src[e + w*(c0 + i + lds*k)]   for e < w, i < ncol, k < nrows
 __global__ void cvt_kernel(const double* __restrict__ src, float* __restrict__ dst, int w, long lds, long ldd, long c0,

@@ -18,6 +18,9 @@ void launch_mcica_kiss(const ColIn&, const Scratch&, const RunCfg&, cudaStream_t
 // mt_ncol columns; returns the kernels launched or -1 (allocation failure)
 int launch_mcica_mt(const ColIn&, const Scratch&, const RunCfg&, long mt_ncol, long mt_c0, cudaStream_t);
 void free_mt_buffers();
+#define MTJ_NPOW 44  // jump distances below 2^44 words (140 sub-columns x 2^24 columns x 2 x 640 layers < 2^43)
+const unsigned* mt_jump_pow2_table();  // lw_mtjump.cpp: x^(2^b) mod phi(MT19937), MTJ_NPOW x 624 words; NULL on failure
+int mt_jump_selftest();                // host-only check of the jump algebra against plain stepping
 // FP32 mode: float copies of the caller arrays the band kernels read, into Scratch::inf; fills *out with pointers
 // biased by the chunk's first column (the kernels index caller arrays with c0 + i); returns kernels launched
 int launch_cvt_inputs(const ColIn&, const Scratch&, const RunCfg&, int cloudy, int inflag, ColInF* out, cudaStream_t);
@@ -48,6 +51,7 @@ LW_DECL_TU(0) LW_DECL_TU(1) LW_DECL_TU(2) LW_DECL_TU(3) LW_DECL_TU(4) LW_DECL_TU
 #define LW_TAUMOL_MINB 4  // resident CTAs per SM the (column, layer) taumol kernel is compiled for
 #endif
 #define LW_NUM_SWEEP_TUS 6
+void set_kiss_sparse(int on);  // KISS generator: step over the draws of cloud-free layers (default on)
 void launch_colprep(const ColIn&, const Scratch&, const RunCfg&, cudaStream_t);
 void launch_cldoptics(const ColIn&, const Scratch&, const RunCfg&, cudaStream_t);  // needs the masks and secdiff
 void launch_taumol(const ColIn&, const Scratch&, const RunCfg&, cudaStream_t);

@@ -128,3 +128,12 @@ def test_fp32_variant_is_generated_from_the_same_source():
     code = "\n".join(l.split("//")[0] for l in body.split("\n"))
     assert not re.search(r"\bdouble2?\b", code), "double-typed code left in the float variant"
     assert "acc_t" in code and "ld.global.nc.v4.f32" in body
+
+
+def test_mersenne_twister_jump_ahead_matches_stepping():
+    """The GF(2) jump-ahead behind the parallel irng = 1 generator (lw_mtjump.cpp: characteristic polynomial of
+    MT19937 by Berlekamp-Massey, x^(2^b) mod phi by squaring, one dot-product pass per set bit of the distance) lands on
+    the same 624-word state as stepping the generator of src/mcica_random_numbers.f90:134-152 n times, for n up to
+    10^6 (host-only check of the table the device kernel uses)."""
+    from rrtmg_lw_b200 import api
+    assert api.lib().rrtmg_lw_b200_mt_jump_selftest() == 0

@@ -531,3 +531,30 @@ def test_parity_batches_cover_every_branch(gpu, oracle):
     assert (c["half"] >= 100).all(), c["half"].tolist()
     assert (c["adjfac"] >= 100).all(), dict(zip(oracle.BRANCH_ADJFAC_SITES, c["adjfac"].tolist()))
     assert (c["cloudy"] >= 100).all() and (c["clear"] >= 100).all(), (c["cloudy"], c["clear"])
+
+
+@pytest.mark.parametrize("icld", [1, 2])
+def test_kiss_stepping_over_clear_layers_is_bit_exact(gpu, oracle, icld):
+    """The KISS generator stops at the highest layer with a cloud fraction and jumps over runs of cloud-free layers
+    (closed-form n-step maps of the four component generators); the masks must equal the oracle's, which draws every
+    number, and the library's own exhaustive mode -- on columns with clear runs of every length from 1 to > 100."""
+    b = synth.make_batch(700, 137, cloudy=True, seed=77)
+    g = torch.Generator().manual_seed(9)
+    cf = torch.zeros(137, 700, dtype=torch.float64)
+    for i in range(700):
+        l = int(torch.randint(0, 4, (1,), generator=g))
+        while l < 137:
+            n = int(torch.randint(1, 4, (1,), generator=g))
+            cf[l:l + n, i] = torch.rand(min(n, 137 - l), generator=g, dtype=torch.float64)
+            l += n + 1 + (i % 120)  # clear run of 1 + i % 120 layers
+    b.cldfrac[:] = cf
+    ref = oracle.mcica_subcol_lw(b, icld, permuteseed=140, irng=0)
+    got = driver.run_mcica_subcol(b, icld, permuteseed=140, device="cuda:0")
+    gpu.set_option("kiss_sparse", 0)
+    try:
+        full = driver.run_mcica_subcol(b, icld, permuteseed=140, device="cuda:0")
+    finally:
+        gpu.set_option("kiss_sparse", 1)
+    assert ref["cldfmcl"].sum() > 1000
+    assert np.array_equal(_np(got["cldfmcl"]), ref["cldfmcl"])
+    assert torch.equal(got["cldfmcl"], full["cldfmcl"])
