@@ -170,8 +170,10 @@ int rrtmg_lw_b200_set_chunk(int max_columns);
  *   cldprmc + rtrnmc sweep kernels with one thread per (column, band group) that stream the 8-byte layer optical
  *   depths; 2 = fused per-band kernels (one thread per (column, band), 16-byte sweep state; the optional FP32 mode
  *   runs on these).
- * "sweep_groups": 1 (default) = sweep kernels over band groups {1,2} {3} {4} {5} {6,7} {8,9} {10-12} {13-16};
- *   0 = one sweep kernel per band.
+ * "sweep_groups": 0 (default) = one sweep kernel per band (see "tail_group"); 1 = sweep kernels over the band groups
+ *   {1,2} {3} {4} {5} {6,7} {8,9} {10-12} {13-16} (fewer launches and flux slots, more registers per thread: slower).
+ * "tail_group": 1 (default) = bands 13-16 (10 g-points together) run as one sweep kernel when the band range holds
+ *   all four; 0 = one kernel each.
  * "band_lo" / "band_hi": band range istart..iend of the following runs (default 1..16): only those bands enter the
  *   flux sums, as in the column-mode program's per-band output (src/rrtmg_lw.1col.f90:463-467); two-phase path.
  * "concurrency": 1 (default) = independent kernels of a pass run on side streams of the library (McICA generator and

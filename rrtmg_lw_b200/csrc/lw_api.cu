@@ -39,6 +39,7 @@ struct Ctx {
     static constexpr int NSIDE = 3;
     cudaStream_t side[NSIDE] = {};
     cudaEvent_t e_fork = nullptr, e_colprep = nullptr, e_t = nullptr, e_cld = nullptr, e_side[NSIDE] = {};
+    int tail_group = 1;       // set_option("tail_group", 0): bands 13-16 as four sweep kernels instead of one
     int concurrency = 1;      // set_option("concurrency", 0) keeps every kernel on the caller's stream
     long out_ld = 0;          // set_option("out_ld", n): column extent of the OUTPUT arrays of device-pointer calls (0 = ld)
     long cap_cols = 0;
@@ -366,11 +367,18 @@ int run_device(Mode mode, int ncol, int nlay, int icld, int idrv, int inflag, in
                 for (const auto& g : kSweepGroups)
                     if (!sweep(g[0], g[1])) return RRTMG_LW_ERR_ARG;
             } else {
-                // longest kernels first when they are dealt over several streams (bands by g-point count)
+                // longest kernels first when they are dealt over several streams (bands by g-point count).  Bands 13-16
+                // (4 + 2 + 2 + 2 g-points) go as one kernel when the run holds all four: a band's sweep has a fixed cost per
+                // column (temperatures, mask words, its flux slot) that a 2-g-point band does not amortise.
                 const int order[NBND] = {3, 5, 4, 2, 7, 9, 1, 6, 8, 11, 12, 10, 13, 14, 15, 16};
+                const bool tail4 = G.tail_group != 0 && cld != CLD_GRID && b_lo <= 13 && b_hi == NBND;
                 for (int k = 0; k < NBND; ++k) {
                     const int b = conc ? order[k] : k + 1;
                     if (b < b_lo || b > b_hi) continue;
+                    if (tail4 && b >= 13) {
+                        if (b == 13 && !sweep(13, 4)) return RRTMG_LW_ERR_ARG;
+                        continue;
+                    }
                     if (!sweep(b, 1)) return RRTMG_LW_ERR_ARG;
                 }
             }
@@ -1130,6 +1138,11 @@ extern "C" int rrtmg_lw_b200_set_option(const char* name, int value) {
     if (std::strcmp(name, "out_ld") == 0) {
         if (value < 0) return RRTMG_LW_ERR_ARG;
         G.out_ld = value;
+        return RRTMG_LW_OK;
+    }
+    if (std::strcmp(name, "tail_group") == 0) {
+        if (value != 0 && value != 1) return RRTMG_LW_ERR_ARG;
+        G.tail_group = value;
         return RRTMG_LW_OK;
     }
     if (std::strcmp(name, "kiss_sparse") == 0) {

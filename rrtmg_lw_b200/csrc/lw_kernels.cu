@@ -644,8 +644,9 @@ int launch_mcica_mt(const ColIn& in, const Scratch& s, const RunCfg& r, long mt_
 //   s3  multiply-with-carry, a = 18000 (low/high half)   x -> a x mod (a 2^16 - 1)
 //   s4  multiply-with-carry, a = 30903                   x -> a x mod (a 2^16 - 1)
 // The host tabulates the 140 jumps once per (permuteseed, draws_per_subcolumn) (KissJump); the
-// numbers drawn are bit-identical to the sequential stream.  One CTA = one column, one warp = 32
-// sub-columns, so a layer's 32 cloud bits are one __ballot_sync.
+// numbers drawn are bit-identical to the sequential stream.  One CTA = 8 consecutive columns taken one after the
+// other (their mask words then leave as whole 32-byte sectors), one warp = 32 sub-columns, so a layer's 32 cloud bits
+// are one __ballot_sync.
 struct KissJump {
     unsigned a1[NGPT], c1[NGPT];   // s1_n = a1 * s1_0 + c1
     unsigned p3[NGPT], p4[NGPT];   // a^(n-1) mod m (applied after one explicit step; n = 0 -> unused)
@@ -678,110 +679,137 @@ __device__ __forceinline__ void kiss_jump(Kiss& k, const KissRun* __restrict__ R
     k.s3 = t3; k.s4 = t4;
 }
 
+constexpr int KISS_CPB = 8;  // columns per CTA: a CTA's mask words of one (layer, word) are one 32-byte sector
 __global__ void __launch_bounds__(160) mcica_kiss_par_kernel(ColIn in, Scratch s, RunCfg r, const KissJump* __restrict__ J,
                                                              const KissRun* __restrict__ R) {
-    extern __shared__ unsigned mk_words[];  // nlay x 5 mask words, 1 word: cloud top, 1 word: highest layer with cldfrac > 0
-    const int i = blockIdx.x;
-    const long ci = r.c0 + i;
+    extern __shared__ unsigned mk_sm[];
     const int nlay = r.nlay;
+    const int W5 = nlay * 5;
+    unsigned* words = mk_sm;                                     // KISS_CPB x nlay x 5 mask words
+    int* lst = reinterpret_cast<int*>(mk_sm + KISS_CPB * W5);    // KISS_CPB x nlay: the layers a column draws at, ascending
+    int* nl = lst + KISS_CPB * nlay;                             // KISS_CPB: their number
+    unsigned* top = reinterpret_cast<unsigned*>(nl + KISS_CPB);  // KISS_CPB: cloud top
+    const int i0 = blockIdx.x * KISS_CPB;
     const long P = s.pitch;
     const int icld = r.icld;
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
     const int sc = w * 32 + lane;
     const bool act = sc < NGPT;
     const double cldmin = 1.0e-20;
-    const double p1 = in.play[ci] * 1.e2, p2 = in.play[ci + in.ld] * 1.e2;
-    if (p1 < p2) {  // uniform over the CTA: the reference STOPs (mcica:465); the column is left cloud-free
-        if (threadIdx.x == 0) { raise(s, 4, ci, 1); s.ctop[i] = 0; }
-        for (int k = threadIdx.x; k < nlay * 5; k += blockDim.x) s.mask[(long)k * P + i] = 0u;
-        return;
-    }
-    if (threadIdx.x == 0) { mk_words[nlay * 5] = 0u; mk_words[nlay * 5 + 1] = 0u; }
-    __syncthreads();
-    // icld 1 / 2: layers above the highest one with a cloud fraction draw nothing that matters, and (R given) runs of
-    // cloud-free layers below it are jumped over
+    // icld 1 / 2 (R given): only layers with a cloud fraction draw numbers that can reach the mask; the stream is
+    // stepped (short runs) or jumped (long runs) over the draws of the cloud-free layers between them
     const bool sparse = (icld == 1 || icld == 2) && R != nullptr;
-    if (sparse) {
-        unsigned top = 0u;
-        for (int l = threadIdx.x; l < nlay; l += blockDim.x)
-            if (in.cldfrac[ci + in.ld * l] >= cldmin) top = (unsigned)(l + 1);
-        if (top) atomicMax(&mk_words[nlay * 5 + 1], top);
-        __syncthreads();
-    }
-    const int lend = sparse ? (int)mk_words[nlay * 5 + 1] : nlay;
-    Kiss k;
-    if (act) {
-        const double p3 = in.play[ci + 2 * in.ld] * 1.e2, p4 = in.play[ci + 3 * in.ld] * 1.e2;
-        const unsigned z1 = (unsigned)(int)((p1 - (double)(int)p1) * 1000000000.0);
-        const unsigned z2 = (unsigned)(int)((p2 - (double)(int)p2) * 1000000000.0);
-        const unsigned z3 = (unsigned)(int)((p3 - (double)(int)p3) * 1000000000.0);
-        const unsigned z4 = (unsigned)(int)((p4 - (double)(int)p4) * 1000000000.0);
-        k.s1 = J->a1[sc] * z1 + J->c1[sc];
-        unsigned y = 0;
-#pragma unroll 8
-        for (int b = 0; b < 32; ++b) y ^= ((z2 >> b) & 1u) ? J->m2[sc][b] : 0u;
-        k.s2 = y;
-        if (J->n[sc] == 0u) {
-            k.s3 = z3; k.s4 = z4;
-        } else {
-            unsigned t3 = 18000u * (z3 & 65535u) + (z3 >> 16);
-            unsigned t4 = 30903u * (z4 & 65535u) + (z4 >> 16);
-            if (t3 != KISS_M3) t3 = (unsigned)(((unsigned long long)J->p3[sc] * t3) % KISS_M3);
-            if (t4 != KISS_M4) t4 = (unsigned)(((unsigned long long)J->p4[sc] * t4) % KISS_M4);
-            k.s3 = t3; k.s4 = t4;
+    for (int k = tid; k < KISS_CPB * W5; k += blockDim.x) words[k] = 0u;
+    if (tid < KISS_CPB) { nl[tid] = 0; top[tid] = 0u; }
+    __syncthreads();
+    for (int c = w; c < KISS_CPB; c += 5) {  // one warp lists a column's drawing layers
+        const int i = i0 + c;
+        if (i >= r.ncol) continue;
+        const long ci = r.c0 + i;
+        int cnt = 0;
+        for (int l0 = 0; l0 < nlay; l0 += 32) {
+            const int l = l0 + lane;
+            const bool on = l < nlay && (!sparse || in.cldfrac[ci + in.ld * l] >= cldmin);
+            const unsigned m = __ballot_sync(0xffffffffu, on);
+            if (on) lst[c * nlay + cnt + __popc(m & ((1u << lane) - 1u))] = l;
+            cnt += __popc(m);
         }
-    } else {
-        k.s1 = k.s2 = k.s3 = k.s4 = 0u;
+        if (lane == 0) nl[c] = cnt;
     }
-    double prev = 0.;
-    double rmax = 0.;
-    if (icld == 3 && act) rmax = k.next();
-    double cfm = 0.;
-    int l = 0;
-    while (l < lend) {
-        double cf = in.cldfrac[ci + in.ld * l];
-        if (cf < cldmin) cf = 0.;
-        if (sparse && cf == 0.) {  // uniform over the CTA: a run of n cloud-free layers
-            int n = 1;
-            while (l + n < lend && in.cldfrac[ci + in.ld * (l + n)] < cldmin) ++n;
-            if (n >= LW_KISS_JUMP_MIN) kiss_jump(k, R, n);
-            else for (int j = 0; j < n; ++j) k.step();
-            if (lane == 0) for (int j = 0; j < n; ++j) mk_words[(l + j) * 5 + w] = 0u;
-            prev = 0.;  // any value < 1: the layer above a clear one never keeps it
-            cfm = 0.;
-            l += n;
+    __syncthreads();
+    for (int c = 0; c < KISS_CPB; ++c) {
+        const int i = i0 + c;
+        if (i >= r.ncol) break;
+        const long ci = r.c0 + i;
+        const double p1 = in.play[ci] * 1.e2, p2 = in.play[ci + in.ld] * 1.e2;
+        if (p1 < p2) {  // the reference STOPs (mcica:465); the column is left cloud-free
+            if (tid == 0) raise(s, 4, ci, 1);
             continue;
         }
-        double x;
-        if (icld == 3) {
-            x = rmax;
-        } else {
-            x = k.next();
-            if (icld >= 4) {
-                const double x2 = k.next();
-                if (l > 0 && x2 < in.alpha[ci + in.ld * l]) x = prev;
-            } else if (icld == 2 && l > 0) {
-                if (prev > 1. - cfm) x = prev; else x = x * (1. - cfm);
+        Kiss k;
+        if (act) {
+            const double p3 = in.play[ci + 2 * in.ld] * 1.e2, p4 = in.play[ci + 3 * in.ld] * 1.e2;
+            const unsigned z1 = (unsigned)(int)((p1 - (double)(int)p1) * 1000000000.0);
+            const unsigned z2 = (unsigned)(int)((p2 - (double)(int)p2) * 1000000000.0);
+            const unsigned z3 = (unsigned)(int)((p3 - (double)(int)p3) * 1000000000.0);
+            const unsigned z4 = (unsigned)(int)((p4 - (double)(int)p4) * 1000000000.0);
+            k.s1 = J->a1[sc] * z1 + J->c1[sc];
+            unsigned y = 0;
+#pragma unroll 8
+            for (int b = 0; b < 32; ++b) y ^= ((z2 >> b) & 1u) ? J->m2[sc][b] : 0u;
+            k.s2 = y;
+            if (J->n[sc] == 0u) {
+                k.s3 = z3; k.s4 = z4;
+            } else {
+                unsigned t3 = 18000u * (z3 & 65535u) + (z3 >> 16);
+                unsigned t4 = 30903u * (z4 & 65535u) + (z4 >> 16);
+                if (t3 != KISS_M3) t3 = (unsigned)(((unsigned long long)J->p3[sc] * t3) % KISS_M3);
+                if (t4 != KISS_M4) t4 = (unsigned)(((unsigned long long)J->p4[sc] * t4) % KISS_M4);
+                k.s3 = t3; k.s4 = t4;
             }
+        } else {
+            k.s1 = k.s2 = k.s3 = k.s4 = 0u;
         }
-        prev = x;
-        cfm = cf;
-        const unsigned word = __ballot_sync(0xffffffffu, act && (x >= 1. - cf));
-        if (lane == 0) mk_words[l * 5 + w] = word;
-        ++l;
+        double prev = 0., rmax = 0., cfm = 0.;
+        if (icld == 3 && act) rmax = k.next();
+        const int n_draw = nl[c];
+        int lprev = -1;
+        for (int q = 0; q < n_draw; ++q) {
+            const int l = lst[c * nlay + q];
+            const int gap = l - lprev - 1;  // cloud-free layers stepped over (sparse only; uniform over the CTA)
+            if (gap > 0) {
+                if (gap >= LW_KISS_JUMP_MIN) kiss_jump(k, R, gap);
+                else for (int j = 0; j < gap; ++j) k.step();
+                prev = 0.;  // any value < 1: the layer above a clear one never keeps it (prev > 1 - 0 cannot hold)
+                cfm = 0.;
+            }
+            lprev = l;
+            double cf = in.cldfrac[ci + in.ld * l];
+            if (cf < cldmin) cf = 0.;
+            double x;
+            if (icld == 3) {
+                x = rmax;
+            } else {
+                x = k.next();
+                if (icld >= 4) {
+                    const double x2 = k.next();
+                    if (l > 0 && x2 < in.alpha[ci + in.ld * l]) x = prev;
+                } else if (icld == 2 && l > 0) {
+                    if (prev > 1. - cfm) x = prev; else x = x * (1. - cfm);
+                }
+            }
+            prev = x;
+            cfm = cf;
+            const unsigned word = __ballot_sync(0xffffffffu, act && (x >= 1. - cf));
+            if (lane == 0) words[c * W5 + l * 5 + w] = word;
+        }
     }
-    if (lane == 0) for (int q = lend; q < nlay; ++q) mk_words[q * 5 + w] = 0u;
     __syncthreads();
-    // per-layer cloud flag (icldlyr), column cloud top, cldprmc input validation, mask write-out
-    for (int l = threadIdx.x; l < nlay; l += blockDim.x) {
-        unsigned any = 0;
+    // per-layer cloud flag (icldlyr, bit 31 of word 4), column cloud top, cldprmc input validation, mask write-out:
+    // the KISS_CPB columns' words of a (layer, word) leave as one 32-byte store
+    for (int l = tid; l < nlay; l += blockDim.x) {
+        unsigned any[KISS_CPB];
 #pragma unroll
-        for (int q = 0; q < 5; ++q) any |= mk_words[l * 5 + q];
+        for (int c = 0; c < KISS_CPB; ++c) {
+            unsigned a = 0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) s.mask[((long)l * 5 + q) * P + i] = mk_words[l * 5 + q];
-        s.mask[((long)l * 5 + 4) * P + i] = mk_words[l * 5 + 4] | (any ? 0x80000000u : 0u);
-        if (any) {
-            atomicMax(&mk_words[nlay * 5], (unsigned)(l + 1));
+            for (int q = 0; q < 5; ++q) a |= words[c * W5 + l * 5 + q];
+            any[c] = a;
+        }
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            unsigned v[KISS_CPB];
+#pragma unroll
+            for (int c = 0; c < KISS_CPB; ++c) v[c] = words[c * W5 + l * 5 + q] | ((q == 4 && any[c]) ? 0x80000000u : 0u);
+            uint4* dst = reinterpret_cast<uint4*>(s.mask + ((long)l * 5 + q) * P + i0);
+            dst[0] = make_uint4(v[0], v[1], v[2], v[3]);
+            dst[1] = make_uint4(v[4], v[5], v[6], v[7]);
+        }
+#pragma unroll
+        for (int c = 0; c < KISS_CPB; ++c) {
+            if (!any[c]) continue;
+            const long ci = r.c0 + i0 + c;
+            atomicMax(&top[c], (unsigned)(l + 1));
             const long a = ci + in.ld * l;
             const double ciwp = in.ciwp[a], clwp = in.clwp[a];
             bool taubig = false;
@@ -804,7 +832,7 @@ __global__ void __launch_bounds__(160) mcica_kiss_par_kernel(ColIn in, Scratch s
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) s.ctop[i] = (int)mk_words[nlay * 5];
+    if (tid < KISS_CPB && i0 + tid < r.ncol) s.ctop[i0 + tid] = (int)top[tid];
 }
 
 // host side of the jumps ---------------------------------------------------------------------
@@ -1162,9 +1190,17 @@ void launch_mcica_kiss(const ColIn& in, const Scratch& s, const RunCfg& r, cudaS
     const long draws = r.icld == 3 ? 1 : (r.icld >= 4 ? 2L * r.nlay : (long)r.nlay);
     const KissJump* J = kiss_jump_table(r.permuteseed, draws, st);
     if (!J) { mcica_kiss_kernel<<<nblk(r.ncol, 128), 128, 0, st>>>(in, s, r); return; }
-    const size_t smem = ((size_t)r.nlay * 5 + 2) * sizeof(unsigned);
+    const size_t smem = ((size_t)KISS_CPB * r.nlay * 6 + 2 * KISS_CPB) * sizeof(unsigned);
+    if (smem > 48 * 1024) {
+        static size_t attr_d[16] = {};
+        size_t& cur = attr_d[cur_dev_kj()];
+        if (smem > cur) {
+            cudaFuncSetAttribute(mcica_kiss_par_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cur = smem;
+        }
+    }
     const KissRun* R = g_kiss_sparse ? kiss_run_table(st) : nullptr;
-    mcica_kiss_par_kernel<<<r.ncol, 160, smem, st>>>(in, s, r, J, R);
+    mcica_kiss_par_kernel<<<(unsigned)nblk(r.ncol, KISS_CPB), 160, smem, st>>>(in, s, r, J, R);
 }
 // dst[e + w*(i + ldd*k)] = (float) src[e + w*(c0 + i + lds*k)]   for e < w, i < ncol, k < nrows
 __global__ void cvt_kernel(const double* __restrict__ src, float* __restrict__ dst, int w, long lds, long ldd, long c0,
