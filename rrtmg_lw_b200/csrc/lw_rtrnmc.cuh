@@ -251,6 +251,42 @@ __device__ __forceinline__ void cloud_point(const SweepTab& tb, double st, bool 
 }
 
 // ------------------------------------------------------------------------------------------
+// Experiment LW_SWEEP_TMA=1 (rejected variants): a layer's optical depths of the CTA's 128 columns are ONE
+// contiguous run of NGG x 1 KB in phase 1's layout, so instead of 128 threads x NGG / 2 16-byte cp.async one elected
+// thread issues one bulk copy of the TMA unit (cp.async.bulk, completion on an mbarrier with a transaction count) per
+// ring stage; the consumers wait on the barrier's phase.  The price: the copy overwrites every thread's slots, so the
+// stage has to be released by the whole CTA (__syncthreads per layer) where the per-thread cp.async needs no barrier.
+#ifndef LW_SWEEP_TMA
+#define LW_SWEEP_TMA 0
+#endif
+#if LW_SWEEP_TMA
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(b))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LW_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LW_DONE_%=;\n"
+        "bra LW_WAIT_%=;\n"
+        "LW_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(b)),
+        "r"(parity)
+        : "memory");
+}
+#endif
+
 // the sweep kernel of bands B0 .. B0 + NB - 1
 template <int B0, int NB, int CLD, int IDRV, int MINB>
 __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, ColOut out, Scratch s, RunCfg r, const SweepTab tb) {
@@ -258,8 +294,17 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
     using RG = SweepRing<B0, NB>;
     constexpr int NGG = GR::NGG;
     constexpr int G0 = GR::G0;
-    extern __shared__ double ring[];
+    extern __shared__ __align__(128) double ring[];
     const int tid = threadIdx.x;
+#if LW_SWEEP_TMA
+    __shared__ __align__(8) unsigned long long mbar[RG::NST];
+    if (tid == 0) {
+        for (int k = 0; k < RG::NST; ++k) mbar_init(&mbar[k], 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    unsigned mpar = 0u;  // phase parity per stage
+#endif
     const int i_raw = blockIdx.x * blockDim.x + tid;
     // out-of-range threads of the last CTA shadow the last valid column (no early return: keeps all lanes of a warp alive)
     const bool live = i_raw < r.ncol;
@@ -299,16 +344,27 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
             const int l0 = lev - 1;
             const long a = ci + in.ld * l0;
             double* dst = ring + (size_t)stage * RG::SLOTS * SWEEP_THREADS;
+#if LW_SWEEP_TMA
+            if (tid == 0) {  // one bulk copy for the CTA's optical depths of the layer, one for its Planck-fraction etas
+                constexpr unsigned OD_BYTES = NGG * SWEEP_THREADS * sizeof(double);
+                constexpr unsigned PF_BYTES = GR::NPFG * SWEEP_THREADS * sizeof(double);
+                mbar_expect_tx(&mbar[stage], OD_BYTES + PF_BYTES);
+                bulk_g2s(dst, s.od + ((blk_lay0 + l0) * NGPT + G0) * 128, OD_BYTES, &mbar[stage]);
+                if constexpr (GR::NPFG > 0)
+                    bulk_g2s(dst + RG::S_PF * SWEEP_THREADS, s.pfs + ((blk_lay0 + l0) * NPF + GR::PF0) * 128, PF_BYTES, &mbar[stage]);
+            }
+#else
             const double2* od = od_src(l0);
 #pragma unroll
             for (int p = 0; p < NGG / 2; ++p) cp_async_pair(dst + (2 * p) * SWEEP_THREADS + 2 * tid, od + p * 128);
-            cp_async_val(dst + RG::S_TLAY * SWEEP_THREADS + tid, in.tlay + a);
-            cp_async_val(dst + RG::S_TLEV * SWEEP_THREADS + tid, in.tlev + (down ? a : a + in.ld));
             if constexpr (GR::NPFG > 0) {
                 const double* pf = pf_src(l0);
 #pragma unroll
                 for (int k = 0; k < GR::NPFG; ++k) cp_async_val(dst + (RG::S_PF + k) * SWEEP_THREADS + tid, pf + k * 128);
             }
+#endif
+            cp_async_val(dst + RG::S_TLAY * SWEEP_THREADS + tid, in.tlay + a);
+            cp_async_val(dst + RG::S_TLEV * SWEEP_THREADS + tid, in.tlev + (down ? a : a + in.ld));
             if constexpr (CLD != CLD_NONE) {
                 auto di = [&](int k) { return reinterpret_cast<int*>(dst + (RG::S_INT + k / RG::IPS) * SWEEP_THREADS + tid) + (k % RG::IPS); };
                 const unsigned* mw = s.mask + ((long)l0 * 5) * P + i;
@@ -362,6 +418,10 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
         const long idx = (long)l0 * P + i;
         const long a = ci + in.ld * l0;
         cp_wait<RG::NST - 1>();
+#if LW_SWEEP_TMA
+        mbar_wait(&mbar[stage], (mpar >> stage) & 1u);
+        mpar ^= 1u << stage;
+#endif
         acc_t acc_d = 0., acc_dc = 0.;
         int it_lay, it_lev;
         double fr_lay, fr_lev;
@@ -495,6 +555,9 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
             o[0] = acc_d;
             if (CLD != CLD_NONE && ctop > 0) o[128] = acc_dc;
         }
+#if LW_SWEEP_TMA
+        __syncthreads();  // every thread is done with the stage the bulk copy is about to overwrite
+#endif
         issue(stage, lev - RG::NST, true);
         stage = stage + 1 == RG::NST ? 0 : stage + 1;
     }
@@ -505,6 +568,9 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
     acc_t (&radlu)[NGG] = radld;
     acc_t (&radclru)[NGG] = radclrd;
     acc_t d_radlu[IDRV ? NGG : 1], d_radclru[IDRV ? NGG : 1];
+#if LW_SWEEP_TMA
+    __syncthreads();
+#endif
 #pragma unroll
     for (int k = 0; k < RG::NST; ++k) issue(k, 1 + k, false);
     {
@@ -586,6 +652,10 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
         const long idx = (long)l0 * P + i;
         const long a = ci + in.ld * l0;
         cp_wait<RG::NST - 1>();
+#if LW_SWEEP_TMA
+        mbar_wait(&mbar[stage], (mpar >> stage) & 1u);
+        mpar ^= 1u << stage;
+#endif
         acc_t acc_u = 0., acc_uc = 0., acc_du = 0., acc_duc = 0.;
         int it_lay, it_lev;
         double fr_lay, fr_lev;
@@ -703,6 +773,9 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
                 if (CLD != CLD_NONE && ctop > 0) o[640] = acc_duc;
             }
         }
+#if LW_SWEEP_TMA
+        __syncthreads();
+#endif
         issue(stage, lev + RG::NST, false);
         stage = stage + 1 == RG::NST ? 0 : stage + 1;
     }

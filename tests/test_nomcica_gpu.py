@@ -114,7 +114,11 @@ def test_nomcica_host_call_chunks_and_clear_limit(gpu, oracle):
     for k in KEYS:
         assert np.array_equal(_np(dev[k]), got[k]), k
     b.cldfrac[:] = 0.0
-    clear = driver.run_clear_or_strict(b, idrv=1, device="cuda:0")
+    gpu.set_option("tail_group", 0)  # one sweep kernel per band, like the non-McICA path: same summation order
+    try:
+        clear = driver.run_clear_or_strict(b, idrv=1, device="cuda:0")
+    finally:
+        gpu.set_option("tail_group", 1)
     none = driver.run_nomcica(b, icld=2, idrv=1, device="cuda:0")
     gpu.sync()
     for k in KEYS + ("duflx_dt", "duflxc_dt"):
