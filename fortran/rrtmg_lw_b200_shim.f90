@@ -1,14 +1,16 @@
 ! rrtmg_lw_b200_shim.f90 -- thin ISO_C_BINDING layer that keeps the reference's GCM interface
 ! UNCHANGED and routes it to the B200 library (include/rrtmg_lw_b200.h).
 !
-! It provides replacements for three reference modules, with the same module names, public names
+! The shim provides replacements for three reference modules, with the same module names, public names
 ! and dummy-argument lists, so a host GCM relinks without touching its radiation driver:
 !
-!   module rrtmg_lw_init        : rrtmg_lw_ini(cpdair)             src/rrtmg_lw_init.f90:47
-!   module rrtmg_lw_rad         : rrtmg_lw(ncol,nlay,icld,...)     src/rrtmg_lw_rad.f90:99-108
-!   module mcica_subcol_gen_lw  : get_alpha, mcica_subcol_lw       src/mcica_subcol_gen_lw.f90:68,183
+!   module rrtmg_lw_init        : rrtmg_lw_ini(cpdair)             src/rrtmg_lw_init.f90:47            (this file)
+!   module mcica_subcol_gen_lw  : get_alpha, mcica_subcol_lw       src/mcica_subcol_gen_lw.f90:68,183  (this file)
+!   module rrtmg_lw_rad         : rrtmg_lw(ncol,nlay,icld,...)     one of, like the reference's two source files:
+!        rrtmg_lw_b200_shim_rad.f90          McICA sub-column arrays    src/rrtmg_lw_rad.f90:99-108
+!        rrtmg_lw_b200_shim_rad_nomcica.f90  grid-mean cloud arrays     src/rrtmg_lw_rad.nomcica.f90:99-108
 !
-! Build: compile this file INSTEAD OF the reference's rrtmg_lw_init.f90 (its table builders are
+! Build: compile this file and ONE of the two rad files INSTEAD OF the reference's rrtmg_lw_init.f90 (its table builders are
 ! re-done inside the library), rrtmg_lw_rad.f90, mcica_subcol_gen_lw.f90, rrtmg_lw_setcoef.f90,
 ! rrtmg_lw_taumol.f90, rrtmg_lw_cldprmc.f90, rrtmg_lw_rtrnmc.f90, mcica_random_numbers.f90; keep
 ! modules/parkind.f90, modules/rrlw_kg01..16.f90 and the k-data source (rrtmg_lw_k_g.f90 or
@@ -60,6 +62,21 @@
          type(c_ptr), value :: duflx_dt, duflxc_dt, stream
          end function
 
+         integer(c_int) function c_rrtmg_lw_nomcica(ncol, ld, nlay, icld, idrv, play, plev, tlay, tlev, tsfc, &
+               h2ovmr, o3vmr, co2vmr, ch4vmr, n2ovmr, o2vmr, cfc11vmr, cfc12vmr, cfc22vmr, ccl4vmr, emis, &
+               inflglw, iceflglw, liqflglw, cldfr, taucld, cicewp, cliqwp, reice, reliq, tauaer, &
+               uflx, dflx, hr, uflxc, dflxc, hrc, duflx_dt, duflxc_dt, memspace, stream) &
+               bind(C, name='rrtmg_lw_b200_rrtmg_lw_nomcica')
+         import :: c_int, c_double, c_ptr
+         integer(c_int), value :: ncol, ld, nlay, idrv, inflglw, iceflglw, liqflglw, memspace
+         integer(c_int), intent(inout) :: icld
+         real(c_double), intent(in) :: play(*), plev(*), tlay(*), tlev(*), tsfc(*), h2ovmr(*), o3vmr(*), &
+               co2vmr(*), ch4vmr(*), n2ovmr(*), o2vmr(*), cfc11vmr(*), cfc12vmr(*), cfc22vmr(*), ccl4vmr(*), &
+               emis(*), cldfr(*), taucld(*), cicewp(*), cliqwp(*), reice(*), reliq(*), tauaer(*)
+         real(c_double), intent(out) :: uflx(*), dflx(*), hr(*), uflxc(*), dflxc(*), hrc(*)
+         type(c_ptr), value :: duflx_dt, duflxc_dt, stream
+         end function
+
          integer(c_int) function c_mcica_subcol_lw(iplon, ncol, ld, nlay, icld, permuteseed, irng, play, &
                cldfrac, ciwp, clwp, rei, rel, tauc, alpha, cldfmcl, ciwpmcl, clwpmcl, reicmcl, relqmcl, &
                taucmcl, memspace, stream) bind(C, name='rrtmg_lw_b200_mcica_subcol_lw')
@@ -86,6 +103,12 @@
          integer(c_int), value :: code
          end function
 
+         ! the GPU this thread's calls use (one rank per GPU: call once after MPI_Init with the node-local rank)
+         integer(c_int) function c_set_device(device) bind(C, name='rrtmg_lw_b200_set_device')
+         import :: c_int
+         integer(c_int), value :: device
+         end function
+
          ! run-time switches without a reference counterpart (include/rrtmg_lw_b200.h, INTEGRATION.md section 6)
          integer(c_int) function c_set_option(name, value) bind(C, name='rrtmg_lw_b200_set_option')
          import :: c_int, c_char
@@ -105,6 +128,23 @@
       call check(c_set_option('mt_global_ncol'//c_null_char, int(global_ncol, c_int)), 'set_option(mt_global_ncol)')
       call check(c_set_option('mt_col_offset'//c_null_char, int(col_offset, c_int)), 'set_option(mt_col_offset)')
       end subroutine rrtmg_lw_b200_set_mt_block
+
+      subroutine rrtmg_lw_b200_set_device(device)
+      integer, intent(in) :: device
+      call check(c_set_device(int(device, c_int)), 'set_device')
+      end subroutine rrtmg_lw_b200_set_device
+
+      ! The reference also lists inatm (module rrtmg_lw_rad) and generate_stochastic_clouds (module
+      ! mcica_subcol_gen_lw) as public.  Both are per-column internals of its CPU pipeline -- inatm fills one column's
+      ! work arrays for setcoef / taumol, generate_stochastic_clouds is the body of mcica_subcol_lw on Pa pressures --
+      ! whose outputs never leave the device here.  The shim keeps the names (a `use ..., only:` list that mentions
+      ! them still compiles) and stops with this message if a host model really calls one.
+      subroutine internal_only(name)
+      character(len=*), intent(in) :: name
+      write(*,'(a,a,a)') ' ', name, ': internal to the B200 library (the column state stays on the device); '// &
+            'call rrtmg_lw / mcica_subcol_lw instead'
+      error stop 1
+      end subroutine internal_only
 
       ! reference behaviour on these conditions is STOP 'text' (e.g. src/rrtmg_lw_cldprmc.f90:204)
       subroutine check(rc, where)
@@ -346,71 +386,25 @@
       end module rrtmg_lw_init
 
 !------------------------------------------------------------------------------------------------
-      module rrtmg_lw_rad
-      use iso_c_binding
-      use parkind, only : im => kind_im, rb => kind_rb
-      use rrtmg_lw_b200_c
-      implicit none
-      public :: rrtmg_lw
-
-      contains
-
-      subroutine rrtmg_lw &
-            (ncol    ,nlay    ,icld    ,idrv    , &
-             play    ,plev    ,tlay    ,tlev    ,tsfc    , &
-             h2ovmr  ,o3vmr   ,co2vmr  ,ch4vmr  ,n2ovmr  ,o2vmr , &
-             cfc11vmr,cfc12vmr,cfc22vmr,ccl4vmr ,emis    , &
-             inflglw ,iceflglw,liqflglw,cldfmcl , &
-             taucmcl ,ciwpmcl ,clwpmcl ,reicmcl ,relqmcl , &
-             tauaer  , &
-             uflx    ,dflx    ,hr      ,uflxc   ,dflxc,  hrc, &
-             duflx_dt,duflxc_dt )
-      integer(kind=im), intent(in) :: ncol, nlay
-      integer(kind=im), intent(inout) :: icld
-      integer(kind=im), intent(in) :: idrv
-      real(kind=rb), intent(in), contiguous, target :: play(:,:), plev(:,:), tlay(:,:), tlev(:,:), tsfc(:)
-      real(kind=rb), intent(in), contiguous, target :: h2ovmr(:,:), o3vmr(:,:), co2vmr(:,:), ch4vmr(:,:), &
-                                                       n2ovmr(:,:), o2vmr(:,:), cfc11vmr(:,:), cfc12vmr(:,:), &
-                                                       cfc22vmr(:,:), ccl4vmr(:,:), emis(:,:)
-      integer(kind=im), intent(in) :: inflglw, iceflglw, liqflglw
-      real(kind=rb), intent(in), contiguous, target :: cldfmcl(:,:,:), ciwpmcl(:,:,:), clwpmcl(:,:,:), &
-                                                       reicmcl(:,:), relqmcl(:,:), taucmcl(:,:,:), tauaer(:,:,:)
-      real(kind=rb), intent(out), contiguous, target :: uflx(:,:), dflx(:,:), hr(:,:), uflxc(:,:), dflxc(:,:), hrc(:,:)
-      real(kind=rb), intent(out), contiguous, target, optional :: duflx_dt(:,:), duflxc_dt(:,:)
-      integer(c_int) :: ld, ic
-      type(c_ptr) :: p_d, p_dc
-      ! `contiguous` makes the compiler pack a strided actual argument; every array must then share
-      ! the column extent, which is what a GCM chunk (pcols) gives
-      ld = int(size(play, 1), c_int)
-      if (size(plev,1) /= ld .or. size(tlay,1) /= ld .or. size(tlev,1) /= ld .or. size(h2ovmr,1) /= ld .or. &
-          size(emis,1) /= ld .or. size(tauaer,1) /= ld .or. size(uflx,1) /= ld .or. size(hr,1) /= ld .or. &
-          size(cldfmcl,2) /= ld .or. size(reicmcl,1) /= ld) then
-         write(*,*) 'RRTMG_LW: arrays must share one column extent (size(x,1))'
-         error stop 1
-      end if
-      p_d = c_null_ptr; p_dc = c_null_ptr
-      if (present(duflx_dt)) p_d = c_loc(duflx_dt)
-      if (present(duflxc_dt)) p_dc = c_loc(duflxc_dt)
-      ic = int(icld, c_int)
-      call check(c_rrtmg_lw(int(ncol,c_int), ld, int(nlay,c_int), ic, int(idrv,c_int), play, plev, tlay, tlev, &
-            tsfc, h2ovmr, o3vmr, co2vmr, ch4vmr, n2ovmr, o2vmr, cfc11vmr, cfc12vmr, cfc22vmr, ccl4vmr, emis, &
-            int(inflglw,c_int), int(iceflglw,c_int), int(liqflglw,c_int), cldfmcl, taucmcl, ciwpmcl, clwpmcl, &
-            reicmcl, relqmcl, tauaer, uflx, dflx, hr, uflxc, dflxc, hrc, p_d, p_dc, RRTMG_LW_HOST, c_null_ptr), &
-            'RRTMG_LW')
-      icld = int(ic, im)      ! clamped to 2 when outside [0,3] (src/rrtmg_lw_rad.f90:470)
-      end subroutine rrtmg_lw
-
-      end module rrtmg_lw_rad
-
-!------------------------------------------------------------------------------------------------
       module mcica_subcol_gen_lw
       use iso_c_binding
       use parkind, only : im => kind_im, rb => kind_rb
       use rrtmg_lw_b200_c
       implicit none
-      public :: get_alpha, mcica_subcol_lw
+      public :: get_alpha, mcica_subcol_lw, generate_stochastic_clouds
 
       contains
+
+      ! src/mcica_subcol_gen_lw.f90:295-296 -- name kept, see rrtmg_lw_b200_c::internal_only
+      subroutine generate_stochastic_clouds(ncol, nlay, nsubcol, icld, irng, pmid, cld, clwp, ciwp, &
+                               alpha, tauc, cld_stoch, clwp_stoch, ciwp_stoch, tauc_stoch, changeSeed)
+      integer(kind=im), intent(in) :: ncol, nlay, nsubcol, icld
+      integer(kind=im), intent(inout) :: irng
+      real(kind=rb), intent(in) :: pmid(:,:), cld(:,:), clwp(:,:), ciwp(:,:), alpha(:,:), tauc(:,:,:)
+      real(kind=rb), intent(out) :: cld_stoch(:,:,:), clwp_stoch(:,:,:), ciwp_stoch(:,:,:), tauc_stoch(:,:,:)
+      integer(kind=im), optional, intent(in) :: changeSeed
+      call internal_only('GENERATE_STOCHASTIC_CLOUDS')
+      end subroutine generate_stochastic_clouds
 
       subroutine get_alpha(iplon, ncol, nlayers, icld, idcor, decorr_con, &
                            dz, lat, juldat, cldfrac, alpha)

@@ -79,6 +79,39 @@ def test_fortran_shim_binds_only_exported_symbols():
         assert hasattr(lib, n), n
     puts = set((int(b), n) for b, n in re.findall(r"call put\((\d+), '([a-z0-9_]+)'", txt))
     assert puts == set((a[0], a[1]) for a in kdata.karrays())
+    # the two rad files (McICA / non-McICA, one module name like the reference's two sources) call interfaces the
+    # common file declares
+    for f, c in (("rrtmg_lw_b200_shim_rad.f90", "c_rrtmg_lw"), ("rrtmg_lw_b200_shim_rad_nomcica.f90", "c_rrtmg_lw_nomcica")):
+        t = open(os.path.join(ROOT, "fortran", f)).read()
+        assert "module rrtmg_lw_rad" in t and "public :: rrtmg_lw, inatm" in t
+        assert ("call check(%s(" % c) in t and ("function %s(" % c) in txt
+
+
+def _dummy_list(text, name):
+    """Dummy-argument names of `subroutine name (...)` in free-form Fortran, continuation lines joined."""
+    m = re.search(r"subroutine\s+%s\s*&?\s*\(" % name, text, flags=re.I)
+    assert m, name
+    depth, k = 1, m.end()
+    while depth:
+        depth += {"(": 1, ")": -1}.get(text[k], 0)
+        k += 1
+    body = re.sub(r"!.*", "", text[m.end():k - 1])
+    return [a.strip().lower() for a in body.replace("&", " ").replace("\n", " ").split(",")]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference tree not mounted")
+def test_fortran_shim_keeps_the_reference_dummy_argument_lists():
+    """Same public names, same dummy arguments in the same order as the reference's GCM entry points (what makes the
+    shim a relink-only replacement)."""
+    ref = lambda f: open(os.path.join("/root/reference/src", f)).read()  # noqa: E731
+    mine = lambda f: open(os.path.join(ROOT, "fortran", f)).read()  # noqa: E731
+    pairs = [("rrtmg_lw_rad.f90", "rrtmg_lw_b200_shim_rad.f90", ("rrtmg_lw", "inatm")),
+             ("rrtmg_lw_rad.nomcica.f90", "rrtmg_lw_b200_shim_rad_nomcica.f90", ("rrtmg_lw", "inatm")),
+             ("mcica_subcol_gen_lw.f90", "rrtmg_lw_b200_shim.f90", ("get_alpha", "mcica_subcol_lw", "generate_stochastic_clouds")),
+             ("rrtmg_lw_init.f90", "rrtmg_lw_b200_shim.f90", ("rrtmg_lw_ini",))]
+    for rf, mf, names in pairs:
+        for n in names:
+            assert _dummy_list(mine(mf), n) == _dummy_list(ref(rf), n), (mf, n)
 
 
 def test_kdata_header_matches_python_layout():
