@@ -17,6 +17,8 @@ _LIB = os.path.join(_HERE, "liborc.so")
 _STATIC = os.path.join(os.path.dirname(_HERE), "rrtmg_lw_b200", "data", "lw_static_tables.bin")
 
 _lib = None
+_plain = None      # liborc.so while the coverage build is switched in
+_ini_args = None   # (blob, cpdair, default_real_kind) of the last ini(), replayed into the coverage build
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
 
@@ -47,6 +49,8 @@ def _p(a):
 
 
 def ini(kdata_blob: np.ndarray, cpdair: float = 1004.0, default_real_kind: int = 4):
+    global _ini_args
+    _ini_args = (kdata_blob, cpdair, default_real_kind)
     st = np.fromfile(_STATIC, dtype="<f8")
     rc = lib().orc_ini(C.c_double(cpdair), _p(st), _p(np.ascontiguousarray(kdata_blob)), C.c_int(default_real_kind))
     assert rc == 0, rc
@@ -184,6 +188,22 @@ BRANCH_ADJFAC_SITES = ("taumol:550 b3 lower n2o", "taumol:736 b3 upper n2o", "ta
                        "taumol:1639 b7 upper co2", "taumol:1721 b8 lower co2", "taumol:1768 b8 upper co2",
                        "taumol:1879 b9 lower n2o", "taumol:2036 b9 upper n2o", "taumol:2497 b13 co2")
 BINARY_LOWER_BANDS = (3, 4, 5, 7, 9, 12, 13, 15, 16)
+
+
+def branch_arm(on=True):
+    """Switches every following oracle call to the coverage build liborc_cov.so (same arithmetic + the 143 branch
+    counters) / back to the plain library, which carries no instrumentation because it is what gets timed."""
+    global _lib, _plain
+    if on and _plain is None:
+        build()
+        _plain = lib()
+        cov = C.CDLL(os.path.join(_HERE, "liborc_cov.so"))
+        cov.orc_get_table.restype = C.c_long
+        _lib = cov
+        if _ini_args is not None:
+            ini(*_ini_args)
+    elif not on and _plain is not None:
+        _lib, _plain = _plain, None
 
 
 def branch_counts(reset=False):

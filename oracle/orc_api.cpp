@@ -315,13 +315,15 @@ extern "C" long orc_get_table(const char* name, double* out, long cap) {
 }
 
 // branch-coverage counters (orc_common.h NBRANCH): copies them out and optionally resets them
+// (counted only in the coverage build liborc_cov.so; all zero otherwise)
 static std::atomic<long long> g_branch[orc::NBRANCH];
 namespace orc {
 thread_local int g_cur_band = 0;
-void branch_hit(int idx, long long n) {
+void branch_hit_slow(int idx, long long n) {
     if (idx >= 0 && idx < NBRANCH) g_branch[idx].fetch_add(n, std::memory_order_relaxed);
 }
 }  // namespace orc
+
 extern "C" int orc_branch_counts(long long* out, int cap, int reset) {
     for (int i = 0; i < orc::NBRANCH; ++i) {
         if (out && i < cap) out[i] = g_branch[i].load();

@@ -74,6 +74,10 @@ void orc_kiss_stream(int s1, int s2, int s3, int s4, int n, double* reals_out, i
  * "<band>:<reduced array>" e.g. "3:absa"; returns element count (0 if unknown) */
 long orc_get_table(const char* name, double* out, long cap);
 
+/* branch-coverage counters of taumol / rtrnmc (143 of them, orc_common.h): counted only by the coverage build
+ * liborc_cov.so (same arithmetic + counters); the library timed as the CPU baseline carries no instrumentation */
+int orc_branch_counts(long long* out, int cap, int reset);
+
 /* op-counting build (liborc_count.so) only: {add/sub, mul, div, exp, log, pow} executed by the calling
  * thread since the last reset; -1 in the normal build */
 void orc_opcount(long long* out6, int reset);

@@ -169,7 +169,16 @@ struct Column {
 //   [138,141) cloudy-layer sub-branches of rtrnmc.f90:358-425 (odtot < 0.06, odepth <= 0.06, else)
 //   [141,143) clear-layer branches rtrnmc.f90:429-440 (odepth <= 0.06, table)
 constexpr int NBRANCH = 143;
-void branch_hit(int idx, long long n = 1);
+// compiled in only in the coverage build (liborc_cov.so, -DORC_BRANCH_COUNTERS): the library that is timed as the CPU
+// baseline carries no instrumentation
+void branch_hit_slow(int idx, long long n);
+inline void branch_hit(int idx, long long n = 1) {
+#ifdef ORC_BRANCH_COUNTERS
+    branch_hit_slow(idx, n);
+#else
+    (void)idx; (void)n;
+#endif
+}
 extern thread_local int g_cur_band;  // set by the taugbN being evaluated (for the shared eta_fac helper)
 
 // status codes shared by oracle entry points (mirror the reference's STOP sites)

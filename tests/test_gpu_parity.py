@@ -515,6 +515,7 @@ def test_parity_batches_cover_every_branch(gpu, oracle):
     times: the three eta branches of both (p, T) corners of every binary-species band (taumol.f90:569-598), both
     atmosphere halves of every band, all ten adjfac sites (:550, 736, 1355, 1483, 1639, 1721, 1768, 1879, 2036, 2497),
     the three cloudy-layer sub-branches (rtrnmc.f90:358-425) and both clear-layer branches (:429-440)."""
+    oracle.branch_arm(True)
     oracle.branch_counts(reset=True)
     for name in sorted(COVERAGE_BATCHES):
         kw = dict(COVERAGE_BATCHES[name])
@@ -526,6 +527,7 @@ def test_parity_batches_cover_every_branch(gpu, oracle):
         gpu.sync()
         _check(got, ref, 1, what="coverage batch " + name)
     c = oracle.branch_counts(reset=True)
+    oracle.branch_arm(False)
     for band in oracle.BINARY_LOWER_BANDS:
         assert (c["eta"][band - 1] >= 100).all(), ("eta branches of band", band, c["eta"][band - 1].tolist())
     assert (c["half"] >= 100).all(), c["half"].tolist()
