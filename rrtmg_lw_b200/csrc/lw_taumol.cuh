@@ -25,7 +25,12 @@
 namespace lw {
 
 // ===== LW_COMMON_BEGIN =====
-constexpr int TAUMOL_THREADS = 128;
+#ifndef LW_TAUMOL_THREADS
+#define LW_TAUMOL_THREADS 128
+#endif
+constexpr int TAUMOL_THREADS = LW_TAUMOL_THREADS;  // a multiple of the 128-column block of the scratch layout
+constexpr int OD_BLK = 128;
+static_assert(TAUMOL_THREADS % OD_BLK == 0, "a CTA covers whole 128-column blocks");
 // ===== LW_COMMON_END =====
 
 // ===== LW_PRECISION_BEGIN =====
@@ -82,7 +87,7 @@ __device__ __forceinline__ void band_odepth(const LayerFs& L, int ipk, bool lowe
                     od[k] = od_state(odepth < 0.0 ? 0.0 : odepth, C.bpade);
                     if (dbg) s.dbg_taug[(long)(G0 + g + j + k) * nlay + l] = a[j + k];
                 }
-                if (live) __stcs(reinterpret_cast<double2*>(odp + (G0 + g + j) * TAUMOL_THREADS), make_double2(od[0], od[1]));
+                if (live) __stcs(reinterpret_cast<double2*>(odp + (G0 + g + j) * OD_BLK), make_double2(od[0], od[1]));
             }
         }
     };
@@ -102,14 +107,14 @@ __device__ __forceinline__ void band_odepth(const LayerFs& L, int ipk, bool lowe
         }
     }
     if constexpr (pf_slot(B) >= 0) {
-        if (live) __stcs(pfp + pf_slot(B) * TAUMOL_THREADS, W.smpl);
+        if (live) __stcs(pfp + pf_slot(B) * OD_BLK, W.smpl);
     }
 }
 
 // BMASK: bit b-1 set = band b is evaluated by this instantiation (all 16 by default; subsets recompute setcoef)
 template <unsigned BMASK, int MINB>
 __global__ void __launch_bounds__(TAUMOL_THREADS, MINB) taumol_kernel(ColIn in, Scratch s, RunCfg r) {
-    __shared__ double fs[NFIELD * TAUMOL_THREADS];
+    extern __shared__ double fs[];  // NFIELD x TAUMOL_THREADS
     const int tid = threadIdx.x;
     const int l = blockIdx.y;
     const int i_raw = blockIdx.x * TAUMOL_THREADS + tid;
@@ -266,15 +271,22 @@ __global__ void __launch_bounds__(TAUMOL_THREADS, MINB) taumol_kernel(ColIn in, 
     const double pavel_e = pavel;
 #endif
     const LayerFs L{fs + src};
-    const long rec = (long)blockIdx.x * nlay + l;  // (column block, layer)
-    double* odp = s.od + rec * NGPT * TAUMOL_THREADS + 2 * src;
-    double* pfp = s.pfs + rec * NPF * TAUMOL_THREADS + src;
+    const long rec = ((long)blockIdx.x * (TAUMOL_THREADS / OD_BLK) + (src / OD_BLK)) * nlay + l;  // (128-column block, layer)
+    double* odp = s.od + rec * NGPT * OD_BLK + 2 * (src % OD_BLK);
+    double* pfp = s.pfs + rec * NPF * OD_BLK + (src % OD_BLK);
     const double* sdp = s.secdiff + i_e;
     const double* tap = in.tauaer + (r.c0 + i_e) + in.ld * l;
     const long tas = in.ld * (long)nlay;
+#ifdef LW_TAUMOL_BAND_SYNC
+#define LW_BAND_SYNC() __syncthreads()  /* keeps the warps of a CTA in the same band (same table rows, same code) */
+#else
+#define LW_BAND_SYNC()
+#endif
 #define LW_BAND(B)                                                                                                   \
-    if constexpr ((BMASK >> (B - 1)) & 1u)                                                                           \
-        band_odepth<B>(L, ipk_e, lower_e, pavel_e, sdp[(long)(B - 1) * s.pitch], tap[tas * (B - 1)], odp, pfp, live_e, dbg_e, s, l, nlay);
+    if constexpr ((BMASK >> (B - 1)) & 1u) {                                                                         \
+        band_odepth<B>(L, ipk_e, lower_e, pavel_e, sdp[(long)(B - 1) * s.pitch], tap[tas * (B - 1)], odp, pfp, live_e, dbg_e, s, l, nlay); \
+        LW_BAND_SYNC();                                                                                              \
+    }
     LW_BAND(1) LW_BAND(2) LW_BAND(3) LW_BAND(4) LW_BAND(5) LW_BAND(6) LW_BAND(7) LW_BAND(8)
     LW_BAND(9) LW_BAND(10) LW_BAND(11) LW_BAND(12) LW_BAND(13) LW_BAND(14) LW_BAND(15) LW_BAND(16)
 #undef LW_BAND

@@ -29,7 +29,18 @@ cudaError_t LW_CAT(upload_constants_stu, LW_STU)(const ConstTab& c, const DevPtr
 #if LW_STU == 0
 void launch_taumol(const ColIn& in, const Scratch& s, const RunCfg& r, cudaStream_t st) {
     const dim3 grid((unsigned)((r.ncol + TAUMOL_THREADS - 1) / TAUMOL_THREADS), (unsigned)r.nlay);
-    taumol_kernel<0xffffu, LW_TAUMOL_MINB><<<grid, TAUMOL_THREADS, 0, st>>>(in, s, r);
+    constexpr size_t smem = (size_t)NFIELD * TAUMOL_THREADS * sizeof(double);
+    auto kern = taumol_kernel<0xffffu, LW_TAUMOL_MINB>;
+    if (smem > 40 * 1024) {  // static (sort arrays) + dynamic shared memory beyond 48 KB needs the opt-in
+        static unsigned attr_set = 0u;  // bit d = done on device d
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!((attr_set >> dev) & 1u)) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_set |= 1u << dev;
+        }
+    }
+    kern<<<grid, TAUMOL_THREADS, smem, st>>>(in, s, r);
 }
 #elif LW_STU == 6
 void launch_gridcloud_prep(const ColIn& in, const Scratch& s, const RunCfg& r, int maxran, cudaStream_t st) {
