@@ -295,9 +295,14 @@ def main():
                     help="64 = the headline FP64 path; 32 = the optional FP32 mode of the band kernels (secondary line)")
     ap.add_argument("--band-kernel", type=int, default=4, choices=[2, 4],
                     help="4 = two-phase path (taumol per (column, layer) + sweep kernels); 2 = fused per-band kernels")
+    ap.add_argument("--gather-transport", default="nccl", choices=["nccl", "p2p"],
+                    help="N > 1: how a chunk's outputs reach rank 0: torch.distributed's NCCL gather (default), or peer "
+                         "copies into IPC-mapped buffers (copy engines; measured 38 GB/s on this pool's boxes against "
+                         "660 GB/s for NCCL over NVLink, profiles/r02_p2p_vs_nccl.log -- kept for boxes where peer "
+                         "copies take NVLink)")
     ap.add_argument("--gather-chunks", type=int, default=8,
                     help="N > 1: column chunks of a rank's block whose output gathers (NCCL, into rank 0) overlap the next "
-                         "chunk's kernels")
+                         "chunk's kernels; n = n equal chunks, 0 = tapered schedule (1/4 1/4 1/4 1/8 1/16 1/32 1/32)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
@@ -350,21 +355,81 @@ def main():
     # N > 1: the step INCLUDES the gather of every rank's six output arrays into rank 0 (the one exchange of the path,
     # SURVEY 8(e)): the rank's block runs in column chunks whose packed (rows, chunk) output buffers are the send
     # buffers; chunk i's gather (NCCL stream) overlaps chunk i+1's kernels.  N = 1 has nothing to gather.
-    nch = max(1, args.gather_chunks)
-    cw = -(-ncol // nch)
-    nch = -(-ncol // cw)
+    # chunk schedule: n > 0 (default 8) = n equal chunks; 0 = tapered, 1/4 1/4 1/4 1/8 1/16 1/32 1/32 of the block (small
+    # last chunks shorten the transfer left over at the end of the step; measured equal to 8 equal chunks at N = 8 and
+    # 3 % slower at N = 2, so the exposed cost at N = 8 is not that tail -- DESIGN.md section 8)
+    if args.gather_chunks > 0:
+        cw_u = -(-ncol // args.gather_chunks)
+        bounds = [(lo, min(lo + cw_u, ncol)) for lo in range(0, ncol, cw_u)]
+    else:
+        bounds, lo = [], 0
+        for f in (4, 4, 4, 8, 16, 32):
+            w_ = max(128, (ncol // f) // 128 * 128)
+            if lo + w_ >= ncol:
+                break
+            bounds.append((lo, lo + w_))
+            lo += w_
+        bounds.append((lo, ncol))
+    nch = len(bounds)
     send = recv = None
     if world > 1:
-        send = [torch.zeros((wl.R, cw), dtype=torch.float64, device=dev) for _ in range(nch)]
+        send = [torch.zeros((wl.R, hi - lo), dtype=torch.float64, device=dev) for lo, hi in bounds]
         if rank == 0:   # [chunk][rank] packed blocks: the gathered result, no further assembly
-            recv = torch.empty((nch, world, wl.R, cw), dtype=torch.float64, device=dev)
+            recv = [torch.empty((world, wl.R, hi - lo), dtype=torch.float64, device=dev) for lo, hi in bounds]
+
+    # transport of a chunk into the root.  "nccl" (default): torch.distributed gather, 660 GB/s per pair over NVLink.
+    # "p2p": the root's receive buffers are mapped into every rank (CUDA IPC) and a rank PUSHES its finished chunk with a
+    # peer copy on a side stream (copy engines, no SM held by a communication kernel; the root's own chunks are written
+    # in place by its kernels) -- on this pool's boxes such copies run at 38 GB/s (PCIe class), so it is not the default.
+    transport = args.gather_transport
+    peer = None
+    copy_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+    if world > 1 and transport == "p2p":
+        ok = 1
+        try:
+            from torch.multiprocessing.reductions import reduce_tensor
+            obj = [[reduce_tensor(t) for t in recv] if rank == 0 else None]
+            dist.broadcast_object_list(obj, src=0)
+            if rank != 0:
+                peer = [fn(*a) for fn, a in obj[0]]   # the root's (world, R, w) buffers, addressable from this rank
+                peer[0][rank, :1, :1].copy_(send[0][:1, :1])   # makes torch enable peer access to the root's device
+                torch.cuda.synchronize()
+                import ctypes
+                cudart = ctypes.CDLL("libcudart.so.12")
+                cudart.cudaMemcpyAsync.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
+                                                   ctypes.c_void_p]
+                cudart.cudaMemcpyAsync.restype = ctypes.c_int
+
+                def push(c):
+                    # a raw peer copy on THIS rank's stream (its copy engine writes over NVLink): nothing is enqueued in a
+                    # context of the root's GPU, so the root's kernels are never time-sliced against another process
+                    rc_ = cudart.cudaMemcpyAsync(peer[c][rank].data_ptr(), send[c].data_ptr(),
+                                                 send[c].numel() * 8, 4, copy_stream.cuda_stream)
+                    if rc_ != 0:
+                        raise RuntimeError("cudaMemcpyAsync (peer) failed: %d" % rc_)
+        except Exception as e:  # noqa: BLE001 -- no peer access / IPC on this box: fall back to NCCL, all ranks together
+            sys.stderr.write("rank %d: p2p gather unavailable (%s), using NCCL\n" % (rank, e))
+            ok = 0
+        flag = torch.tensor([ok], device=dev, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            transport, peer = "nccl", None
 
     def step_gathered():
+        if transport == "p2p":
+            for c, (lo, hi) in enumerate(bounds):
+                if rank == 0:
+                    wl.step(lo, hi, out=packed_views(recv[c][0], rows), out_ld=hi - lo)
+                else:
+                    wl.step(lo, hi, out=packed_views(send[c], rows), out_ld=hi - lo)
+                    copy_stream.wait_stream(torch.cuda.current_stream())
+                    push(c)
+            torch.cuda.current_stream().wait_stream(copy_stream)
+            return
         works = []
-        for c in range(nch):
-            lo, hi = c * cw, min((c + 1) * cw, ncol)
-            wl.step(lo, hi, out=packed_views(send[c], rows), out_ld=cw)
-            works.append(dist.gather(send[c], [recv[c, r] for r in range(world)] if rank == 0 else None, dst=0,
+        for c, (lo, hi) in enumerate(bounds):
+            wl.step(lo, hi, out=packed_views(send[c], rows), out_ld=hi - lo)
+            works.append(dist.gather(send[c], [recv[c][r] for r in range(world)] if rank == 0 else None, dst=0,
                                      async_op=True))
         for w_ in works:
             w_.wait()
@@ -388,19 +453,26 @@ def main():
         # the same step without the exchange, for reference; and the proof that what arrived is what was computed
         ms_ng = timed(torch, dist, world, dev, wl.step, max(2, min(args.steps, 5)), 1) / max(2, min(args.steps, 5))
         step_gathered()
+        barrier()
+        if transport == "p2p" and rank == 0:   # the root's kernels wrote its own block straight into recv[c][0]
+            for c in range(nch):
+                send[c].copy_(recv[c][0])
         wl.step()
         torch.cuda.synchronize()
-        mine = torch.stack([send[c][:, :min(cw, ncol - c * cw)].sum() for c in range(nch)]).sum().reshape(1)
+        mine = torch.stack([send[c].sum() for c in range(nch)]).sum().reshape(1)
         sums = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(sums, mine)
         same = None
         if rank == 0:
-            got = [float(recv[:, r].sum()) for r in range(world)]
+            got = [float(sum(recv[c][r].sum() for c in range(nch))) for r in range(world)]
             same = bool(all(abs(got[r] - float(sums[r])) <= 1e-9 * abs(got[r]) for r in range(world)))
-            same = same and bool(torch.equal(torch.cat([recv[c, 0][:, :min(cw, ncol - c * cw)] for c in range(nch)], dim=1),
-                                             wl.pack))
-        gather_res = {"included_in_value": True, "chunks": nch, "dst": 0, "transport": "NCCL gather (torch.distributed) of "
-                      "packed (rows, chunk) buffers the kernels write directly; no packing, no assembly",
+            same = same and bool(torch.equal(torch.cat([recv[c][0] for c in range(nch)], dim=1), wl.pack))
+        gather_res = {"included_in_value": True, "chunks": nch, "chunk_columns": [hi - lo for lo, hi in bounds], "dst": 0,
+                      "transport": ("peer copies (copy engines over NVLink) of the packed (rows, chunk) buffers the kernels write, "
+                                    "pushed by each rank into the root's IPC-mapped receive buffers; the root's kernels write "
+                                    "its own block in place" if transport == "p2p" else
+                                    "NCCL gather (torch.distributed) of packed (rows, chunk) buffers the kernels write "
+                                    "directly; no packing, no assembly"),
                       "bytes_into_root_per_step": (world - 1) * ncol * wl.R * 8,
                       "ungathered": {"value": world * ncol / (ms_ng * 1e-3), "unit": "columns/s", "ms_per_step": ms_ng},
                       "root_holds_every_ranks_block": same}
