@@ -65,7 +65,11 @@ __device__ __forceinline__ void band_odepth(const LayerFs& L, int ipk, bool lowe
 #ifdef LW_F32
     constexpr int VEC = NGPAD[B - 1] % 8 == 0 ? 8 : 4;
 #else
-    constexpr int VEC = NGPAD[B - 1] < 8 ? NGPAD[B - 1] : 8;
+#ifndef LW_TAUMOL_VEC
+#define LW_TAUMOL_VEC 4  // g-points evaluated per table-row burst: 4 = one 256-bit load per row in flight (8 = two: more
+                         // registers in flight, spills at 128 registers; measured 5 % slower, profiles/r02_taumol_vec_experiment.log)
+#endif
+    constexpr int VEC = NGPAD[B - 1] < LW_TAUMOL_VEC ? NGPAD[B - 1] : LW_TAUMOL_VEC;
 #endif
     using GV = typename std::conditional<VEC == 4, D4, VA<VEC / 4>>::type;
     using BL = BandLayer<B, true>;
