@@ -58,7 +58,23 @@ struct SweepRing {
 #define LW_SWEEP_NST 2
 #endif
     static constexpr int NST = LW_SWEEP_NST;  // ring stages = layers of prefetch distance
-    static constexpr size_t BYTES = (size_t)NST * SLOTS * SWEEP_THREADS * sizeof(double);
+    static constexpr size_t RING_BYTES = (size_t)NST * SLOTS * SWEEP_THREADS * sizeof(double);
+    // Rejected variant, off by default (LW_SWEEP_CLR_SMEM_MIN=16 switches it on): groups of >= MIN g-points keep the
+    // clear-sky recurrences of their first LW_SWEEP_CLR_SMEM_N g-points in shared memory ([g][thread], behind the ring)
+    // instead of registers, so that a 16-g band fits 128 registers and four CTAs per SM.  Measured 35 % SLOWER on bands
+    // 3 and 5 (3.21 vs 2.37 ms per 262 144 columns, profiles/r02_sweep_clear_stream_smem_experiment.log): the extra
+    // shared-memory round trip sits on the recurrence's dependency chain.
+#ifndef LW_SWEEP_CLR_SMEM_MIN
+#define LW_SWEEP_CLR_SMEM_MIN 99
+#endif
+#ifndef LW_SWEEP_CLR_SMEM_N
+#define LW_SWEEP_CLR_SMEM_N 8
+#endif
+    LW_HD static constexpr int clr_smem(int cld) { return (cld != CLD_NONE && G::NGG >= LW_SWEEP_CLR_SMEM_MIN) ? LW_SWEEP_CLR_SMEM_N : 0; }
+    LW_HD static constexpr size_t bytes(int cld) {
+        return RING_BYTES + (size_t)clr_smem(cld) * SWEEP_THREADS * sizeof(double);
+    }
+    static constexpr size_t BYTES = RING_BYTES;
 };
 
 // Planck function of band B at the temperature whose table position is (it, frac), setcoef.f90:173-226
@@ -250,6 +266,16 @@ __device__ __forceinline__ void cloud_point(const SweepTab& tb, double st, bool 
     ittot_out = tsmall ? -1 : ittot;
 }
 
+// per-g values of a thread: the first NSM in the thread's column of a [g][thread] shared-memory block, the rest in
+// registers (g is a compile-time constant wherever it is indexed: the loops are unrolled)
+template <int N, int NSM>
+struct HybArr {
+    acc_t v[N - NSM > 0 ? N - NSM : 1];
+    acc_t* p;
+    __device__ __forceinline__ acc_t& operator[](int g) { return g < NSM ? p[g * SWEEP_THREADS] : v[g - NSM]; }
+    __device__ __forceinline__ void bind(void* q) { p = reinterpret_cast<acc_t*>(q); }
+};
+
 // ------------------------------------------------------------------------------------------
 // Experiment LW_SWEEP_TMA=1 (rejected variants): a layer's optical depths of the CTA's 128 columns are ONE
 // contiguous run of NGG x 1 KB in phase 1's layout, so instead of 128 threads x NGG / 2 16-byte cp.async one elected
@@ -405,7 +431,9 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
         static_assert(NB <= 8, "at most 8 bands per group");
     };
 
-    acc_t radld[NGG], radclrd[NGG];
+    acc_t radld[NGG];
+    HybArr<NGG, RG::clr_smem(CLD)> radclrd;
+    radclrd.bind(reinterpret_cast<char*>(ring) + RG::RING_BYTES + tid * sizeof(acc_t));
 #pragma unroll
     for (int g = 0; g < NGG; ++g) { radld[g] = 0.; radclrd[g] = 0.; }
 
@@ -566,7 +594,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
     // ---------------------------------------------------------------- surface, rtrnmc.f90:465-484
     // radld / radclrd are dead after the sweep; they become the upward radiances
     acc_t (&radlu)[NGG] = radld;
-    acc_t (&radclru)[NGG] = radclrd;
+    auto& radclru = radclrd;
     acc_t d_radlu[IDRV ? NGG : 1], d_radclru[IDRV ? NGG : 1];
 #if LW_SWEEP_TMA
     __syncthreads();

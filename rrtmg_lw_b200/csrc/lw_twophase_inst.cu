@@ -75,7 +75,9 @@ bool launch_gridcloud_sweep(int band, int maxran, int idrv, const ColIn& in, con
 #define LW_SWEEP_BASE_REGS 72
 #endif
 constexpr int sweep_minb(int ngg, int cld, int idrv) {
-    const int est = (cld != CLD_NONE ? 4 : 2) * ngg * (idrv ? 2 : 1) + LW_SWEEP_BASE_REGS;
+    // part of the clear-sky stream of a wide cloudy group lives in shared memory (SweepRing::clr_smem): 2 registers less each
+    const int clr_sm = (cld != CLD_NONE && ngg >= LW_SWEEP_CLR_SMEM_MIN) ? LW_SWEEP_CLR_SMEM_N : 0;
+    const int est = ((cld != CLD_NONE ? 4 : 2) * ngg * (idrv ? 2 : 1) - 2 * clr_sm) + LW_SWEEP_BASE_REGS;
     return est <= 128 ? 4 : (est <= 168 ? 3 : 2);
 }
 
@@ -84,10 +86,10 @@ static void launch_g(int cld, int idrv, const ColIn& in, const ColOut& out, cons
                      const SweepTab& tb, cudaStream_t st) {
     const int threads = SWEEP_THREADS;
     const int blocks = (r.ncol + threads - 1) / threads;
-    const size_t smem = SweepRing<B0, NB>::BYTES;
     constexpr int NGG = Grp<B0, NB>::NGG;
 #define LW_GO(CLD, IDRV)                                                                                         \
     do {                                                                                                         \
+        const size_t smem = SweepRing<B0, NB>::bytes(CLD);                                                       \
         auto kern = rtrnmc_kernel<B0, NB, CLD, IDRV, sweep_minb(NGG, CLD, IDRV)>;                                \
         static unsigned attr_set = 0u; /* bit d = done on device d (the attribute is per device) */             \
         int dev_ = 0;                                                                                            \
