@@ -62,6 +62,18 @@ enum { RRTMG_LW_HOST = 0, RRTMG_LW_DEVICE = 1 };
  *                     8 = of the shipped `-r8` makefiles (affects default-kind literals only) */
 int rrtmg_lw_b200_ini(double cpdair, const double* kdata, long nkdata, int default_real_kind);
 
+/* The two halves of rrtmg_lw_ini, for deployments that do not want the k-data or the start-up reduction on the
+ * compute nodes.  rrtmg_lw_b200_tables_build is HOST-ONLY (needs no CUDA device): it runs the rrtmg_lw_ini restatement
+ * (src/rrtmg_lw_init.f90:125-173, 215-298, 385-2034: constants, lookup tables, the 16-g -> 140-g reduction of every
+ * k-table) and writes a versioned binary image of the result; returns the image size in bytes (call with out = NULL to
+ * size the buffer), or -RRTMG_LW_ERR_ARG.  rrtmg_lw_b200_ini_tables uploads such an image (checksum, version and
+ * shape checked: RRTMG_LW_ERR_ARG otherwise) and leaves the library in the same state as rrtmg_lw_b200_ini with the
+ * k-data the image was built from -- bit-identical tables and results.  tools/make_table_blob.py is the command-line
+ * form. */
+long rrtmg_lw_b200_tables_build(double cpdair, const double* kdata, long nkdata, int default_real_kind,
+                                void* out, long cap);
+int rrtmg_lw_b200_ini_tables(const void* blob, long nbytes);
+
 /* Array-by-array alternative to building the blob: hand over one unreduced k-array of
  * modules/rrlw_kgNN.f90 (e.g. band 3, "kao", 585*16 doubles, Fortran element order) as the
  * reference's lw_kgbNN left it; after all RRTMG_LW_NKARRAYS arrays were put,

@@ -47,6 +47,8 @@ _fp = C.POINTER(C.c_float)
 SIGNATURES = {
     "rrtmg_lw_b200_kdata_put": (C.c_int, [C.c_int, C.c_char_p, _dp, C.c_long]),
     "rrtmg_lw_b200_ini": (C.c_int, [C.c_double, _dp, C.c_long, C.c_int]),
+    "rrtmg_lw_b200_tables_build": (C.c_long, [C.c_double, _dp, C.c_long, C.c_int, C.c_void_p, C.c_long]),
+    "rrtmg_lw_b200_ini_tables": (C.c_int, [C.c_void_p, C.c_long]),
     "rrtmg_lw_b200_rrtmg_lw": (C.c_int, [C.c_int, C.c_int, C.c_int, _ip, C.c_int] + [_dp] * 16 + [C.c_int] * 3 +
                                [_dp] * 15 + [C.c_int, C.c_void_p]),
     "rrtmg_lw_b200_rrtmg_lw_nomcica": (C.c_int, [C.c_int, C.c_int, C.c_int, _ip, C.c_int] + [_dp] * 16 + [C.c_int] * 3 +
@@ -157,6 +159,26 @@ def rrtmg_lw_ini(cpdair: float, kdata: np.ndarray, default_real_kind: int = 4):
         rc = lib().rrtmg_lw_b200_ini(float(cpdair), _ptr(k), k.size, int(default_real_kind))
     if rc:
         raise RrtmgLwError(rc, "rrtmg_lw_ini")
+
+
+def tables_build(cpdair: float, kdata: np.ndarray, default_real_kind: int = 4) -> bytes:
+    """Host-only half of ``rrtmg_lw_ini``: the reduced tables as a versioned binary image (no GPU needed)."""
+    a = np.ascontiguousarray(kdata, dtype=np.float64)
+    n = lib().rrtmg_lw_b200_tables_build(float(cpdair), _ptr(a), a.size, int(default_real_kind), None, 0)
+    if n < 0:
+        raise RrtmgLwError(-n, "tables_build")
+    buf = C.create_string_buffer(n)
+    m = lib().rrtmg_lw_b200_tables_build(float(cpdair), _ptr(a), a.size, int(default_real_kind), buf, n)
+    if m != n:
+        raise RrtmgLwError(7, "tables_build")
+    return buf.raw
+
+
+def rrtmg_lw_ini_tables(blob: bytes):
+    """``rrtmg_lw_ini`` from an image made by :func:`tables_build` / ``tools/make_table_blob.py``."""
+    rc = lib().rrtmg_lw_b200_ini_tables(blob, len(blob))
+    if rc:
+        raise RrtmgLwError(rc, "rrtmg_lw_ini_tables")
 
 
 def kdata_put(band: int, name: str, array: np.ndarray):

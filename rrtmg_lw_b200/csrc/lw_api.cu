@@ -578,6 +578,33 @@ extern "C" int rrtmg_lw_b200_kdata_put(int band, const char* name, const double*
     return RRTMG_LW_ERR_ARG;  // unknown (band, name)
 }
 
+static int upload_tables();  // G.H -> the current device
+
+// host-only half of rrtmg_lw_ini: the reduced tables as a versioned binary image (no CUDA device needed)
+extern "C" long rrtmg_lw_b200_tables_build(double cpdair, const double* kdata, long nkdata, int default_real_kind,
+                                           void* out, long cap) {
+    if (!kdata || nkdata != RRTMG_LW_KDATA_DOUBLES) return -RRTMG_LW_ERR_ARG;
+    if (default_real_kind != 4 && default_real_kind != 8) return -RRTMG_LW_ERR_ARG;
+    if (out && cap < 0) return -RRTMG_LW_ERR_ARG;
+    HostTables H;
+    build_host_tables(cpdair, kStaticTables, kdata, default_real_kind, H);
+    return host_tables_write(H, out, out ? cap : 0);
+}
+
+// rrtmg_lw_ini from such an image: no k-data, no reduction at start-up
+extern "C" int rrtmg_lw_b200_ini_tables(const void* blob, long nbytes) {
+    LW_ENTER();
+    HostTables H;
+    if (!host_tables_read(blob, nbytes, H)) return RRTMG_LW_ERR_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        std::fprintf(stderr, "rrtmg_lw_b200: no CUDA device; this library has no CPU path\n");
+        return RRTMG_LW_ERR_CUDA;
+    }
+    G.H = std::move(H);
+    return upload_tables();
+}
+
 extern "C" int rrtmg_lw_b200_ini(double cpdair, const double* kdata, long nkdata, int default_real_kind) {
     LW_ENTER();
     if (!kdata && nkdata == 0) {
@@ -596,6 +623,10 @@ extern "C" int rrtmg_lw_b200_ini(double cpdair, const double* kdata, long nkdata
     }
     static_assert(sizeof(kStaticTables) / sizeof(double) == 9110, "static table blob size");
     build_host_tables(cpdair, kStaticTables, kdata, default_real_kind, G.H);
+    return upload_tables();
+}
+
+static int upload_tables() {
     HostTables& H = G.H;
     auto up = [&](double** d, const std::vector<double>& h) -> int {
         if (*d) cudaFree(*d);

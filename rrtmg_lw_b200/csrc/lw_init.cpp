@@ -185,4 +185,137 @@ void build_host_tables(double cpdair, const double* st, const double* kdata, int
     while (H.arena_p.size() & 3) H.arena_p.push_back(0.0);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Table image: 8-byte words throughout.  Header: magic, version, sizeof(ConstTab), default real kind, section count;
+// then length-prefixed sections in a fixed order; last word: a checksum (sum of all preceding words as uint64).
+namespace {
+constexpr unsigned long long kTblMagic = 0x314c42544c574c52ull;  // "RLWLTBL1" little-endian
+constexpr unsigned long long kTblVersion = 1;
+
+struct Writer {
+    unsigned long long* out;
+    long cap_words;
+    long n = 0;
+    unsigned long long sum = 0;
+    void word(unsigned long long v) {
+        if (out && n < cap_words) out[n] = v;
+        sum += v;
+        ++n;
+    }
+    void raw(const void* p, size_t bytes) {  // bytes is a multiple of 8 or padded with zeros
+        const size_t w = (bytes + 7) / 8;
+        word((unsigned long long)bytes);
+        const unsigned char* q = static_cast<const unsigned char*>(p);
+        for (size_t k = 0; k < w; ++k) {
+            unsigned long long v = 0;
+            const size_t m = bytes - 8 * k < 8 ? bytes - 8 * k : 8;
+            std::memcpy(&v, q + 8 * k, m);
+            word(v);
+        }
+    }
+    void vec(const std::vector<double>& v) { raw(v.data(), v.size() * sizeof(double)); }
+};
+
+struct Reader {
+    const unsigned long long* in;
+    long nwords;
+    long n = 0;
+    bool ok = true;
+    unsigned long long word() {
+        if (n >= nwords) { ok = false; return 0; }
+        return in[n++];
+    }
+    bool raw(void* p, size_t expect_bytes) {
+        const unsigned long long bytes = word();
+        if (!ok || bytes != expect_bytes) { ok = false; return false; }
+        const size_t w = (bytes + 7) / 8;
+        if (n + (long)w > nwords) { ok = false; return false; }
+        std::memcpy(p, in + n, bytes);
+        n += (long)w;
+        return true;
+    }
+    bool vec(std::vector<double>& v, size_t max_doubles) {
+        if (n >= nwords) { ok = false; return false; }
+        const unsigned long long bytes = in[n];
+        if (bytes % 8 != 0 || bytes / 8 > max_doubles) { ok = false; return false; }
+        v.resize(bytes / 8);
+        return raw(v.data(), bytes);
+    }
+};
+}  // namespace
+
+long host_tables_write(const HostTables& H, void* out, long cap) {
+    Writer w{static_cast<unsigned long long*>(out), out ? cap / 8 : 0};
+    w.word(kTblMagic);
+    w.word(kTblVersion);
+    w.word(sizeof(ConstTab));
+    w.word((unsigned long long)H.ct.drk);
+    ConstTab ct = H.ct;  // device pointers are not part of the image
+    std::memset(ct.band, 0, sizeof(ct.band));
+    std::memset(ct.bandp, 0, sizeof(ct.bandp));
+    w.raw(&ct, sizeof(ConstTab));
+    w.vec(H.arena);
+    w.raw(H.off, sizeof(H.off));
+    w.vec(H.arena_p);
+    w.raw(H.offp, sizeof(H.offp));
+    w.vec(H.totplnk); w.vec(H.totplnkderiv);
+    w.vec(H.exp_tbl); w.vec(H.tfn_tbl); w.vec(H.tau_tbl);
+    w.vec(H.absice2); w.vec(H.absice3); w.vec(H.absliq1);
+    w.raw(H.rwgt, sizeof(H.rwgt));
+    w.word((unsigned long long)H.named.size());
+    for (const auto& kv : H.named) {
+        w.raw(kv.first.data(), kv.first.size());
+        w.vec(kv.second);
+    }
+    const unsigned long long sum = w.sum;
+    w.word(sum);
+    const long bytes = w.n * 8;
+    return bytes;
+}
+
+bool host_tables_read(const void* blob, long nbytes, HostTables& H) {
+    if (!blob || nbytes < 64 || nbytes % 8 != 0) return false;
+    Reader r{static_cast<const unsigned long long*>(blob), nbytes / 8};
+    unsigned long long sum = 0;
+    for (long k = 0; k + 1 < r.nwords; ++k) sum += r.in[k];
+    if (sum != r.in[r.nwords - 1]) return false;
+    if (r.word() != kTblMagic || r.word() != kTblVersion || r.word() != sizeof(ConstTab)) return false;
+    const unsigned long long drk = r.word();
+    if (drk != 4 && drk != 8) return false;
+    const size_t big = (size_t)1 << 26;
+    if (!r.raw(&H.ct, sizeof(ConstTab))) return false;
+    if ((unsigned long long)H.ct.drk != drk) return false;
+    if (!r.vec(H.arena, big) || !r.raw(H.off, sizeof(H.off)) || !r.vec(H.arena_p, big) || !r.raw(H.offp, sizeof(H.offp)))
+        return false;
+    if (!r.vec(H.totplnk, big) || !r.vec(H.totplnkderiv, big) || !r.vec(H.exp_tbl, big) || !r.vec(H.tfn_tbl, big) ||
+        !r.vec(H.tau_tbl, big) || !r.vec(H.absice2, big) || !r.vec(H.absice3, big) || !r.vec(H.absliq1, big))
+        return false;
+    if (!r.raw(H.rwgt, sizeof(H.rwgt))) return false;
+    const unsigned long long nnamed = r.word();
+    if (!r.ok || nnamed > 4096) return false;
+    H.named.clear();
+    for (unsigned long long k = 0; k < nnamed; ++k) {
+        if (r.n >= r.nwords) return false;
+        const unsigned long long len = r.in[r.n];
+        if (len > 256) return false;
+        std::string name(len, ' ');
+        if (!r.raw(&name[0], len)) return false;
+        std::vector<double> v;
+        if (!r.vec(v, big)) return false;
+        H.named.emplace_back(std::move(name), std::move(v));
+    }
+    // consistency the kernels rely on
+    if (H.totplnk.size() != 181 * 17 || H.totplnkderiv.size() != 181 * 17 || H.exp_tbl.size() != NTBL + 1 ||
+        H.tfn_tbl.size() != NTBL + 1 || H.tau_tbl.size() != NTBL + 1 || H.absice2.size() != 43 * 16 ||
+        H.absice3.size() != 46 * 16 || H.absliq1.size() != 58 * 16)
+        return false;
+    for (int b = 0; b < NBND; ++b)
+        for (int k = 0; k < 13; ++k) {
+            if (H.off[b][k] != (size_t)-1 && H.off[b][k] >= H.arena.size()) return false;
+            if (H.offp[b][k] != (size_t)-1 && H.offp[b][k] >= H.arena_p.size()) return false;
+        }
+    return r.ok && r.n == r.nwords - 1;
+}
+
 }  // namespace lw

@@ -131,4 +131,11 @@ struct HostTables {
 // Builds everything on the host.  static_tables = blob of tools/extract_static_tables.py.
 void build_host_tables(double cpdair, const double* static_tables, const double* kdata, int drk, HostTables& out);
 
+// Versioned binary image of a HostTables (the result of the rrtmg_lw_ini restatement: reduced k-tables in device
+// layout, lookup tables, constants): what a deployment ships instead of the k-data + the init-time reduction.
+// write: returns the image size in bytes; fills `out` when it is non-NULL and `cap` is large enough.
+// read: false when the image is truncated, of another version or inconsistent.
+long host_tables_write(const HostTables& H, void* out, long cap);
+bool host_tables_read(const void* blob, long nbytes, HostTables& H);
+
 }  // namespace lw

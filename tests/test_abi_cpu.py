@@ -34,6 +34,11 @@ def test_strerror_and_version_do_not_need_a_gpu():
     assert b"sm_100a" in L.rrtmg_lw_b200_version()
 
 
+def _has_gpu():
+    import torch
+    return torch.cuda.is_available()
+
+
 def test_no_cpu_fallback():
     """Without a CUDA device init must fail with ERR_CUDA (5), and compute entries with
     ERR_NOT_INIT (6) -- never a silent CPU path."""
@@ -170,3 +175,34 @@ def test_mersenne_twister_jump_ahead_matches_stepping():
     10^6 (host-only check of the table the device kernel uses)."""
     from rrtmg_lw_b200 import api
     assert api.lib().rrtmg_lw_b200_mt_jump_selftest() == 0
+
+
+def test_table_image_is_built_on_the_host_and_validated(kblob, tmp_path):
+    """The host-side half of rrtmg_lw_ini as a tool (packaging item): the versioned table image is built
+    without a GPU, is deterministic, depends on the inputs it should depend on, and `rrtmg_lw_b200_ini_tables` refuses a
+    corrupt, truncated or foreign image with ERR_ARG before it ever looks for a device (ERR_CUDA on this CPU box for a
+    valid one: there is no CPU path)."""
+    import subprocess
+    import sys
+    from rrtmg_lw_b200 import api
+    img = api.tables_build(1004.0, kblob, 4)
+    assert img[:8] == b"RLWLTBL1" and int.from_bytes(img[8:16], "little") == 1 and len(img) % 8 == 0
+    assert img == api.tables_build(1004.0, kblob, 4)
+    assert img != api.tables_build(1004.0, kblob, 8)          # default-kind literals are part of the tables
+    assert img != api.tables_build(1005.0, kblob, 4)          # heatfac
+    with pytest.raises(api.RrtmgLwError) as e:
+        api.tables_build(1004.0, kblob[:-1], 4)
+    assert e.value.code == 7
+    out = tmp_path / "tables.bin"
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "make_table_blob.py"), "--kdata", "synthetic",
+                           "--cpdair", "1004.0", "-o", str(out)])
+    assert out.read_bytes() == img
+    if not _has_gpu():
+        with pytest.raises(api.RrtmgLwError) as e:
+            api.rrtmg_lw_ini_tables(img)
+        assert e.value.code == 5
+    bad = bytearray(img); bad[len(img) // 2] ^= 0x10
+    for blob in (bytes(bad), img[:-8], img[8:], b"\0" * 64, b""):
+        with pytest.raises(api.RrtmgLwError) as e:
+            api.rrtmg_lw_ini_tables(blob)
+        assert e.value.code == 7

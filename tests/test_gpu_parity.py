@@ -560,3 +560,23 @@ def test_kiss_stepping_over_clear_layers_is_bit_exact(gpu, oracle, icld):
     assert ref["cldfmcl"].sum() > 1000
     assert np.array_equal(_np(got["cldfmcl"]), ref["cldfmcl"])
     assert torch.equal(got["cldfmcl"], full["cldfmcl"])
+
+
+def test_init_from_the_table_image_is_bit_identical(gpu, oracle, kblob):
+    """rrtmg_lw_b200_ini_tables(image built on the host) leaves the library exactly where rrtmg_lw_b200_ini(k-data)
+    does: every reduced table readable through get_table and a cloudy + dF/dT run are bit-identical."""
+    from rrtmg_lw_b200 import api
+    b = synth.make_batch(512, 72, cloudy=True, aerosol=True)
+    ref = driver.run_fused(b, icld=2, idrv=1, device="cuda:0")
+    names = ["tau_tbl", "exp_tbl", "tfn_tbl", "rwgt", "heatfac", "fluxfac", "3:absa", "3:absb", "16:fracrefa", "9:kb_mn2o"]
+    tabs = {n: api.get_table(n) for n in names}
+    try:
+        api.rrtmg_lw_ini_tables(api.tables_build(1004.0, kblob, 4))
+        got = driver.run_fused(b, icld=2, idrv=1, device="cuda:0")
+        gpu.sync()
+        for k in KEYS + ("duflx_dt", "duflxc_dt"):
+            assert torch.equal(got[k], ref[k]), k
+        for n in names:
+            assert tabs[n].size > 0 and np.array_equal(api.get_table(n), tabs[n]), n
+    finally:
+        api.rrtmg_lw_ini(1004.0, kblob, 4)
