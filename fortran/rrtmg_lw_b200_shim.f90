@@ -109,6 +109,27 @@
          integer(c_int), value :: device
          end function
 
+         ! multi-GPU output gather (one rank per GPU; include/rrtmg_lw_b200.h): rank 0 makes the 128-byte id, the host
+         ! broadcasts it (MPI_Bcast(id, 128, MPI_BYTE, 0, comm)), every rank calls comm_init, then gathers per step
+         integer(c_int) function c_comm_unique_id(id128) bind(C, name='rrtmg_lw_b200_comm_unique_id')
+         import :: c_int, c_char
+         character(kind=c_char), intent(out) :: id128(128)
+         end function
+         integer(c_int) function c_comm_init(nranks, rank, id128) bind(C, name='rrtmg_lw_b200_comm_init')
+         import :: c_int, c_char
+         integer(c_int), value :: nranks, rank
+         character(kind=c_char), intent(in) :: id128(128)
+         end function
+         integer(c_int) function c_gather(send, count, recv, root, stream) bind(C, name='rrtmg_lw_b200_gather')
+         import :: c_int, c_long, c_ptr
+         type(c_ptr), value :: send, recv, stream      ! DEVICE addresses (c_loc of device arrays / host_data use_device)
+         integer(c_long), value :: count
+         integer(c_int), value :: root
+         end function
+         integer(c_int) function c_comm_finalize() bind(C, name='rrtmg_lw_b200_comm_finalize')
+         import :: c_int
+         end function
+
          ! run-time switches without a reference counterpart (include/rrtmg_lw_b200.h, INTEGRATION.md section 6)
          integer(c_int) function c_set_option(name, value) bind(C, name='rrtmg_lw_b200_set_option')
          import :: c_int, c_char

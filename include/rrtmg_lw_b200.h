@@ -209,6 +209,24 @@ int rrtmg_lw_b200_set_chunk(int max_columns);
  *   one (0 = off: every call is its own stream). */
 int rrtmg_lw_b200_set_option(const char* name, int value);
 
+/* Multi-GPU: the output gather behind the C ABI.  One rank per GPU, started by the host's launcher; columns
+ * are block-partitioned over the ranks and nothing is exchanged on the data path.  A host that wants the ranks' output
+ * blocks on one rank:
+ *   rank 0:     rrtmg_lw_b200_comm_unique_id(id)   128 bytes, which the host broadcasts to every rank (MPI_Bcast, ...)
+ *   all ranks:  rrtmg_lw_b200_comm_init(nranks, rank, id)
+ *   per step:   rrtmg_lw_b200_gather(send, count, recv, root, stream)
+ *               every rank contributes `count` doubles of DEVICE memory (e.g. a packed (rows, columns) output buffer
+ *               written with the "out_ld" option); the root receives rank r's block at recv + r * count (recv: DEVICE
+ *               memory, nranks * count doubles, ignored elsewhere).  NCCL send / receive pairs, enqueued on `stream`
+ *               after the rank's kernels; several gathers of column chunks may be in flight while later chunks compute.
+ *               rrtmg_lw_b200_comm_finalize()
+ * NCCL (libnccl.so.2) is loaded at the first of these calls; the library has no link-time dependency on it.  Errors:
+ * RRTMG_LW_ERR_CUDA (NCCL missing or failing), RRTMG_LW_ERR_NOT_INIT (gather before comm_init), RRTMG_LW_ERR_ARG. */
+int rrtmg_lw_b200_comm_unique_id(void* id128);
+int rrtmg_lw_b200_comm_init(int nranks, int rank, const void* id128);
+int rrtmg_lw_b200_gather(const double* send, long count, double* recv, int root, void* stream);
+int rrtmg_lw_b200_comm_finalize(void);
+
 /* Host-only self test of the n-step jumps of the KISS generator used by the sub-column-parallel
  * McICA kernel (src/mcica_subcol_gen_lw.f90:731-741 stepped n times == one jump); returns the number
  * of mismatches (0 = ok).  Needs no CUDA device. */

@@ -65,6 +65,10 @@ SIGNATURES = {
     "rrtmg_lw_b200_set_chunk": (C.c_int, [C.c_int]),
     "rrtmg_lw_b200_set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "rrtmg_lw_b200_set_device": (C.c_int, [C.c_int]),
+    "rrtmg_lw_b200_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "rrtmg_lw_b200_comm_init": (C.c_int, [C.c_int, C.c_int, C.c_void_p]),
+    "rrtmg_lw_b200_gather": (C.c_int, [_dp, C.c_long, _dp, C.c_int, C.c_void_p]),
+    "rrtmg_lw_b200_comm_finalize": (C.c_int, []),
     "rrtmg_lw_b200_kiss_jump_selftest": (C.c_int, []),
     "rrtmg_lw_b200_mt_jump_selftest": (C.c_int, []),
     "rrtmg_lw_b200_launch_count": (C.c_long, [C.c_int]),
@@ -267,6 +271,34 @@ def get_alpha(iplon, ncol, nlayers, icld, idcor, decorr_con, dz, lat, juldat, cl
                                        _ptr(alpha), space, _stream(space))
     if rc:
         raise RrtmgLwError(rc, "get_alpha")
+
+
+def comm_unique_id() -> bytes:
+    """Rank 0: the 128-byte NCCL id every rank passes to :func:`comm_init` (broadcast it with the host's own means)."""
+    buf = C.create_string_buffer(128)
+    rc = lib().rrtmg_lw_b200_comm_unique_id(buf)
+    if rc:
+        raise RrtmgLwError(rc, "comm_unique_id")
+    return buf.raw
+
+
+def comm_init(nranks: int, rank: int, unique_id: bytes):
+    rc = lib().rrtmg_lw_b200_comm_init(int(nranks), int(rank), unique_id)
+    if rc:
+        raise RrtmgLwError(rc, "comm_init")
+
+
+def gather(send, recv, root: int = 0):
+    """Gather every rank's ``send`` (CUDA float64 tensor) into ``recv`` (root only: ``(nranks,) + send.shape``) through
+    the library's NCCL gather, on the current torch stream."""
+    rc = lib().rrtmg_lw_b200_gather(_ptr(send), int(send.numel()), _ptr(recv) if recv is not None else None, int(root),
+                                    _stream(DEVICE))
+    if rc:
+        raise RrtmgLwError(rc, "gather")
+
+
+def comm_finalize():
+    lib().rrtmg_lw_b200_comm_finalize()
 
 
 def sync():
