@@ -295,8 +295,9 @@ def main():
                     help="64 = the headline FP64 path; 32 = the optional FP32 mode of the band kernels (secondary line)")
     ap.add_argument("--band-kernel", type=int, default=4, choices=[2, 4],
                     help="4 = two-phase path (taumol per (column, layer) + sweep kernels); 2 = fused per-band kernels")
-    ap.add_argument("--gather-transport", default="nccl", choices=["nccl", "p2p"],
-                    help="N > 1: how a chunk's outputs reach rank 0: torch.distributed's NCCL gather (default), or peer "
+    ap.add_argument("--gather-transport", default="abi", choices=["abi", "nccl", "p2p"],
+                    help="N > 1: how a chunk's outputs reach rank 0: the library's own NCCL gather behind the C ABI "
+                         "(rrtmg_lw_b200_gather, default), torch.distributed's NCCL gather, or peer "
                          "copies into IPC-mapped buffers (copy engines; measured 38 GB/s on this pool's boxes against "
                          "660 GB/s for NCCL over NVLink, profiles/r02_p2p_vs_nccl.log -- kept for boxes where peer "
                          "copies take NVLink)")
@@ -377,7 +378,9 @@ def main():
         if rank == 0:   # [chunk][rank] packed blocks: the gathered result, no further assembly
             recv = [torch.empty((world, wl.R, hi - lo), dtype=torch.float64, device=dev) for lo, hi in bounds]
 
-    # transport of a chunk into the root.  "nccl" (default): torch.distributed gather, 660 GB/s per pair over NVLink.
+    # transport of a chunk into the root.  "abi" (default): the library's NCCL gather behind the C ABI
+    # (rrtmg_lw_b200_comm_init / rrtmg_lw_b200_gather: what a Fortran host would call), enqueued on a side stream behind
+    # the chunk's kernels.  "nccl": torch.distributed gather (same wire protocol, 660 GB/s per pair over NVLink).
     # "p2p": the root's receive buffers are mapped into every rank (CUDA IPC) and a rank PUSHES its finished chunk with a
     # peer copy on a side stream (copy engines, no SM held by a communication kernel; the root's own chunks are written
     # in place by its kernels) -- on this pool's boxes such copies run at 38 GB/s (PCIe class), so it is not the default.
@@ -415,7 +418,29 @@ def main():
         if int(flag.item()) == 0:
             transport, peer = "nccl", None
 
+    if world > 1 and transport == "abi":
+        ok = 1
+        try:
+            uid = [api.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            api.comm_init(world, rank, uid[0])
+        except Exception as e:  # noqa: BLE001 -- e.g. no loadable libnccl.so.2: fall back to torch's, all ranks together
+            sys.stderr.write("rank %d: C-ABI gather unavailable (%s), using torch.distributed\n" % (rank, e))
+            ok = 0
+        flag = torch.tensor([ok], device=dev, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            transport = "nccl"
+
     def step_gathered():
+        if transport == "abi":
+            for c, (lo, hi) in enumerate(bounds):
+                wl.step(lo, hi, out=packed_views(send[c], rows), out_ld=hi - lo)
+                copy_stream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(copy_stream):   # the gather orders behind the chunk's kernels, beside the next chunk's
+                    api.gather(send[c], recv[c] if rank == 0 else None, root=0)
+            torch.cuda.current_stream().wait_stream(copy_stream)
+            return
         if transport == "p2p":
             for c, (lo, hi) in enumerate(bounds):
                 if rank == 0:
@@ -471,6 +496,9 @@ def main():
                       "transport": ("peer copies (copy engines over NVLink) of the packed (rows, chunk) buffers the kernels write, "
                                     "pushed by each rank into the root's IPC-mapped receive buffers; the root's kernels write "
                                     "its own block in place" if transport == "p2p" else
+                                    "the library's NCCL gather behind the C ABI (rrtmg_lw_b200_gather: grouped ncclSend / ncclRecv "
+                                    "on a side stream) of packed (rows, chunk) buffers the kernels write directly; no packing, "
+                                    "no assembly" if transport == "abi" else
                                     "NCCL gather (torch.distributed) of packed (rows, chunk) buffers the kernels write "
                                     "directly; no packing, no assembly"),
                       "bytes_into_root_per_step": (world - 1) * ncol * wl.R * 8,
