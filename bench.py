@@ -672,6 +672,32 @@ def main():
         run_extra("C2", w2, 5, "clear sky, rrtmg_lw() strict entry, idrv=0, 65 536 columns x 72 layers per GPU (weak)")
         del w2
         torch.cuda.empty_cache()
+        # the reference's literal two-call sequence (README.md:179-183 of the reference): mcica_subcol_lw materialises the
+        # four (140, ncol, nlay) sub-column arrays, rrtmg_lw reads them back -- 345 KB per column through the interface
+        # instead of 25 KB; what an unmodified GCM gets before it switches to the fused entry
+        n2c = 65536
+        w2 = Workload(api, driver, dev, n2c, NLAY, 2, 0, False, rank)
+        mk3 = lambda: torch.zeros((NLAY, n2c, 140), dtype=torch.float64, device=dev)  # noqa: E731
+        mc = {k: mk3() for k in ("cldfmcl", "ciwpmcl", "clwpmcl", "taucmcl")}
+        mc["reicmcl"] = torch.zeros((NLAY, n2c), dtype=torch.float64, device=dev)
+        mc["relqmcl"] = torch.zeros((NLAY, n2c), dtype=torch.float64, device=dev)
+
+        def two_call(w=w2, m=mc):
+            bb, o = w.b, w.out
+            api.mcica_subcol_lw(1, n2c, NLAY, 2, 1, 0, bb.play, bb.cldfrac, bb.ciwp, bb.clwp, bb.rei, bb.rel, bb.tauc, None,
+                                m["cldfmcl"], m["ciwpmcl"], m["clwpmcl"], m["reicmcl"], m["relqmcl"], m["taucmcl"])
+            api.rrtmg_lw(n2c, NLAY, 2, 0, *w.at, 2, 3, 1, m["cldfmcl"], m["taucmcl"], m["ciwpmcl"], m["clwpmcl"],
+                         m["reicmcl"], m["relqmcl"], bb.tauaer, o["uflx"], o["dflx"], o["hr"], o["uflxc"], o["dflxc"],
+                         o["hrc"], None, None)
+        w2.step = two_call
+        run_extra("C3_two_call", w2, 3, "the reference's two-call sequence mcica_subcol_lw -> rrtmg_lw with the sub-column "
+                  "arrays materialised on the device (345 KB per column through the interface), 65 536 columns x 72 "
+                  "layers per GPU (weak); same flops as C3")
+        if rank == 0:
+            extras["C3_two_call"]["flops_per_column"] = flops.get("C3")
+        del w2, mc
+        torch.cuda.empty_cache()
+        api.set_option("release_scratch", 1)
         w2 = Workload(api, driver, dev, ncol, NLAY, 5, 1, True, rank)
         run_extra("C4", w2, 3, "icld=5 exponential-random overlap, idcor=1 alpha (get_alpha on device), 16-band aerosol "
                   "tau, idrv=1; %d columns x 72 layers per GPU (weak)" % ncol)
