@@ -338,7 +338,7 @@ int run_device(Mode mode, int ncol, int nlay, int icld, int idrv, int inflag, in
                 launch_cldoptics(in, S, r, qm); G.launches++;
                 if (conc) CK(cudaEventRecord(G.e_cld, qm));
             }
-            if (cld == CLD_ARRAYS) { launch_cldflags(in, S, r, st); G.launches += 2; }
+            if (cld == CLD_ARRAYS) { launch_cldarrays(in, S, r, st); G.launches += 2; }  // after colprep: needs secdiff
             if (cld == CLD_GRID) { launch_gridcloud_prep(in, S, r, icld != 1, st); G.launches++; }  // needs colprep's secdiff
             if (G.timing) CK(cudaEventRecord(G.ev[1], st));
             if (G.timing) CK(cudaEventRecord(G.evb[nstage++], st));

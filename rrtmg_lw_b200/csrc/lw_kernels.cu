@@ -190,6 +190,53 @@ __global__ void __launch_bounds__(128) colprep_kernel(ColIn in, Scratch s, RunCf
     if (s.dbg_col == i) { s.dbg_scal[0] = laytrop; s.dbg_scal[1] = pwvcm; }
 }
 
+// cldprmc for one sub-column of band b (0-based), cldprmc.f90:177-266: cloud optical depth from the water paths and
+// effective radii; tauc_in is the caller's value, returned unchanged unless inflag = 2 finds cloud water
+__device__ __forceinline__ double cld_tauc_band(int b, double ciwp, double clwp, double radice, double radliq, double tauc_in,
+                                                const RunCfg& r) {
+    double tauc = tauc_in;
+    const double cwp = ciwp + clwp;
+    if (r.inflag == 2 && (cwp >= 1.e-20 || tauc >= 1.e-20)) {
+        double abscoice = 0.0, abscoliq = 0.0;
+        if (ciwp != 0.0) {
+            if (r.iceflag == 0) {
+                abscoice = C.absice0[0] + C.absice0[1] / radice;
+            } else if (r.iceflag == 1) {
+                const int icb[16] = {1, 2, 3, 3, 3, 4, 4, 4, 5, 5, 5, 5, 5, 5, 5, 5};
+                abscoice = C.absice1[0 + 2 * (icb[b] - 1)] + C.absice1[1 + 2 * (icb[b] - 1)] / radice;
+            } else {
+                const double factor = (radice - 2.) / 3.;
+                int index = (int)factor;
+                const int nrad = r.iceflag == 2 ? 43 : 46;
+                if (index == nrad) index = nrad - 1;
+                if (index < 1) index = 1;        // unreachable for valid radii; keeps loads in bounds
+                if (index > nrad - 1) index = nrad - 1;
+                const double fint = factor - (double)index;
+                const double* t = (r.iceflag == 2 ? D.absice2 : D.absice3) + nrad * b;
+                const double x0 = ldg(t + index - 1), x1 = ldg(t + index);
+                abscoice = x0 + fint * (x1 - (x0));
+            }
+        }
+        if (clwp != 0.0) {
+            if (r.liqflag == 0) {
+                abscoliq = C.absliq0;
+            } else {
+                int index = (int)(radliq - 1.5);
+                if (index == 0) index = 1;
+                if (index == 58) index = 57;
+                if (index < 1) index = 1;
+                if (index > 57) index = 57;
+                const double fint = radliq - 1.5 - (double)index;
+                const double* t = D.absliq1 + 58 * b;
+                const double x0 = ldg(t + index - 1), x1 = ldg(t + index);
+                abscoliq = x0 + fint * (x1 - (x0));
+            }
+        }
+        tauc = ciwp * abscoice + clwp * abscoliq;
+    }
+    return tauc;
+}
+
 // ---------------------------------------------------------------------------------------------
 // cldprmc for the McICA mask entry of the two-phase path (cldprmc.f90:177-266 + rtrnmc.f90:316-326): one thread per
 // (column, layer).  Every sub-column of a band that holds cloud in this layer has the same water paths and radii
@@ -209,7 +256,6 @@ __global__ void __launch_bounds__(128) cldoptics_kernel(ColIn in, Scratch s, Run
     const unsigned w[5] = {mw[0], mw[P], mw[2 * P], mw[3 * P], w4 & 0x7fffffffu};
     const double ciwp = in.ciwp[a], clwp = in.clwp[a];
     const double radice = in.rei[a], radliq = in.rel[a];
-    const double cwp = ciwp + clwp;
     double* q = s.cldb + ((((long)(i >> 7) * r.nlay + l) * NBND) * 2) * 128 + (i & 127);
     for (int b = 0; b < NBND; ++b) {
         // the band's sub-column bits: g-points GOFF[b] .. GOFF[b] + NGC[b] - 1
@@ -221,45 +267,7 @@ __global__ void __launch_bounds__(128) cldoptics_kernel(ColIn in, Scratch s, Run
         if (sh + ng > 32) bits |= w[wlo + 1] << (32 - sh);
         bits &= (1u << ng) - 1u;
         if (!bits) continue;
-        double tauc = in.tauc ? in.tauc[b + 16 * a] : 0.0;
-        if (r.inflag == 2 && (cwp >= 1.e-20 || tauc >= 1.e-20)) {
-            double abscoice = 0.0, abscoliq = 0.0;
-            if (ciwp != 0.0) {
-                if (r.iceflag == 0) {
-                    abscoice = C.absice0[0] + C.absice0[1] / radice;
-                } else if (r.iceflag == 1) {
-                    const int icb[16] = {1, 2, 3, 3, 3, 4, 4, 4, 5, 5, 5, 5, 5, 5, 5, 5};
-                    abscoice = C.absice1[0 + 2 * (icb[b] - 1)] + C.absice1[1 + 2 * (icb[b] - 1)] / radice;
-                } else {
-                    const double factor = (radice - 2.) / 3.;
-                    int index = (int)factor;
-                    const int nrad = r.iceflag == 2 ? 43 : 46;
-                    if (index == nrad) index = nrad - 1;
-                    if (index < 1) index = 1;        // unreachable for valid radii; keeps loads in bounds
-                    if (index > nrad - 1) index = nrad - 1;
-                    const double fint = factor - (double)index;
-                    const double* t = (r.iceflag == 2 ? D.absice2 : D.absice3) + nrad * b;
-                    const double x0 = ldg(t + index - 1), x1 = ldg(t + index);
-                    abscoice = x0 + fint * (x1 - (x0));
-                }
-            }
-            if (clwp != 0.0) {
-                if (r.liqflag == 0) {
-                    abscoliq = C.absliq0;
-                } else {
-                    int index = (int)(radliq - 1.5);
-                    if (index == 0) index = 1;
-                    if (index == 58) index = 57;
-                    if (index < 1) index = 1;
-                    if (index > 57) index = 57;
-                    const double fint = radliq - 1.5 - (double)index;
-                    const double* t = D.absliq1 + 58 * b;
-                    const double x0 = ldg(t + index - 1), x1 = ldg(t + index);
-                    abscoliq = x0 + fint * (x1 - (x0));
-                }
-            }
-            tauc = ciwp * abscoice + clwp * abscoliq;
-        }
+        const double tauc = cld_tauc_band(b, ciwp, clwp, radice, radliq, in.tauc ? in.tauc[b + 16 * a] : 0.0, r);
         const double odcld = s.secdiff[(long)b * P + i] * tauc;
         q[(b * 2) * 128] = odcld;
         q[(b * 2 + 1) * 128] = 1. - exp(-odcld);
@@ -1023,6 +1031,104 @@ __global__ void __launch_bounds__(128) cldflags_kernel(ColIn in, Scratch s, RunC
     }
 }
 
+// Strict rrtmg_lw() on the two-phase path: everything the sweeps need from the caller's per-g cloud arrays, computed with
+// the arrays read the way they lie in memory ((140, ncol, nlay): a column's 140 sub-columns are one contiguous run).
+// CTA = 16 consecutive columns of one layer, thread = sub-column g.  Per (column, layer): the cldfmc == 1 flags as 140
+// mask bits + the icldlyr flag (rtrnmc.f90:316-329), the column's cloud top, cldprmc's validation (STOP sites), and, for
+// layers in which any of the 16 columns holds cloud, odcld = secdiff * taucmc and efclfrac = 1 - exp(-odcld) of every
+// sub-column (cldprmc.f90:177-266, rtrnmc.f90:331-345), transposed through shared memory so that the [g][layer][column]
+// scratch is written in 128-byte runs.
+constexpr int CA_COLS = 16;
+__global__ void __launch_bounds__(160) cldarrays_kernel(ColIn in, Scratch s, RunCfg r) {
+    __shared__ double sh_ef[NGPT][CA_COLS + 1], sh_oc[NGPT][CA_COLS + 1];
+    __shared__ unsigned sh_w[CA_COLS][5];
+    __shared__ int sh_any;
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const int g = tid;
+    const int l = blockIdx.y;
+    const int i0 = blockIdx.x * CA_COLS;
+    const long P = s.pitch;
+    const long plane = (long)r.nlay * P;
+    double* S_EF = s.gcld;
+    double* S_OC = s.gcld + (long)NGPT * plane;
+    const int goff[NBND] = {0, 10, 22, 38, 52, 68, 76, 88, 96, 108, 114, 122, 130, 134, 136, 138};
+    int b = 0;
+#pragma unroll
+    for (int k = 1; k < NBND; ++k) b += (g >= goff[k]);
+    if (tid == 0) sh_any = 0;
+    __syncthreads();
+    for (int c = 0; c < CA_COLS; ++c) {
+        const int i = i0 + c;
+        bool on = false;
+        int bad = 0;
+        double ef = 0., odc = 0.;
+        if (i < r.ncol && g < NGPT) {
+            const long ci = r.c0 + i;
+            const long a = ci + in.ld * l;
+            const double cf = in.cldfmcl[140 * a + g];
+            if (cf >= 1.e-20) {
+                const double ciwp = in.ciwpmcl[140 * a + g], clwp = in.clwpmcl[140 * a + g];
+                const double tauc_in = in.taucmcl[140 * a + g];
+                if ((ciwp + clwp) >= 1.e-20 || tauc_in >= 1.e-20) {
+                    if (r.inflag == 1) bad = 1;
+                    if (r.inflag == 2) {
+                        if (ciwp != 0.0) {
+                            const double rad = in.reicmcl[a];
+                            if ((r.iceflag == 0 && rad < 10.0) || (r.iceflag == 1 && (rad < 13.0 || rad > 130.)) ||
+                                (r.iceflag == 2 && (rad < 5.0 || rad > 131.0)) || (r.iceflag == 3 && (rad < 5.0 || rad > 140.0)))
+                                bad = 2;
+                        }
+                        if (clwp != 0.0 && r.liqflag == 1) {
+                            const double rad = in.relqmcl[a];
+                            if ((rad < 2.5 || rad > 60.) && bad == 0) bad = 3;
+                        }
+                    }
+                }
+                if (cf == 1.) {
+                    on = true;
+                    const double tauc = cld_tauc_band(b, ciwp, clwp, in.reicmcl[a], in.relqmcl[a], tauc_in, r);
+                    odc = s.secdiff[(long)b * P + i] * tauc;
+                    ef = (1. - exp(-odc)) * cf;
+                }
+            }
+        }
+        const unsigned word = __ballot_sync(0xffffffffu, on);
+        const unsigned anybad = __ballot_sync(0xffffffffu, bad != 0);
+        if (anybad) {
+            const int src = __ffs(anybad) - 1;
+            const int code = __shfl_sync(0xffffffffu, bad, src);
+            if (lane == 0) raise(s, code, r.c0 + i, l + 1);
+        }
+        if (lane == 0) {
+            sh_w[c][w] = word;
+            if (word) sh_any = 1;
+        }
+        if (g < NGPT) { sh_ef[g][c] = ef; sh_oc[g][c] = odc; }
+    }
+    __syncthreads();
+    // mask words (bit 31 of word 4 = icldlyr), cloud top
+    if (tid < CA_COLS * 5) {
+        const int c = tid / 5, q = tid % 5;
+        const int i = i0 + c;
+        if (i < r.ncol) {
+            const unsigned any = sh_w[c][0] | sh_w[c][1] | sh_w[c][2] | sh_w[c][3] | sh_w[c][4];
+            s.mask[((long)l * 5 + q) * P + i] = sh_w[c][q] | ((q == 4 && any) ? 0x80000000u : 0u);
+            if (q == 0 && any) atomicMax(&s.ctop[i], l + 1);
+        }
+    }
+    if (!sh_any) return;
+    // per-g rows of this layer: 16 columns = 128 contiguous bytes
+    for (int k = tid; k < NGPT * CA_COLS; k += blockDim.x) {
+        const int gg = k / CA_COLS, c = k % CA_COLS;
+        const int i = i0 + c;
+        if (i < r.ncol) {
+            const long o = (long)gg * plane + (long)l * P + i;
+            S_EF[o] = sh_ef[gg][c];
+            S_OC[o] = sh_oc[gg][c];
+        }
+    }
+}
+
 __global__ void zero_int_kernel(int* p, long n) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = 0;
@@ -1248,6 +1354,11 @@ int launch_cvt_inputs(const ColIn& in, const Scratch& s, const RunCfg& r, int cl
 void launch_cldflags(const ColIn& in, const Scratch& s, const RunCfg& r, cudaStream_t st) {
     zero_int_kernel<<<nblk(r.ncol, 256), 256, 0, st>>>(s.ctop, r.ncol);
     cldflags_kernel<<<nblk((long)r.ncol * r.nlay * 32, 128), 128, 0, st>>>(in, s, r);
+}
+void launch_cldarrays(const ColIn& in, const Scratch& s, const RunCfg& r, cudaStream_t st) {
+    zero_int_kernel<<<nblk(r.ncol, 256), 256, 0, st>>>(s.ctop, r.ncol);
+    const dim3 grid((unsigned)nblk(r.ncol, CA_COLS), (unsigned)r.nlay);
+    cldarrays_kernel<<<grid, 160, 0, st>>>(in, s, r);
 }
 void launch_finalize(const ColIn& in, const ColOut& out, const Scratch& s, const RunCfg& r, int cloudy, cudaStream_t st) {
     finalize_kernel<<<nblk(r.ncol, 128), 128, 0, st>>>(in, out, s, r, cloudy);

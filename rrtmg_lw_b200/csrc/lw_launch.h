@@ -53,6 +53,7 @@ LW_DECL_TU(0) LW_DECL_TU(1) LW_DECL_TU(2) LW_DECL_TU(3) LW_DECL_TU(4) LW_DECL_TU
 #define LW_NUM_SWEEP_TUS 6
 void set_kiss_sparse(int on);  // KISS generator: step over the draws of cloud-free layers (default on)
 void launch_colprep(const ColIn&, const Scratch&, const RunCfg&, cudaStream_t);
+void launch_cldarrays(const ColIn&, const Scratch&, const RunCfg&, cudaStream_t);  // strict entry, two-phase path; needs secdiff
 void launch_cldoptics(const ColIn&, const Scratch&, const RunCfg&, cudaStream_t);  // needs the masks and secdiff
 void launch_taumol(const ColIn&, const Scratch&, const RunCfg&, cudaStream_t);
 #define LW_DECL_STU(n)                                                                                             \

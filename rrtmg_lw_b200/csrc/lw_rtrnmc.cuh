@@ -143,54 +143,6 @@ struct PlFrac {
     }
 };
 
-// cldprmc for one (sub-column, layer) of band B: cloud optical depth from the water paths and effective radii
-// (cldprmc.f90:177-266); tauc_in is the caller's value, returned unchanged unless inflag = 2 finds cloud water
-template <int B>
-__device__ __forceinline__ double cld_tauc(double ciwp, double clwp, double radice, double radliq, double tauc_in,
-                                           const RunCfg& r) {
-    double tauc = tauc_in;
-    const double cwp = ciwp + clwp;
-    if (r.inflag == 2 && (cwp >= 1.e-20 || tauc >= 1.e-20)) {
-        double abscoice = 0.0, abscoliq = 0.0;
-        if (ciwp != 0.0) {
-            if (r.iceflag == 0) {
-                abscoice = C.absice0[0] + C.absice0[1] / radice;
-            } else if (r.iceflag == 1) {
-                constexpr int icb[16] = {1, 2, 3, 3, 3, 4, 4, 4, 5, 5, 5, 5, 5, 5, 5, 5};
-                abscoice = C.absice1[0 + 2 * (icb[B - 1] - 1)] + C.absice1[1 + 2 * (icb[B - 1] - 1)] / radice;
-            } else {
-                const double factor = (radice - 2.) / 3.;
-                int index = (int)factor;
-                const int nrad = r.iceflag == 2 ? 43 : 46;
-                if (index == nrad) index = nrad - 1;
-                if (index < 1) index = 1;        // unreachable for valid radii; keeps loads in bounds
-                if (index > nrad - 1) index = nrad - 1;
-                const double fint = factor - (double)index;
-                const double* t = (r.iceflag == 2 ? D.absice2 : D.absice3) + nrad * (B - 1);
-                const double x0 = ldg(t + index - 1), x1 = ldg(t + index);
-                abscoice = x0 + fint * (x1 - (x0));
-            }
-        }
-        if (clwp != 0.0) {
-            if (r.liqflag == 0) {
-                abscoliq = C.absliq0;
-            } else {
-                int index = (int)(radliq - 1.5);
-                if (index == 0) index = 1;
-                if (index == 58) index = 57;
-                if (index < 1) index = 1;
-                if (index > 57) index = 57;
-                const double fint = radliq - 1.5 - (double)index;
-                const double* t = D.absliq1 + 58 * (B - 1);
-                const double x0 = ldg(t + index - 1), x1 = ldg(t + index);
-                abscoliq = x0 + fint * (x1 - (x0));
-            }
-        }
-        tauc = ciwp * abscoice + clwp * abscoliq;
-    }
-    return tauc;
-}
-
 // itr = int(tblint * tblind + 0.5) (rtrnmc.f90:386, 404, 412), kept inside the table for out-of-range cloud inputs
 // (a negative cloud optical depth would index the reference's tables out of bounds; here it must not fault the device)
 __device__ __forceinline__ int tbl_index(double tblind) {
@@ -395,7 +347,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
                 auto di = [&](int k) { return reinterpret_cast<int*>(dst + (RG::S_INT + k / RG::IPS) * SWEEP_THREADS + tid) + (k % RG::IPS); };
                 const unsigned* mw = s.mask + ((long)l0 * 5) * P + i;
                 cp_async4(di(0), mw + 4 * P);
-                if constexpr (CLD == CLD_MASK) {
+                {   // sub-column cloud bits: McICA mask (CLD_MASK) or cldfmc == 1 flags of the caller's arrays (CLD_ARRAYS)
                     constexpr int wlo = G0 >> 5, sh = G0 & 31;
                     cp_async4(di(1), mw + (long)wlo * P);
                     if constexpr (sh + NGG > 32) cp_async4(di(2), mw + (long)(wlo + 1) * P);
@@ -459,7 +411,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
         bool cldlyr = false;
         unsigned gbits = 0;
         if constexpr (CLD != CLD_NONE) cldlyr = (((unsigned)st_i(stage, 0)) >> 31) != 0;
-        if constexpr (CLD == CLD_MASK) { if (cldlyr) gbits = group_bits(stage); }
+        if constexpr (CLD != CLD_NONE) { if (cldlyr) gbits = group_bits(stage); }
 
         for_bands([&](auto kc) {
             constexpr int K = decltype(kc)::value;
@@ -476,18 +428,19 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
             // optical depth along the diffusivity angle and its absorptivity come from the cloud-optics kernel
             unsigned bits = 0;
             double odcld_b = 0., abscld_b = 0.;
-            if constexpr (CLD == CLD_MASK) {
+            if constexpr (CLD != CLD_NONE) {
                 if (cldlyr) {
                     bits = (gbits >> GO) & ((1u << NG) - 1u);
-                    if (bits) { const double* q = cldb(l0, B); odcld_b = __ldg(q); abscld_b = __ldg(q + 128); }
+                    if constexpr (CLD == CLD_MASK) {
+                        if (bits) { const double* q = cldb(l0, B); odcld_b = __ldg(q); abscld_b = __ldg(q + 128); }
+                    }
                 }
             }
             acc_t dsum = 0., dcsum = 0.;
             // does any column of the warp hold cloud in this band's sub-columns of this layer?  (warp-uniform: the
             // loop with the cloud path is straight-line code for all lanes, the one without it never sees a cloud)
             bool wcld = false;
-            if constexpr (CLD == CLD_MASK) wcld = __any_sync(0xffffffffu, bits != 0);
-            if constexpr (CLD == CLD_ARRAYS) wcld = __any_sync(0xffffffffu, cldlyr);
+            if constexpr (CLD != CLD_NONE) wcld = __any_sync(0xffffffffu, bits != 0);
             if (CLD != CLD_NONE && wcld) {
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
@@ -503,21 +456,11 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
                         on = (bits >> g) & 1u;
                         odc = on ? odcld_b : 0.; ef = on ? abscld_b : 0.;
                     } else {
-                        // strict rrtmg_lw(): per-g cloud arrays, cldprmc evaluated on the fly; only cldfmc == 1 is
-                        // cloud to rtrnmc (rtrnmc.f90:316-329)
-                        on = false; odc = 0.; ef = 0.;
-                        if (cldlyr) {
-                            const long ag = (G0 + GO + g) + 140 * a;
-                            const double cf = in.cldfmcl[ag];
-                            if (cf == 1.) {
-                                const double tauc = cld_tauc<B>(in.ciwpmcl[ag], in.clwpmcl[ag], in.reicmcl[a], in.relqmcl[a],
-                                                                in.taucmcl[ag], r);
-                                on = true;
-                                odc = ldg(s.secdiff + (long)(B - 1) * P + i) * tauc;
-                                ef = (1. - exp(-odc)) * cf;
-                            }
-                            if (live) { S_EF[(long)(G0 + GO + g) * plane + idx] = ef; S_OC[(long)(G0 + GO + g) * plane + idx] = odc; }
-                        }
+                        // strict rrtmg_lw(): per-g cloud optical depth and absorptivity of the sub-columns with cldfmc == 1
+                        // (the only ones that are cloud to rtrnmc, rtrnmc.f90:316-329), from the cloud-arrays kernel
+                        on = (bits >> g) & 1u;
+                        ef = ldg1_if(S_EF + (long)(G0 + GO + g) * plane + idx, on);
+                        odc = ldg1_if(S_OC + (long)(G0 + GO + g) * plane + idx, on);
                     }
                     double atot, bbdtot;
                     int ittot;
@@ -693,7 +636,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
         bool cldlyr = false;
         unsigned gbits = 0;
         if constexpr (CLD != CLD_NONE) cldlyr = (((unsigned)st_i(stage, 0)) >> 31) != 0;
-        if constexpr (CLD == CLD_MASK) { if (cldlyr) gbits = group_bits(stage); }
+        if constexpr (CLD != CLD_NONE) { if (cldlyr) gbits = group_bits(stage); }
 
         for_bands([&](auto kc) {
             constexpr int K = decltype(kc)::value;
@@ -708,16 +651,17 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
             pf.setup(tb, lower, sm);
             unsigned bits = 0;
             double odcld_b = 0., abscld_b = 0.;
-            if constexpr (CLD == CLD_MASK) {
+            if constexpr (CLD != CLD_NONE) {
                 if (cldlyr) {
                     bits = (gbits >> GO) & ((1u << NG) - 1u);
-                    if (bits) { const double* q = cldb(l0, B); odcld_b = __ldg(q); abscld_b = __ldg(q + 128); }
+                    if constexpr (CLD == CLD_MASK) {
+                        if (bits) { const double* q = cldb(l0, B); odcld_b = __ldg(q); abscld_b = __ldg(q + 128); }
+                    }
                 }
             }
             acc_t usum = 0., ucsum = 0., dusum = 0., ducsum = 0.;
             bool wcld = false;
-            if constexpr (CLD == CLD_MASK) wcld = __any_sync(0xffffffffu, bits != 0);
-            if constexpr (CLD == CLD_ARRAYS) wcld = __any_sync(0xffffffffu, cldlyr);
+            if constexpr (CLD != CLD_NONE) wcld = __any_sync(0xffffffffu, bits != 0);
             if (CLD != CLD_NONE && wcld) {
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
@@ -733,12 +677,9 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
                         on = (bits >> g) & 1u;
                         odc = on ? odcld_b : 0.; ef = on ? abscld_b : 0.;
                     } else {
-                        on = false; odc = 0.; ef = 0.;
-                        if (cldlyr) {
-                            on = in.cldfmcl[(G0 + GO + g) + 140 * a] == 1.;
-                            ef = S_EF[(long)(G0 + GO + g) * plane + idx];
-                            odc = S_OC[(long)(G0 + GO + g) * plane + idx];
-                        }
+                        on = (bits >> g) & 1u;
+                        ef = ldg1_if(S_EF + (long)(G0 + GO + g) * plane + idx, on);
+                        odc = ldg1_if(S_OC + (long)(G0 + GO + g) * plane + idx, on);
                     }
                     double atot, bbutot;
                     int ittot;
