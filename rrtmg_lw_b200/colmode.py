@@ -23,7 +23,9 @@ column-mode program (they come from driving the GCM entry, not from this file):
     ``src/rrtmg_lw_setcoef.f90:233-251``), :func:`run_blocks`;
   * ``imca = 0`` with clouds is the non-McICA path (``cldprop`` + ``rtrn`` for icld = 1 / ``rtrnmr`` otherwise,
     ``src/rrtmg_lw.1col.f90:498,557-572``): one run of the library's ``rrtmg_lw_nomcica`` entry;
-  * ``iatm = 1`` (``rrtatm`` layering, N4) is refused with ``NotImplementedError``.
+  * ``iatm = 1``: the sounding is layered by ``rrtatm.py``, a restatement of the part of ``src/rrtatm.f`` the example
+    suite uses (user profile on altitude levels, user boundaries in altitude, vertical path); anything else of LBLATM
+    is refused with ``NotImplementedError``.
 """
 from __future__ import annotations
 
@@ -152,8 +154,9 @@ def parse_in_aer(text: str, nlayers: int):
     return tau
 
 
-def parse_input_rrtm(text: str, cld_text: str | None = None, aer_text: str | None = None) -> Case:
-    """``readprof`` for the first ``$`` record set of an INPUT_RRTM file (iatm = 0)."""
+def parse_input_rrtm(text: str, cld_text: str | None = None, aer_text: str | None = None, airmwt: float = 0.0) -> Case:
+    """``readprof`` for the first ``$`` record set of an INPUT_RRTM file: layer records (iatm = 0) or a sounding that
+    ``rrtatm`` layers (iatm = 1; ``airmwt``: see trap T18 in ``rrtatm.py`` -- 0.0 reproduces the reference program)."""
     lines = text.split("\n")
     i = next(k for k, ln in enumerate(lines) if ln[:1] == "$")
     c = Case()
@@ -163,8 +166,8 @@ def parse_input_rrtm(text: str, cld_text: str | None = None, aer_text: str | Non
                                                  _int(fl[94:95]))
     if c.numangs == -1:
         c.numangs = 0
-    if c.iatm != 0:
-        raise NotImplementedError("iatm = 1 needs the rrtatm layering (SURVEY 8(f) N4)")
+    if c.iatm not in (0, 1):
+        raise ValueError("iatm must be 0 or 1")
     k = i + 2
     rec = lines[k].ljust(95); k += 1                                                         # format 9012
     c.tbound, c.iemiss, c.ireflect = _real(rec[0:10], 3), _int(rec[11:12]), _int(rec[14:15])
@@ -182,6 +185,16 @@ def parse_input_rrtm(text: str, cld_text: str | None = None, aer_text: str | Non
             c.semiss[b] = semis[0]
         elif c.iemiss == 2 and semis[b] != 0.0:
             c.semiss[b] = semis[b]
+    if c.iatm == 1:
+        # the sounding is layered by rrtatm (1col:1000-1008); rrtatm.py restates the part of it the example suite uses
+        from . import rrtatm
+        if c.ixsect == 1:
+            raise NotImplementedError("iatm = 1 with cross-sections (XAMNTS)")
+        atm, k = rrtatm.layer_atmosphere(lines, k, airmwt=airmwt)
+        c.nlayers, c.nmol = atm["nlayers"], atm["nmol"]
+        c.pavel, c.tavel, c.pz, c.tz, c.altz = atm["pavel"], atm["tavel"], atm["pz"], atm["tz"], atm["altz"]
+        c.wkl, c.wbrodl = atm["wkl"], atm["wbrodl"]
+        return _finish_case(c, cld_text, aer_text)
     hdr = lines[k]; k += 1                                                                   # 9013
     iform, c.nlayers, c.nmol = _int(hdr[1:2]), _int(hdr[2:5]), _int(hdr[5:10]) or 7
     if iform == 1:
@@ -227,6 +240,11 @@ def parse_input_rrtm(text: str, cld_text: str | None = None, aer_text: str | Non
             for _ in range(xextra):
                 vals += _fields(lines[k], 0, xw, 8, d=7 if xw == 15 else 3); k += 1
             c.wx0.append((vals[:7] + vals[8:])[:nx])
+    return _finish_case(c, cld_text, aer_text)
+
+
+def _finish_case(c: Case, cld_text, aer_text) -> Case:
+    """Tail of ``readprof``: surface temperature default, cloud and aerosol files."""
     if c.tbound < 0:
         c.tbound = c.tz[0]
     if c.icld >= 1:

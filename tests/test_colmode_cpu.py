@@ -5,6 +5,7 @@ the driver loop (McICA averaging, idrv dtbound adjustment) run over the oracle a
 data-independent numbers of the goldens (surface upward flux, incl. the idrv = 1 adjusted value)."""
 import dataclasses
 import json
+import math
 import os
 import sys
 
@@ -30,9 +31,11 @@ def _supported(suite):
 
 
 def test_suite_inventory(suite):
-    """14 runs in script.run_std_atm; 13 parse (iatm = 0), ICRCCM_sonde is the rrtatm case (N4)."""
+    """14 runs in script.run_std_atm; all parse: 13 with layer records (iatm = 0), ICRCCM_sonde through the rrtatm
+    layering (iatm = 1, N4)."""
     assert len(suite) == 14
-    assert [n for n, d in suite.items() if d["case"] is None] == ["ICRCCM_sonde"]
+    assert [n for n, d in suite.items() if d["case"] is None] == []
+    assert [n for n, d in suite.items() if d["case"]["iatm"] == 1] == ["ICRCCM_sonde"]
     flags = {n: (d["case"]["icld"], d["case"]["imca"], d["case"]["idrv"], d["case"]["iaer"], d["case"]["ixsect"])
              for n, d in _supported(suite).items()}
     assert flags["MLS-clr"] == (0, 0, 0, 0, 0)
@@ -69,8 +72,6 @@ def test_fixture_is_what_the_reference_files_parse_to(suite):
     for n, d in _supported(suite).items():
         c = colmode.parse_input_rrtm(*[rd(f) for f in d["files"]])
         assert dataclasses.asdict(c) == d["case"], n
-    with pytest.raises(NotImplementedError):
-        colmode.parse_input_rrtm(rd("input_rrtm_ICRCCM_sonde"))
 
 
 @have_ref
@@ -233,3 +234,48 @@ def test_iout_99_yields_the_17_blocks_of_the_goldens(suite, oracle):
     # bands 1..15 are additive; band 16's share of the broadband block is the 2600 -> infinity integral, larger than block 17
     share16 = blocks[0]["uflx"] - total
     assert (share16 > blocks[16]["uflx"] - 1e-12).all() and share16[0] > blocks[16]["uflx"][0]
+
+
+def test_rrtatm_layering_of_the_sonde_case(suite, oracle):
+    """IATM = 1: the sounding of input_rrtm_ICRCCM_sonde layered by rrtmg_lw_b200/rrtatm.py, the
+    restatement of the part of src/rrtatm.f that case uses.  Pinned on the reference's own output file: all 32 level
+    pressures of output_rrtm_ICRCCM_sonde to its print precision (the top four come from the U.S. Standard defaults of
+    DEFALT, the rest from AMERGE's exponential interpolation), the surface upward flux, and -- trap T18 -- the fact that
+    the golden is a DRY result: the program converts the sonde's g/kg water vapour with AIRMWT = 0.  Further checks are
+    physical: every layer's air column equals the hydrostatic one, PBAR / TBAR lie between the boundary values."""
+    d = suite["ICRCCM_sonde"]
+    c = colmode.Case(**d["case"])
+    g = d["golden"]
+    assert c.nlayers == 31 and len(c.pz) == 32 and len(g["pz"]) == 32
+    for mine, gold in zip(c.pz, g["pz"]):
+        assert abs(mine - gold) <= 0.6 * 10.0 ** (math.floor(math.log10(gold)) - 3), (mine, gold)   # 4 significant digits
+    wkl = np.array(c.wkl)
+    altz = np.array(c.altz)
+    sonde = altz[1:] <= 30.0                              # layers inside the sounding (g/kg water vapour)
+    assert sonde.sum() == 27 and (wkl[sonde, 0] == 0.0).all()   # T18: the sonde's water vapour never reaches the radiation code
+    assert (wkl[~sonde, 0] > 0.0).all() and wkl[~sonde, 0].sum() * 18.015 / 6.02214199e23 < 1e-4   # only the model default above it
+    air = np.array(c.wbrodl) + wkl.sum(axis=1)            # molecules cm-2
+    pz = np.array(c.pz)
+    hydro = (pz[:-1] - pz[1:]) * 100.0 / 9.80665 / (28.964e-3 / 6.02214199e23) * 1.0e-4
+    # LBLATM integrates rho dz on the sounding's OWN altitudes: where the sonde's z and p are not hydrostatic (its
+    # 0.06 -> 0.187 km step drops 17 hPa over 127 m) or where the profile switches to the model default (30 km) the
+    # layer differs from dp / g; the body of the troposphere agrees to 0.5 %, the whole column to 1 %.
+    ratio = air / hydro
+    assert np.abs(ratio[3:20] - 1.0).max() < 6e-3
+    assert abs(ratio[0] - 1.0) < 1e-3 and abs(air.sum() / hydro.sum() - 1.0) < 1e-2
+    assert np.abs(ratio[[1, 2]].mean() - 1.0) < 0.03      # the two non-hydrostatic sonde steps compensate
+    assert ((np.array(c.pavel) < pz[:-1]) & (np.array(c.pavel) > pz[1:])).all()
+    tz = np.array(c.tz)
+    lo, hi = np.minimum(tz[:-1], tz[1:]) - 3.0, np.maximum(tz[:-1], tz[1:]) + 3.0
+    assert ((np.array(c.tavel) > lo) & (np.array(c.tavel) < hi)).all()
+    assert abs(wkl[:, 6].sum() / (air.sum() - wkl[:, 6].sum() * 0) - 0.209) < 2e-3      # O2 from the model default
+    r = colmode.run_case(c, OracleBackend(oracle))
+    assert abs(r["uflx"][0] - g["uflx"][0]) <= 1.5e-3     # 406.2213 W m-2: Planck tables at tbound = 290.93 K
+    assert r["dflx"][-1] == 0.0
+    if os.path.isdir(REF_EX):
+        rd = lambda f: open(os.path.join(REF_EX, f)).read()  # noqa: E731
+        wet = colmode.parse_input_rrtm(rd("input_rrtm_ICRCCM_sonde"), airmwt=28.964)
+        h2o = np.array(wet.wkl)[:, 0]
+        pwv_cm = h2o.sum() * 18.015 / 6.02214199e23      # g cm-2 = cm of precipitable water
+        assert 1.0 < pwv_cm < 6.0                         # a humid mid-latitude summer sounding once AIRMWT is set
+        assert np.array_equal(np.array(wet.pz), pz)

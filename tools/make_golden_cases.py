@@ -3,8 +3,8 @@
 (script.run_std_atm) parsed with rrtmg_lw_b200/colmode.py -- the INPUT_RRTM record set, the
 IN_CLD_RRTM / IN_AER_RRTM file the run script pairs it with -- plus the broadband block
 (10-3250 cm-1) of the shipped OUTPUT_RRTM file.  Run in the build container (needs /root/reference;
-the GPU box has no reference mount, so the result is committed).  iatm = 1 (ICRCCM_sonde) is recorded
-as unsupported (rrtatm layering)."""
+the GPU box has no reference mount, so the result is committed).  iatm = 1 (ICRCCM_sonde) goes through
+rrtmg_lw_b200/rrtatm.py (the layering of src/rrtatm.f)."""
 import dataclasses
 import json
 import os
