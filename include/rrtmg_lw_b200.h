@@ -191,6 +191,10 @@ int rrtmg_lw_b200_set_chunk(int max_columns);
  * "concurrency": 1 (default) = independent kernels of a pass run on side streams of the library (McICA generator and
  *   cloud optics beside taumol, the sweep kernels beside each other), forked from and joined to the caller's stream;
  *   0 = everything on the caller's stream.
+ * "mcica_beside": n = 1..4: the KISS generator and the cloud optics run as ONE work-queue kernel with n CTAs per SM resident
+ *   beside taumol (launched ahead of it on a high-priority stream), plus a full-grid launch after taumol for the items left;
+ *   0 (default) = generator and cloud optics as their own kernels.  A measured and rejected scheduling variant (bit-identical
+ *   results; the step time does not change, profiles/r02_mcica_beside_taumol_experiment.log), kept for A/B runs.
  * "kiss_sparse": 1 (default) = the KISS generator (irng = 0, icld 1 / 2) stops at the highest layer with a cloud
  *   fraction and steps over the draws of cloud-free layers with closed-form jumps (those draws cannot reach the
  *   mask); 0 = every number of the reference's stream is drawn.  The masks are bit-identical either way.
@@ -236,6 +240,10 @@ int rrtmg_lw_b200_kiss_jump_selftest(void);
  * polynomial by Berlekamp-Massey, x^(2^b) mod phi by squaring) and returns the number of mismatching state words
  * (0 = ok, -1 = the table could not be built).  Needs no CUDA device. */
 int rrtmg_lw_b200_mt_jump_selftest(void);
+/* Diagnostic of the "mcica_beside" variant: globaltimer stamps (ns) of the work-queue kernel's last pass -- [0] / [1] first
+ * CTA start / last CTA end of the resident launch, [2] / [3] of the mop-up launch, [4] items taken when the mop-up began.
+ * Synchronises the device. */
+void rrtmg_lw_b200_kiss_work_stats(unsigned long long* out8);
 /* Number of kernels launched by this library since the last call with reset != 0. */
 long rrtmg_lw_b200_launch_count(int reset);
 /* CUDA-event time (ms) spent in the band kernels / all kernels of the last HOST- or DEVICE-mode

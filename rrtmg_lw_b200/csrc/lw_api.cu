@@ -20,6 +20,10 @@ static const double kStaticTables[] = {
 namespace lw {
 namespace {
 
+inline int env_int(const char* name, int dflt) {
+    const char* v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : dflt;
+}
 struct Ctx {
     bool inited = false;
     HostTables H;
@@ -38,6 +42,12 @@ struct Ctx {
     // their flux slots) beside each other, on side streams forked from and joined to the caller's stream
     static constexpr int NSIDE = 3;
     cudaStream_t side[NSIDE] = {};
+    int mcica_beside = env_int("RRTMG_LW_MCICA_BESIDE", 0);  // set_option("mcica_beside", n): KISS masks + cloud optics as a work-queue kernel resident
+                              // beside taumol (n CTAs per SM, launched first) + a full-grid launch after taumol for the
+                              // items left; needs concurrency, KISS, the fused McICA entry
+    cudaEvent_t e_kw = nullptr, e_mop = nullptr;
+    cudaStream_t hi = nullptr;  // highest-priority stream for the resident work-queue kernel: its few CTAs are placed
+                                // ahead of taumol's whenever registers come free
     cudaEvent_t e_fork = nullptr, e_colprep = nullptr, e_t = nullptr, e_cld = nullptr, e_side[NSIDE] = {};
     int tail_group = 1;       // set_option("tail_group", 0): bands 13-16 as four sweep kernels instead of one
     int concurrency = 1;      // set_option("concurrency", 0) keeps every kernel on the caller's stream
@@ -255,6 +265,10 @@ int ensure_side_streams() {
     for (auto& q : G.side) CK(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
     for (cudaEvent_t* e : {&G.e_fork, &G.e_colprep, &G.e_t, &G.e_cld}) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     for (auto& e : G.e_side) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (cudaEvent_t* e : {&G.e_kw, &G.e_mop}) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    int prio_least = 0, prio_greatest = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    CK(cudaStreamCreateWithPriority(&G.hi, cudaStreamNonBlocking, prio_greatest));
     return 0;
 }
 
@@ -332,7 +346,17 @@ int run_device(Mode mode, int ncol, int nlay, int icld, int idrv, int inflag, in
             }
             launch_colprep(in, S, r, st); G.launches++;
             if (conc) CK(cudaEventRecord(G.e_colprep, st));
-            if (cld == CLD_MASK) {
+            // masks + cloud optics beside taumol: the work-queue kernel goes first (its one CTA per SM is resident when
+            // taumol's CTAs arrive and take the rest of the registers), a full-grid launch after taumol takes what is left
+            bool beside = conc && cld == CLD_MASK && irng == 0 && G.mcica_beside != 0;
+            if (beside) {
+                static const bool noprio = env_int("RRTMG_LW_BESIDE_NOPRIO", 0) != 0;
+                cudaStream_t qk = noprio ? qm : G.hi;
+                CK(cudaStreamWaitEvent(qk, G.e_colprep, 0));  // the fused cloud optics read colprep's secdiff
+                if (launch_mcica_kiss_work(in, S, r, G.mcica_beside, qk)) { G.launches++; CK(cudaEventRecord(G.e_kw, qk)); }
+                else beside = false;
+            }
+            if (cld == CLD_MASK && !beside) {
                 if ((rc = gen_masks(qm)) != RRTMG_LW_OK) return rc;
                 if (conc) CK(cudaStreamWaitEvent(qm, G.e_colprep, 0));
                 launch_cldoptics(in, S, r, qm); G.launches++;
@@ -342,11 +366,21 @@ int run_device(Mode mode, int ncol, int nlay, int icld, int idrv, int inflag, in
             if (cld == CLD_GRID) { launch_gridcloud_prep(in, S, r, icld != 1, st); G.launches++; }  // needs colprep's secdiff
             if (G.timing) CK(cudaEventRecord(G.ev[1], st));
             if (G.timing) CK(cudaEventRecord(G.evb[nstage++], st));
-            launch_taumol(in, S, r, st); G.launches++;
+            G.launches += launch_taumol(in, S, r, st);
             if (conc) {
                 CK(cudaEventRecord(G.e_t, st));
                 for (auto& q : G.side) CK(cudaStreamWaitEvent(q, G.e_t, 0));
-                if (cld == CLD_MASK) {
+                if (beside) {
+                    // side[1] is past taumol now: the items the resident CTAs have not taken, at full occupancy
+                    launch_mcica_kiss_work(in, S, r, 0, G.side[1]); G.launches++;
+                    CK(cudaEventRecord(G.e_mop, G.side[1]));
+                    CK(cudaStreamWaitEvent(st, G.e_kw, 0));
+                    CK(cudaStreamWaitEvent(st, G.e_mop, 0));
+                    for (auto& q : G.side) {
+                        CK(cudaStreamWaitEvent(q, G.e_kw, 0));
+                        CK(cudaStreamWaitEvent(q, G.e_mop, 0));
+                    }
+                } else if (cld == CLD_MASK) {
                     CK(cudaStreamWaitEvent(st, G.e_cld, 0));
                     for (int k = 1; k < Ctx::NSIDE; ++k) CK(cudaStreamWaitEvent(G.side[k], G.e_cld, 0));
                 }
@@ -1186,6 +1220,11 @@ extern "C" int rrtmg_lw_b200_set_option(const char* name, int value) {
         G.concurrency = value;
         return RRTMG_LW_OK;
     }
+    if (std::strcmp(name, "mcica_beside") == 0) {
+        if (value < 0 || value > 4) return RRTMG_LW_ERR_ARG;
+        G.mcica_beside = value;  // resident work-queue CTAs per SM (0 = off)
+        return RRTMG_LW_OK;
+    }
     if (std::strcmp(name, "sweep_groups") == 0) {
         if (value != 0 && value != 1) return RRTMG_LW_ERR_ARG;
         G.sweep_groups = value;
@@ -1277,6 +1316,7 @@ extern "C" int rrtmg_lw_b200_fp64_peak(double* tflops) {
     return measure_fp64_peak(tflops, 5) ? RRTMG_LW_ERR_CUDA : RRTMG_LW_OK;
 }
 
+extern "C" void rrtmg_lw_b200_kiss_work_stats(unsigned long long* out8) { kiss_work_stats(out8); }
 extern "C" int rrtmg_lw_b200_kiss_jump_selftest(void) { return kiss_jump_selftest(); }
 extern "C" int rrtmg_lw_b200_mt_jump_selftest(void) { return mt_jump_selftest(); }
 
@@ -1303,7 +1343,8 @@ extern "C" void rrtmg_lw_b200_finalize(void) {
         G.s_in = G.s_out = nullptr;
     }
     for (auto& q : G.side) { if (q) cudaStreamDestroy(q); q = nullptr; }
-    for (cudaEvent_t* e : {&G.e_fork, &G.e_colprep, &G.e_t, &G.e_cld}) { if (*e) cudaEventDestroy(*e); *e = nullptr; }
+    if (G.hi) { cudaStreamDestroy(G.hi); G.hi = nullptr; }
+    for (cudaEvent_t* e : {&G.e_fork, &G.e_colprep, &G.e_t, &G.e_cld, &G.e_kw, &G.e_mop}) { if (*e) cudaEventDestroy(*e); *e = nullptr; }
     for (auto& e : G.e_side) { if (e) cudaEventDestroy(e); e = nullptr; }
     G.inited = false;
 }

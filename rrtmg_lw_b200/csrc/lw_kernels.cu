@@ -243,17 +243,12 @@ __device__ __forceinline__ double cld_tauc_band(int b, double ciwp, double clwp,
 // (they are the grid-mean values, mcica:658-679), hence the same band optical depth: the kernel writes, per band whose
 // sub-column bits are not all clear, odcld = secdiff * taucmc and abscld = 1 - exp(-odcld) for the sweep kernels.
 // The layer axis is parallel here, so the exp() and the table lookups stay out of the sweeps' vertical recurrences.
-__global__ void __launch_bounds__(128) cldoptics_kernel(ColIn in, Scratch s, RunCfg r) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int l = blockIdx.y;
-    if (i >= r.ncol) return;
+// (column i of the pass, layer l) whose five mask words are w (flag bit of word 4 cleared)
+__device__ __forceinline__ void cldoptics_point(const ColIn& in, const Scratch& s, const RunCfg& r, const int i, const int l,
+                                                const unsigned (&w)[5]) {
     const long P = s.pitch;
-    const unsigned* mw = s.mask + ((long)l * 5) * P + i;
-    const unsigned w4 = mw[4 * P];
-    if ((w4 >> 31) == 0) return;  // icldlyr = 0
     const long ci = r.c0 + i;
     const long a = ci + in.ld * l;
-    const unsigned w[5] = {mw[0], mw[P], mw[2 * P], mw[3 * P], w4 & 0x7fffffffu};
     const double ciwp = in.ciwp[a], clwp = in.clwp[a];
     const double radice = in.rei[a], radliq = in.rel[a];
     double* q = s.cldb + ((((long)(i >> 7) * r.nlay + l) * NBND) * 2) * 128 + (i & 127);
@@ -272,6 +267,17 @@ __global__ void __launch_bounds__(128) cldoptics_kernel(ColIn in, Scratch s, Run
         q[(b * 2) * 128] = odcld;
         q[(b * 2 + 1) * 128] = 1. - exp(-odcld);
     }
+}
+__global__ void __launch_bounds__(128) cldoptics_kernel(ColIn in, Scratch s, RunCfg r) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int l = blockIdx.y;
+    if (i >= r.ncol) return;
+    const long P = s.pitch;
+    const unsigned* mw = s.mask + ((long)l * 5) * P + i;
+    const unsigned w4 = mw[4 * P];
+    if ((w4 >> 31) == 0) return;  // icldlyr = 0
+    const unsigned w[5] = {mw[0], mw[P], mw[2 * P], mw[3 * P], w4 & 0x7fffffffu};
+    cldoptics_point(in, s, r, i, l, w);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -688,16 +694,17 @@ __device__ __forceinline__ void kiss_jump(Kiss& k, const KissRun* __restrict__ R
 }
 
 constexpr int KISS_CPB = 8;  // columns per CTA: a CTA's mask words of one (layer, word) are one 32-byte sector
-__global__ void __launch_bounds__(160) mcica_kiss_par_kernel(ColIn in, Scratch s, RunCfg r, const KissJump* __restrict__ J,
-                                                             const KissRun* __restrict__ R) {
-    extern __shared__ unsigned mk_sm[];
+// One work item = KISS_CPB consecutive columns starting at i0.  FUSE_CLD: the cloud optics of those columns' cloudy layers
+// (cldoptics_point) follow from the mask words still in shared memory (needs colprep's secdiff in place).
+template <bool FUSE_CLD>
+__device__ __forceinline__ void kiss_item(const ColIn& in, const Scratch& s, const RunCfg& r, const KissJump* __restrict__ J,
+                                          const KissRun* __restrict__ R, unsigned* mk_sm, const int i0) {
     const int nlay = r.nlay;
     const int W5 = nlay * 5;
     unsigned* words = mk_sm;                                     // KISS_CPB x nlay x 5 mask words
     int* lst = reinterpret_cast<int*>(mk_sm + KISS_CPB * W5);    // KISS_CPB x nlay: the layers a column draws at, ascending
     int* nl = lst + KISS_CPB * nlay;                             // KISS_CPB: their number
     unsigned* top = reinterpret_cast<unsigned*>(nl + KISS_CPB);  // KISS_CPB: cloud top
-    const int i0 = blockIdx.x * KISS_CPB;
     const long P = s.pitch;
     const int icld = r.icld;
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
@@ -841,6 +848,56 @@ __global__ void __launch_bounds__(160) mcica_kiss_par_kernel(ColIn in, Scratch s
     }
     __syncthreads();
     if (tid < KISS_CPB && i0 + tid < r.ncol) s.ctop[i0 + tid] = (int)top[tid];
+    if constexpr (FUSE_CLD) {
+        // (column, layer) pairs of the item, column fastest: a warp's stores of a (layer, band) are 64-byte runs
+        for (int p = tid; p < KISS_CPB * nlay; p += blockDim.x) {
+            const int c = p % KISS_CPB, l = p / KISS_CPB;
+            if (i0 + c >= r.ncol) continue;
+            const unsigned* wp = words + c * W5 + l * 5;
+            const unsigned w5[5] = {wp[0], wp[1], wp[2], wp[3], wp[4]};
+            if ((w5[0] | w5[1] | w5[2] | w5[3] | w5[4]) == 0u) continue;
+            cldoptics_point(in, s, r, i0 + c, l, w5);
+        }
+    }
+}
+__global__ void __launch_bounds__(160) mcica_kiss_par_kernel(ColIn in, Scratch s, RunCfg r, const KissJump* __restrict__ J,
+                                                             const KissRun* __restrict__ R) {
+    extern __shared__ unsigned mk_sm[];
+    kiss_item<false>(in, s, r, J, R, mk_sm, (int)blockIdx.x * KISS_CPB);
+}
+// Work-queue form (set_option("mcica_beside", 1)): a grid of one CTA per SM, launched BEFORE taumol, stays resident in
+// the registers taumol's CTAs cannot use (65 536 - 3 x 16 384 per SM) and generates masks + cloud optics in the issue
+// slots the L1-bound band evaluations leave idle; a second launch of the same kernel with a full grid, ordered after
+// taumol, takes whatever items are left on the shared counter.
+#define LW_KISS_WORK_STATS 1
+__device__ unsigned long long g_kiss_stats[8];
+__global__ void __launch_bounds__(160, 8) mcica_kiss_work_kernel(ColIn in, Scratch s, RunCfg r, const KissJump* __restrict__ J,
+                                                              const KissRun* __restrict__ R, unsigned* __restrict__ ctr,
+                                                              const unsigned nitems, const int mop) {
+    extern __shared__ unsigned mk_sm[];
+    __shared__ unsigned sh_item;
+#ifdef LW_KISS_WORK_STATS
+    if (threadIdx.x == 0) {  // [0/2] first CTA start, [1/3] last CTA end (ns), [4] items taken when the mop-up launch began
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (atomicCAS(&g_kiss_stats[mop ? 2 : 0], 0ull, t) == 0ull && mop) g_kiss_stats[4] = *(volatile unsigned*)ctr;
+    }
+#endif
+    for (;;) {
+        __syncthreads();  // the previous item's shared words are free
+        if (threadIdx.x == 0) sh_item = atomicAdd(ctr, 1u);
+        __syncthreads();
+        const unsigned it = sh_item;
+        if (it >= nitems) break;
+        kiss_item<true>(in, s, r, J, R, mk_sm, (int)(it * KISS_CPB));
+    }
+#ifdef LW_KISS_WORK_STATS
+    if (threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        atomicMax(&g_kiss_stats[mop ? 3 : 1], t);
+    }
+#endif
 }
 
 // host side of the jumps ---------------------------------------------------------------------
@@ -1307,6 +1364,51 @@ void launch_mcica_kiss(const ColIn& in, const Scratch& s, const RunCfg& r, cudaS
     }
     const KissRun* R = g_kiss_sparse ? kiss_run_table(st) : nullptr;
     mcica_kiss_par_kernel<<<(unsigned)nblk(r.ncol, KISS_CPB), 160, smem, st>>>(in, s, r, J, R);
+}
+// Work-queue form of the KISS generator with the cloud optics fused (mcica_kiss_work_kernel).  resident > 0: resets the
+// counter and launches `resident` CTAs per SM (the launch that runs beside taumol: 2 x 160 threads x 48 registers fit the
+// 16 384 registers three taumol CTAs leave); resident = 0: a full grid that takes the items still on the counter.  Returns false when the jump tables are not available (the caller uses the grid form).
+__device__ unsigned g_kiss_ctr;
+bool launch_mcica_kiss_work(const ColIn& in, const Scratch& s, const RunCfg& r, int resident, cudaStream_t st) {
+    const long draws = r.icld == 3 ? 1 : (r.icld >= 4 ? 2L * r.nlay : (long)r.nlay);
+    const KissJump* J = kiss_jump_table(r.permuteseed, draws, st);
+    if (!J) return false;
+    const size_t smem = ((size_t)KISS_CPB * r.nlay * 6 + 2 * KISS_CPB) * sizeof(unsigned);
+    if (smem > 48 * 1024) {
+        static size_t attr_d[16] = {};
+        size_t& cur = attr_d[cur_dev_kj()];
+        if (smem > cur) {
+            cudaFuncSetAttribute(mcica_kiss_work_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cur = smem;
+        }
+    }
+    static int nsm_d[16] = {};
+    int& nsm = nsm_d[cur_dev_kj()];
+    if (!nsm) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const KissRun* R = g_kiss_sparse ? kiss_run_table(st) : nullptr;
+    unsigned* ctr = nullptr;
+    cudaGetSymbolAddress((void**)&ctr, g_kiss_ctr);
+    const unsigned nitems = (unsigned)nblk(r.ncol, KISS_CPB);
+    if (resident > 0) {
+        cudaMemsetAsync(ctr, 0, sizeof(unsigned), st);
+#ifdef LW_KISS_WORK_STATS
+        void* stats = nullptr;
+        cudaGetSymbolAddress(&stats, g_kiss_stats);
+        cudaMemsetAsync(stats, 0, sizeof(g_kiss_stats), st);
+#endif
+    }
+    unsigned grid = (unsigned)nsm * (resident > 0 ? (unsigned)resident : 8u);
+    if (grid > nitems) grid = nitems;
+    mcica_kiss_work_kernel<<<grid, 160, smem, st>>>(in, s, r, J, R, ctr, nitems, resident > 0 ? 0 : 1);
+    return true;
+}
+void kiss_work_stats(unsigned long long* out8) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out8, g_kiss_stats, sizeof(g_kiss_stats));
 }
 // dst[e + w*(i + ldd*k)] = (float) src[e + w*(c0 + i + lds*k)]   for e < w, i < ncol, k < nrows
 __global__ void cvt_kernel(const double* __restrict__ src, float* __restrict__ dst, int w, long lds, long ldd, long c0,

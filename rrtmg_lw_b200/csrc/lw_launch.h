@@ -14,6 +14,8 @@ struct DevPtrs;
 
 void launch_prep(const ColIn&, const Scratch&, const RunCfg&, cudaStream_t);
 void launch_mcica_kiss(const ColIn&, const Scratch&, const RunCfg&, cudaStream_t);
+void kiss_work_stats(unsigned long long* out8);
+bool launch_mcica_kiss_work(const ColIn&, const Scratch&, const RunCfg&, int resident, cudaStream_t);
 // Mersenne-Twister generator (irng = 1): masks of a chunk whose first column is global column mt_c0 of a call over
 // mt_ncol columns; returns the kernels launched or -1 (allocation failure)
 int launch_mcica_mt(const ColIn&, const Scratch&, const RunCfg&, long mt_ncol, long mt_c0, cudaStream_t);
@@ -55,7 +57,7 @@ void set_kiss_sparse(int on);  // KISS generator: step over the draws of cloud-f
 void launch_colprep(const ColIn&, const Scratch&, const RunCfg&, cudaStream_t);
 void launch_cldarrays(const ColIn&, const Scratch&, const RunCfg&, cudaStream_t);  // strict entry, two-phase path; needs secdiff
 void launch_cldoptics(const ColIn&, const Scratch&, const RunCfg&, cudaStream_t);  // needs the masks and secdiff
-void launch_taumol(const ColIn&, const Scratch&, const RunCfg&, cudaStream_t);
+int launch_taumol(const ColIn&, const Scratch&, const RunCfg&, cudaStream_t);  // returns the number of launches
 #define LW_DECL_STU(n)                                                                                             \
     bool launch_sweep_stu##n(int b0, int nb, int cld, int idrv, const ColIn&, const ColOut&, const Scratch&, const RunCfg&, \
                              const SweepTab&, cudaStream_t);                                                                        \

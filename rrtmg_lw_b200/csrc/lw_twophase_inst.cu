@@ -27,10 +27,45 @@ cudaError_t LW_CAT(upload_constants_stu, LW_STU)(const ConstTab& c, const DevPtr
 }
 
 #if LW_STU == 0
-void launch_taumol(const ColIn& in, const Scratch& s, const RunCfg& r, cudaStream_t st) {
+// The 16 bands are evaluated by a few launches of the (column, layer) kernel, each instantiated for a band group
+// (mask: bit b-1 = band b) and compiled for its own number of resident CTAs; every launch redoes inatm / setcoef / the
+// sort for its bands (about 2 ms per 1 M columns).  LW_TAUMOL_GROUPS lists them as X(mask, min_ctas_per_sm).
+// Default (variant 0): the five bands with two key species in BOTH atmosphere halves (3 4 5 7 9) at 128 registers /
+// 4 CTAs, the other eleven at 80 registers / 6 CTAs -- the kernel is latency-bound, its rate follows the resident warps,
+// and those eleven spill < 60 bytes each at 80 registers while the five lose at anything below 128.  81.1 -> 70.7 ms per
+// 1 M columns against the one-launch form (variant 9); variants 1-8 are the other groupings that were measured
+// (profiles/r02_taumol_band_groups_experiment.log).
+#ifndef LW_TAUMOL_VARIANT
+#define LW_TAUMOL_VARIANT 0
+#endif
+#if LW_TAUMOL_VARIANT == 0
+#define LW_TAUMOL_GROUPS X(0x015cu, 4) X(0xfea3u, 6)
+#elif LW_TAUMOL_VARIANT == 1
+#define LW_TAUMOL_GROUPS X(0x001cu, 4) X(0x0140u, 4) X(0xfea3u, 6)
+#elif LW_TAUMOL_VARIANT == 2
+#define LW_TAUMOL_GROUPS X(0x015cu, 4) X(0x00a3u, 6) X(0xfe00u, 6)
+#elif LW_TAUMOL_VARIANT == 3
+#define LW_TAUMOL_GROUPS X(0x001cu, 4) X(0x0140u, 4) X(0x00a3u, 6) X(0xfe00u, 6)
+#elif LW_TAUMOL_VARIANT == 4
+#define LW_TAUMOL_GROUPS X(0x4u, 4) X(0x8u, 4) X(0x10u, 4) X(0x40u, 4) X(0x100u, 4) X(0xfea3u, 6)
+#elif LW_TAUMOL_VARIANT == 5
+#define LW_TAUMOL_GROUPS X(0x015cu, 4) X(0xfea3u, 7)
+#elif LW_TAUMOL_VARIANT == 6
+#define LW_TAUMOL_GROUPS X(0x4u, 4) X(0x8u, 4) X(0x10u, 4) X(0x40u, 4) X(0x100u, 4) X(0x00a3u, 6) X(0xfe00u, 6)
+#elif LW_TAUMOL_VARIANT == 9
+#define LW_TAUMOL_GROUPS X(0xffffu, LW_TAUMOL_MINB)
+#elif LW_TAUMOL_VARIANT == 7
+#define LW_TAUMOL_GROUPS X(0x4u, 5) X(0x8u, 5) X(0x10u, 5) X(0x40u, 5) X(0x100u, 5) X(0xfea3u, 6)
+#elif LW_TAUMOL_VARIANT == 8
+#define LW_TAUMOL_GROUPS X(0x015cu, 4) X(0x00a3u, 6) X(0x0e00u, 6) X(0xf000u, 6)
+#endif
+template <unsigned BMASK, int MINB>
+static void launch_taumol_part(const ColIn& in, const Scratch& s, const RunCfg& r, cudaStream_t st) {
     const dim3 grid((unsigned)((r.ncol + TAUMOL_THREADS - 1) / TAUMOL_THREADS), (unsigned)r.nlay);
-    constexpr size_t smem = (size_t)NFIELD * TAUMOL_THREADS * sizeof(double);
-    auto kern = taumol_kernel<0xffffu, LW_TAUMOL_MINB>;
+    // RRTMG_LW_TAUMOL_SMEM_PAD (bytes, dev knob): extra dynamic shared memory per CTA, to lower the residency
+    static const size_t pad = std::getenv("RRTMG_LW_TAUMOL_SMEM_PAD") ? (size_t)std::atol(std::getenv("RRTMG_LW_TAUMOL_SMEM_PAD")) : 0;
+    const size_t smem = (size_t)NFIELD * TAUMOL_THREADS * sizeof(double) + pad;
+    auto kern = taumol_kernel<BMASK, MINB>;
     if (smem > 40 * 1024) {  // static (sort arrays) + dynamic shared memory beyond 48 KB needs the opt-in
         static unsigned attr_set = 0u;  // bit d = done on device d
         int dev = 0;
@@ -41,6 +76,24 @@ void launch_taumol(const ColIn& in, const Scratch& s, const RunCfg& r, cudaStrea
         }
     }
     kern<<<grid, TAUMOL_THREADS, smem, st>>>(in, s, r);
+}
+int launch_taumol(const ColIn& in, const Scratch& s, const RunCfg& r, cudaStream_t st) {
+    int n = 0;
+    constexpr unsigned all = 0u
+#define X(mask, minb) | (mask)
+        LW_TAUMOL_GROUPS
+#undef X
+        ;
+    constexpr unsigned sum = 0u
+#define X(mask, minb) + (mask)
+        LW_TAUMOL_GROUPS
+#undef X
+        ;
+    static_assert(all == 0xffffu && sum == 0xffffu, "LW_TAUMOL_GROUPS must hold every band exactly once");
+#define X(mask, minb) launch_taumol_part<(mask), (minb)>(in, s, r, st); ++n;
+    LW_TAUMOL_GROUPS
+#undef X
+    return n;
 }
 #elif LW_STU == 6
 void launch_gridcloud_prep(const ColIn& in, const Scratch& s, const RunCfg& r, int maxran, cudaStream_t st) {
