@@ -54,6 +54,9 @@ struct SweepRing {
     static constexpr int S_TLAY = G::NGG, S_TLEV = G::NGG + 1, S_PF = G::NGG + 2;
     static constexpr int S_INT = S_PF + G::NPFG;
     static constexpr int SLOTS = S_INT + 4 / IPS;
+#ifndef LW_SWEEP_L2PF
+#define LW_SWEEP_L2PF 0  // layers beyond the ring's own prefetch distance whose state words are pulled into L2
+#endif
 #ifndef LW_SWEEP_NST
 #define LW_SWEEP_NST 2
 #endif
@@ -355,6 +358,16 @@ __global__ void __launch_bounds__(SWEEP_THREADS, MINB) rtrnmc_kernel(ColIn in, C
             }
         }
         cp_commit();
+#if LW_SWEEP_L2PF > 0
+        {   // the state words of the layer LW_SWEEP_L2PF further on: one L2 prefetch per 128-byte line of the CTA's block
+            const int lev2 = down ? lev - LW_SWEEP_L2PF : lev + LW_SWEEP_L2PF;
+            if (lev2 >= 1 && lev2 <= nlay) {
+                const char* base = reinterpret_cast<const char*>(s.od + ((blk_lay0 + (lev2 - 1)) * NGPT + G0) * 128);
+                for (int ln = tid; ln < NGG * 8; ln += SWEEP_THREADS)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + ln * 128));
+            }
+        }
+#endif
     };
     // views of a stage
     auto st_d = [&](int stage, int slot) { return ring[((size_t)stage * RG::SLOTS + slot) * SWEEP_THREADS + tid]; };

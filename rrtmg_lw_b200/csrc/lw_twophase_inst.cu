@@ -127,11 +127,31 @@ bool launch_gridcloud_sweep(int band, int maxran, int idrv, const ColIn& in, con
 #ifndef LW_SWEEP_BASE_REGS
 #define LW_SWEEP_BASE_REGS 72
 #endif
+#ifndef LW_SWEEP_MINB_6G
+#define LW_SWEEP_MINB_6G 6  // band 10: 80 registers, 8 bytes of spill; 3.38 -> 3.13 ms per 1 M columns
+#endif
+#ifndef LW_SWEEP_MINB_8G
+#define LW_SWEEP_MINB_8G 5  // bands 6 8 11 12: 96 registers, no spill; -2 % (80 registers: spills, slower)
+#endif
+#ifndef LW_SWEEP_MINB_10G
+#define LW_SWEEP_MINB_10G 4  // band 1 and the 13-16 group spill at 96 registers: +17 %
+#endif
+#ifndef LW_SWEEP_MINB_12G
+#define LW_SWEEP_MINB_12G 4  // bands 2 7 9 spill at 96 registers: +15 %
+#endif
 constexpr int sweep_minb(int ngg, int cld, int idrv) {
     // part of the clear-sky stream of a wide cloudy group lives in shared memory (SweepRing::clr_smem): 2 registers less each
     const int clr_sm = (cld != CLD_NONE && ngg >= LW_SWEEP_CLR_SMEM_MIN) ? LW_SWEEP_CLR_SMEM_N : 0;
     const int est = ((cld != CLD_NONE ? 4 : 2) * ngg * (idrv ? 2 : 1) - 2 * clr_sm) + LW_SWEEP_BASE_REGS;
-    return est <= 128 ? 4 : (est <= 168 ? 3 : 2);
+    int m = est <= 128 ? 4 : (est <= 168 ? 3 : 2);
+    // narrow groups without the dT derivatives: more resident CTAs (the sweeps are latency-bound too)
+    if (m == 4 && idrv == 0) {
+        if (ngg <= 6) m = LW_SWEEP_MINB_6G;
+        else if (ngg <= 8) m = LW_SWEEP_MINB_8G;
+        else if (ngg <= 10) m = LW_SWEEP_MINB_10G;
+        else if (ngg <= 12) m = LW_SWEEP_MINB_12G;
+    }
+    return m;
 }
 
 template <int B0, int NB>
