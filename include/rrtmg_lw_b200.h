@@ -188,9 +188,10 @@ int rrtmg_lw_b200_set_chunk(int max_columns);
  *   all four; 0 = one kernel each.
  * "band_lo" / "band_hi": band range istart..iend of the following runs (default 1..16): only those bands enter the
  *   flux sums, as in the column-mode program's per-band output (src/rrtmg_lw.1col.f90:463-467); two-phase path.
- * "concurrency": 1 (default) = independent kernels of a pass run on side streams of the library (McICA generator and
- *   cloud optics beside taumol, the sweep kernels beside each other), forked from and joined to the caller's stream;
- *   0 = everything on the caller's stream.
+ * "concurrency": 1 (default) = independent kernels of a pass run on side streams of the library, forked from and joined
+ *   to the caller's stream: the McICA generator and the cloud optics beside taumol, and -- for passes of up to 393 216
+ *   columns, where the overlap of the kernels' tails pays -- the sweep kernels beside each other; 0 = everything on the
+ *   caller's stream; 2 / 3 = only the first / only the second half of that schedule (A/B runs).
  * "mcica_beside": n = 1..4: the KISS generator and the cloud optics run as ONE work-queue kernel with n CTAs per SM resident
  *   beside taumol (launched ahead of it on a high-priority stream), plus a full-grid launch after taumol for the items left;
  *   0 (default) = generator and cloud optics as their own kernels.  A measured and rejected scheduling variant (bit-identical

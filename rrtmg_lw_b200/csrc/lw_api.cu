@@ -50,7 +50,7 @@ struct Ctx {
                                 // ahead of taumol's whenever registers come free
     cudaEvent_t e_fork = nullptr, e_colprep = nullptr, e_t = nullptr, e_cld = nullptr, e_side[NSIDE] = {};
     int tail_group = 1;       // set_option("tail_group", 0): bands 13-16 as four sweep kernels instead of one
-    int concurrency = 1;      // set_option("concurrency", 0) keeps every kernel on the caller's stream
+    int concurrency = 1;      // set_option("concurrency", 0) keeps every kernel on the caller's stream; 1 = auto (see run_device)
     long out_ld = 0;          // set_option("out_ld", n): column extent of the OUTPUT arrays of device-pointer calls (0 = ld)
     long cap_cols = 0;
     int cap_lay = 0;
@@ -339,7 +339,13 @@ int run_device(Mode mode, int ncol, int nlay, int icld, int idrv, int inflag, in
             // beside taumol, and the sweep kernels are dealt over the caller's stream and the side streams.
             const bool conc = G.concurrency != 0 && !G.timing && S.dbg_col < 0;
             if (conc && (rc = ensure_side_streams()) != 0) return rc;
-            cudaStream_t qm = conc ? G.side[0] : st;  // masks + cloud optics
+            // The sweep kernels are dealt over four streams only for passes of up to 393 216 columns: there the overlap of
+            // their tails pays (131 072 columns: 190.4 -> 177.9 ms per 1 M columns), while four sweep kernels interleaved
+            // on every SM cost 4 ms per 1 M columns at 524 288 (173.5 -> 177.5; profiles/r02_stream_schedule_experiment.log).
+            // concurrency 2 / 3 force one half of the schedule (masks beside taumol only / sweeps over streams only).
+            const bool conc_masks = conc && G.concurrency != 3;
+            const bool conc_sweeps = conc && (G.concurrency == 3 || (G.concurrency == 1 && r.ncol <= 393216));
+            cudaStream_t qm = conc_masks ? G.side[0] : st;  // masks + cloud optics
             if (conc) {
                 CK(cudaEventRecord(G.e_fork, st));
                 for (auto& q : G.side) CK(cudaStreamWaitEvent(q, G.e_fork, 0));
@@ -389,7 +395,7 @@ int run_device(Mode mode, int ncol, int nlay, int icld, int idrv, int inflag, in
             int nsweep = 0;
             auto sweep = [&](int b0, int nb) -> bool {
                 cudaStream_t q = st;
-                if (conc) { const int k = nsweep % (Ctx::NSIDE + 1); q = k == 0 ? st : G.side[k - 1]; }
+                if (conc_sweeps) { const int k = nsweep % (Ctx::NSIDE + 1); q = k == 0 ? st : G.side[k - 1]; }
                 ++nsweep;
                 if (G.timing) CK(cudaEventRecord(G.evb[nstage++], st));
                 slots |= 1u << (b0 - 1);
@@ -407,7 +413,7 @@ int run_device(Mode mode, int ncol, int nlay, int icld, int idrv, int inflag, in
                 const int order[NBND] = {3, 5, 4, 2, 7, 9, 1, 6, 8, 11, 12, 10, 13, 14, 15, 16};
                 const bool tail4 = G.tail_group != 0 && cld != CLD_GRID && b_lo <= 13 && b_hi == NBND;
                 for (int k = 0; k < NBND; ++k) {
-                    const int b = conc ? order[k] : k + 1;
+                    const int b = conc_sweeps ? order[k] : k + 1;
                     if (b < b_lo || b > b_hi) continue;
                     if (tail4 && b >= 13) {
                         if (b == 13 && !sweep(13, 4)) return RRTMG_LW_ERR_ARG;
@@ -1216,7 +1222,7 @@ extern "C" int rrtmg_lw_b200_set_option(const char* name, int value) {
         return RRTMG_LW_OK;
     }
     if (std::strcmp(name, "concurrency") == 0) {
-        if (value != 0 && value != 1) return RRTMG_LW_ERR_ARG;
+        if (value < 0 || value > 3) return RRTMG_LW_ERR_ARG;
         G.concurrency = value;
         return RRTMG_LW_OK;
     }
