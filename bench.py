@@ -529,7 +529,7 @@ def main():
         two = args.band_kernel == 4 and args.precision == 64
         roof = {
             "bound": "fp64",
-            "kernel": ("taumol_kernel + 13 rtrnmc_kernel<B0,NB,CLD_MASK,0> (bands 1-12 one each, bands 13-16 together) per pass of %d columns (timed one after the other)"
+            "kernel": ("2 taumol_kernel<band group> (bands 3 4 5 7 9 / the other eleven) + 13 rtrnmc_kernel<B0,NB,CLD_MASK,0> (bands 1-12 one each, bands 13-16 together) per pass of %d columns (timed one after the other)"
                        if two else "band_kernel<1..16,CLD_MASK,0> (16 launches per pass of %d columns)") % args.chunk,
             "achieved": flops_per_col * cols_per_s_band / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
             "frac": flops_per_col * cols_per_s_band / 1e12 / fp64_peak,

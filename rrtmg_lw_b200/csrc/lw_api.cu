@@ -344,7 +344,8 @@ int run_device(Mode mode, int ncol, int nlay, int icld, int idrv, int inflag, in
             // on every SM cost 4 ms per 1 M columns at 524 288 (173.5 -> 177.5; profiles/r02_stream_schedule_experiment.log).
             // concurrency 2 / 3 force one half of the schedule (masks beside taumol only / sweeps over streams only).
             const bool conc_masks = conc && G.concurrency != 3;
-            const bool conc_sweeps = conc && (G.concurrency == 3 || (G.concurrency == 1 && r.ncol <= 393216));
+            const bool conc_sweeps = conc && (G.concurrency >= 3 || (G.concurrency == 1 && r.ncol <= 393216));
+            const int sweep_streams = G.concurrency == 4 ? 2 : (G.concurrency == 5 ? 3 : Ctx::NSIDE + 1);  // 4 / 5: dev knobs
             cudaStream_t qm = conc_masks ? G.side[0] : st;  // masks + cloud optics
             if (conc) {
                 CK(cudaEventRecord(G.e_fork, st));
@@ -395,7 +396,7 @@ int run_device(Mode mode, int ncol, int nlay, int icld, int idrv, int inflag, in
             int nsweep = 0;
             auto sweep = [&](int b0, int nb) -> bool {
                 cudaStream_t q = st;
-                if (conc_sweeps) { const int k = nsweep % (Ctx::NSIDE + 1); q = k == 0 ? st : G.side[k - 1]; }
+                if (conc_sweeps) { const int k = nsweep % sweep_streams; q = k == 0 ? st : G.side[k - 1]; }
                 ++nsweep;
                 if (G.timing) CK(cudaEventRecord(G.evb[nstage++], st));
                 slots |= 1u << (b0 - 1);
@@ -1222,7 +1223,7 @@ extern "C" int rrtmg_lw_b200_set_option(const char* name, int value) {
         return RRTMG_LW_OK;
     }
     if (std::strcmp(name, "concurrency") == 0) {
-        if (value < 0 || value > 3) return RRTMG_LW_ERR_ARG;
+        if (value < 0 || value > 5) return RRTMG_LW_ERR_ARG;
         G.concurrency = value;
         return RRTMG_LW_OK;
     }
