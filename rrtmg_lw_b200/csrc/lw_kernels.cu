@@ -665,7 +665,8 @@ struct KissJump {
     unsigned a1[NGPT], c1[NGPT];   // s1_n = a1 * s1_0 + c1
     unsigned p3[NGPT], p4[NGPT];   // a^(n-1) mod m (applied after one explicit step; n = 0 -> unused)
     unsigned n[NGPT];              // the jump distance itself
-    unsigned m2[NGPT][32];         // columns of the xorshift matrix power
+    unsigned w2[NGPT][8][16];      // xorshift matrix power as 4-bit window tables: y = XOR_k w2[.][k][(x >> 4k) & 15]
+                                   // (8 lookups instead of 32 conditional XORs of matrix columns)
 };
 constexpr unsigned KISS_M3 = 18000u * 65536u - 1u, KISS_M4 = 30903u * 65536u - 1u;
 // n-step jumps for n = 1 .. LW_MAXLAY (seed-independent, built once per device): a run of n cloud-free layers draws n
@@ -674,7 +675,7 @@ constexpr unsigned KISS_M3 = 18000u * 65536u - 1u, KISS_M4 = 30903u * 65536u - 1
 struct KissRun {
     unsigned a1[LW_MAXLAY + 1], c1[LW_MAXLAY + 1];
     unsigned p3[LW_MAXLAY + 1], p4[LW_MAXLAY + 1];  // a^(n-1) mod m
-    unsigned m2[LW_MAXLAY + 1][32];
+    unsigned w2[LW_MAXLAY + 1][8][16];
 };
 #ifndef LW_KISS_JUMP_MIN
 #define LW_KISS_JUMP_MIN 8  // shorter clear runs are stepped draw by draw (a jump costs about as much as 6 steps)
@@ -683,8 +684,8 @@ __device__ __forceinline__ void kiss_jump(Kiss& k, const KissRun* __restrict__ R
     k.s1 = R->a1[n] * k.s1 + R->c1[n];
     unsigned y = 0;
     const unsigned z2 = k.s2;
-#pragma unroll 8
-    for (int b = 0; b < 32; ++b) y ^= ((z2 >> b) & 1u) ? R->m2[n][b] : 0u;
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) y ^= R->w2[n][kk][(z2 >> (4 * kk)) & 15u];
     k.s2 = y;
     unsigned t3 = 18000u * (k.s3 & 65535u) + (k.s3 >> 16);
     unsigned t4 = 30903u * (k.s4 & 65535u) + (k.s4 >> 16);
@@ -750,8 +751,8 @@ __device__ __forceinline__ void kiss_item(const ColIn& in, const Scratch& s, con
             const unsigned z4 = (unsigned)(int)((p4 - (double)(int)p4) * 1000000000.0);
             k.s1 = J->a1[sc] * z1 + J->c1[sc];
             unsigned y = 0;
-#pragma unroll 8
-            for (int b = 0; b < 32; ++b) y ^= ((z2 >> b) & 1u) ? J->m2[sc][b] : 0u;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) y ^= J->w2[sc][kk][(z2 >> (4 * kk)) & 15u];
             k.s2 = y;
             if (J->n[sc] == 0u) {
                 k.s3 = z3; k.s4 = z4;
@@ -913,6 +914,15 @@ unsigned m2_apply(const unsigned* m, unsigned x) {
     for (int b = 0; b < 32; ++b) if ((x >> b) & 1u) y ^= m[b];
     return y;
 }
+// 4-bit window tables of a 32x32 GF(2) matrix given by its columns: w[k][v] = XOR of the columns 4k + b over the bits b of v
+void m2_windows(const unsigned* m, unsigned (*w)[16]) {
+    for (int k = 0; k < 8; ++k)
+        for (unsigned v = 0; v < 16; ++v) {
+            unsigned y = 0;
+            for (int b = 0; b < 4; ++b) if ((v >> b) & 1u) y ^= m[4 * k + b];
+            w[k][v] = y;
+        }
+}
 KissMap kiss_identity() {
     KissMap k; k.a1 = 1u; k.c1 = 0u; k.p3 = 1; k.p4 = 1;
     for (int b = 0; b < 32; ++b) k.m2[b] = 1u << b;
@@ -971,7 +981,13 @@ int kiss_jump_selftest() {
                 s4 = 30903u * (s4 & 65535u) + (s4 >> 16);
             }
             const unsigned j1 = m.a1 * z[0] + m.c1;
-            const unsigned j2 = m2_apply(m.m2, z[1]);
+            unsigned j2 = m2_apply(m.m2, z[1]);
+            {   // the device applies the matrix through its 4-bit window tables
+                unsigned w[8][16], y = 0;
+                m2_windows(m.m2, w);
+                for (int k = 0; k < 8; ++k) y ^= w[k][(z[1] >> (4 * k)) & 15u];
+                if (y != j2) j2 = ~s2;  // counted as a mismatch below
+            }
             unsigned j3 = z[2], j4 = z[3];
             if (n > 0) {
                 j3 = 18000u * (z[2] & 65535u) + (z[2] >> 16);
@@ -1002,7 +1018,7 @@ static const KissJump* kiss_jump_table(int permuteseed, long draws, cudaStream_t
     for (int sc = 0; sc < NGPT; ++sc) {
         const unsigned long long n = n0 + (unsigned long long)sc * (unsigned long long)draws;
         h.a1[sc] = cur.a1; h.c1[sc] = cur.c1;
-        for (int b = 0; b < 32; ++b) h.m2[sc][b] = cur.m2[b];
+        m2_windows(cur.m2, h.w2[sc]);
         h.n[sc] = n > 0xffffffffull ? 0xffffffffu : (unsigned)n;
         if (n == 0) { h.p3[sc] = 1u; h.p4[sc] = 1u; }
         else {
@@ -1029,10 +1045,14 @@ static const KissRun* kiss_run_table(cudaStream_t st) {
         h.p3[n] = (unsigned)cur.p3; h.p4[n] = (unsigned)cur.p4;
         cur = kiss_compose(one, cur);       // n steps
         h.a1[n] = cur.a1; h.c1[n] = cur.c1;
-        for (int b = 0; b < 32; ++b) h.m2[n][b] = cur.m2[b];
+        m2_windows(cur.m2, h.w2[n]);
     }
     h.a1[0] = 1u; h.c1[0] = 0u; h.p3[0] = 1u; h.p4[0] = 1u;
-    for (int b = 0; b < 32; ++b) h.m2[0][b] = 1u << b;
+    {
+        unsigned id[32];
+        for (int b = 0; b < 32; ++b) id[b] = 1u << b;
+        m2_windows(id, h.w2[0]);
+    }
     if (cudaMalloc((void**)&d, sizeof(KissRun)) != cudaSuccess) { d = nullptr; return nullptr; }
     if (cudaMemcpyAsync(d, &h, sizeof(KissRun), cudaMemcpyHostToDevice, st) != cudaSuccess) return nullptr;
     cudaStreamSynchronize(st);
