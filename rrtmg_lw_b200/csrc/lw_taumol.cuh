@@ -229,12 +229,19 @@ __global__ void __launch_bounds__(TAUMOL_THREADS, MINB) taumol_kernel(ColIn in, 
     // a CTA are independent, so the (column -> lane) assignment is free: a counting sort on the (pressure level jp,
     // temperature index jt) pair puts columns that read the same (p, T) corner rows in neighbouring lanes.  Each thread
     // then evaluates the bands of the column it was handed (fields, indices and flags come from shared memory).
-    __shared__ int sh_hist[64];
+    // Third key (LW_TAUMOL_SORT_ETA): the eta bin of the binary-species bands -- H2O / CO2 below the tropopause (bands 3 4 5
+    // 12), O3 / CO2 above it (bands 4 5) -- picks the js rows inside a (jp, jt) group of the k-tables; lanes that agree in
+    // it touch the same 128-byte lines, and the wavefronts of a warp-wide row load are the distinct lines it touches.
+#ifndef LW_TAUMOL_SORT_ETA
+#define LW_TAUMOL_SORT_ETA 1
+#endif
+    constexpr int NBIN = LW_TAUMOL_SORT_ETA ? 128 : 64;
+    __shared__ int sh_hist[NBIN];
     __shared__ int sh_perm[TAUMOL_THREADS];
     __shared__ int sh_ipk[TAUMOL_THREADS];
     __shared__ double sh_pavel[TAUMOL_THREADS];
     __shared__ int sh_jpmin;
-    if (tid < 64) sh_hist[tid] = 0;
+    for (int k = tid; k < NBIN; k += TAUMOL_THREADS) sh_hist[k] = 0;
     if (tid == 0) sh_jpmin = 64;
     sh_ipk[tid] = ipk | (lower ? (1 << 30) : 0);
     sh_pavel[tid] = pavel;
@@ -242,20 +249,32 @@ __global__ void __launch_bounds__(TAUMOL_THREADS, MINB) taumol_kernel(ColIn in, 
     atomicMin(&sh_jpmin, jp);
     __syncthreads();
     int bin = (jp - sh_jpmin) * 5 + (jt - 1);
-    bin = bin > 63 ? 63 : bin;
+#if LW_TAUMOL_SORT_ETA
+    {
+        const double a = lower ? colh2o : colo3;
+        const double sp = a + ldg(&g.rat[lower ? 0 : 5][jp - 1]) * colco2;
+        int eta = (int)((lower ? 8. : 4.) * (a / sp));
+        eta = eta < 0 ? 0 : (eta > 7 ? 7 : eta);
+        bin = bin * 8 + eta;
+    }
+#endif
+    bin = bin > NBIN - 1 ? NBIN - 1 : bin;
     const int pos = atomicAdd(&sh_hist[bin], 1);
     __syncthreads();
-    if (tid < 32) {  // exclusive scan of the 64 bin counts
-        const int c0 = sh_hist[2 * tid], c1 = sh_hist[2 * tid + 1];
-        int incl = c0 + c1;
+    if (tid < 32) {  // exclusive scan of the bin counts
+        constexpr int PER = NBIN / 32;
+        int c[PER], sum = 0;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) { c[k] = sh_hist[PER * tid + k]; sum += c[k]; }
+        int incl = sum;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const int up = __shfl_up_sync(0xffffffffu, incl, d);
             if (tid >= d) incl += up;
         }
-        const int excl = incl - (c0 + c1);
-        sh_hist[2 * tid] = excl;
-        sh_hist[2 * tid + 1] = excl + c0;
+        int run = incl - sum;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) { sh_hist[PER * tid + k] = run; run += c[k]; }
     }
     __syncthreads();
     sh_perm[sh_hist[bin] + pos] = tid;
