@@ -590,3 +590,33 @@ def test_init_from_the_table_image_is_bit_identical(gpu, oracle, kblob):
             assert tabs[n].size > 0 and np.array_equal(api.get_table(n), tabs[n]), n
     finally:
         api.rrtmg_lw_ini(1004.0, kblob, 4)
+
+
+@pytest.mark.parametrize("idrv", [0, 1])
+def test_schedule_variants_are_bit_identical(gpu, oracle, idrv):
+    """The scheduling switches change WHERE kernels run, never what they compute: serial (concurrency 0), masks beside
+    taumol only (2), sweeps over streams only (3) and the resident McICA work-queue kernel with the cloud optics fused
+    (mcica_beside 1 / 2, a second launch of the same kernel taking the items left) give the default schedule's fluxes
+    bit for bit, on a ragged batch cut into three passes; and the default's agree with the oracle to 1e-6."""
+    b = synth.make_batch(1300, 72, cloudy=True, aerosol=True, seed=21)
+    keys = KEYS + (("duflx_dt", "duflxc_dt") if idrv else ())
+    gpu.set_chunk(512)
+    try:
+        ref = driver.run_fused(b, icld=2, idrv=idrv, device="cuda:0")
+        gpu.sync()
+        ref = {k: ref[k].clone() for k in keys}
+        for name, value in (("concurrency", 0), ("concurrency", 2), ("concurrency", 3), ("mcica_beside", 1), ("mcica_beside", 2)):
+            gpu.set_option(name, value)
+            try:
+                got = driver.run_fused(b, icld=2, idrv=idrv, device="cuda:0")
+                gpu.sync()
+                for k in keys:
+                    assert torch.equal(got[k], ref[k]), (name, value, k)
+            finally:
+                gpu.set_option(name, 1 if name == "concurrency" else 0)
+    finally:
+        gpu.set_chunk(262144)
+    mc = oracle.mcica_subcol_lw(b, 2, permuteseed=1, irng=0)
+    want = oracle.rrtmg_lw(b, icld=2, idrv=idrv, inflglw=2, iceflglw=3, liqflglw=1, mc=mc, nthreads=8)
+    assert want["rc"] == 0
+    _check(ref, want, idrv, what="default schedule, three passes")
