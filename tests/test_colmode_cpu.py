@@ -279,3 +279,40 @@ def test_rrtatm_layering_of_the_sonde_case(suite, oracle):
         pwv_cm = h2o.sum() * 18.015 / 6.02214199e23      # g cm-2 = cm of precipitable water
         assert 1.0 < pwv_cm < 6.0                         # a humid mid-latitude summer sounding once AIRMWT is set
         assert np.array_equal(np.array(wet.pz), pz)
+
+
+def test_rrtatm_pieces():
+    """Pieces of the rrtatm restatement on their own: DEFALT's four-point Lagrange interpolation returns a model level
+    exactly at that level and stays monotone in pressure between levels; WATVAP / CONVRT give the same number density for
+    the same humidity written in different units (ppmv, g/kg with AIRMWT set, mb partial pressure, dew point); modes of
+    LBLATM outside the restated subset are refused by name."""
+    from rrtmg_lw_b200 import rrtatm
+    A = rrtatm._us_standard()
+    for k in (0, 7, 25, 49):
+        w = [0.0] * 7
+        p, t = rrtatm._defalt(A["alt_km"][k], 6, 6, [6] * 7, 0.0, 0.0, w)
+        assert abs(p / A["p_mb"][k] - 1.0) < 1e-12 and abs(t - A["t_k"][k]) < 1e-9
+        assert all(abs(w[m] - A["amol_ppmv"][m][k]) <= 1e-9 * max(1.0, abs(w[m])) for m in range(7))
+    ps = [rrtatm._defalt(z, 6, 6, [10] * 7, 0.0, 0.0, [0.0] * 7)[0] for z in np.linspace(0.0, 100.0, 401)]
+    assert all(b < a for a, b in zip(ps, ps[1:]))
+    with pytest.raises(ValueError):
+        rrtatm._defalt(121.0, 6, 6, [6] * 7, 0.0, 0.0, [0.0] * 7)
+    # one humidity, four spellings: 10 000 ppmv at 900 mb, 285 K
+    p, t = 900.0, 285.0
+    rho = rrtatm.ALOSMT * (p / rrtatm.PZERO) * (rrtatm.TZERO / t)
+    vmr = 1.0e-2
+    d_ppmv = rrtatm._watvap(p, t, 10, vmr * 1e6, rho, 28.964)
+    d_gkg = rrtatm._watvap(p, t, 12, vmr * 18.015 / 28.964 * 1e3, rho, 28.964)
+    e_mb = d_ppmv / rho * p                                    # partial pressure of that density
+    d_mb = rrtatm._watvap(p, t, 14, e_mb, rho, 28.964)
+    assert abs(d_gkg / d_ppmv - 1.0) < 1e-12 and abs(d_mb / d_ppmv - 1.0) < 1e-12
+    assert rrtatm._watvap(p, t, 12, 5.0, rho, 0.0) == 0.0     # trap T18: AIRMWT = 0 zeroes a g/kg profile
+    sat = rrtatm._watvap(p, t, 17, 100.0, rho, 28.964)         # 100 % relative humidity
+    assert abs(rrtatm._watvap(p, t, 15, t, rho, 28.964) / sat - 1.0) < 1e-12       # dew point = temperature
+    assert 0.5 * sat < rrtatm._watvap(p, t, 17, 60.0, rho, 28.964) / 0.6 < 1.5 * sat
+    assert 3.0e17 < sat < 4.5e17                               # e_s(285 K) ~ 14 hPa -> 3.6e17 cm-3
+    rec31 = "    1    2   32    1    1    7    0"
+    with pytest.raises(NotImplementedError):
+        rrtatm.layer_atmosphere([rec31], 0)                    # MODEL = 1: model atmospheres are not restated
+    with pytest.raises(NotImplementedError):
+        rrtatm.layer_atmosphere(["    0    2    0    1    1    7    0"], 0)   # IBMAX = 0: automatic layering
