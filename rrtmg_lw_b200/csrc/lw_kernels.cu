@@ -252,6 +252,7 @@ __device__ __forceinline__ void cldoptics_point(const ColIn& in, const Scratch& 
     const double ciwp = in.ciwp[a], clwp = in.clwp[a];
     const double radice = in.rei[a], radliq = in.rel[a];
     double* q = s.cldb + ((((long)(i >> 7) * r.nlay + l) * NBND) * 2) * 128 + (i & 127);
+#pragma unroll
     for (int b = 0; b < NBND; ++b) {
         // the band's sub-column bits: g-points GOFF[b] .. GOFF[b] + NGC[b] - 1
         const int goff[NBND] = {0, 10, 22, 38, 52, 68, 76, 88, 96, 108, 114, 122, 130, 134, 136, 138};
