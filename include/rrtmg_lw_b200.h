@@ -191,7 +191,8 @@ int rrtmg_lw_b200_set_chunk(int max_columns);
  * "concurrency": 1 (default) = independent kernels of a pass run on side streams of the library, forked from and joined
  *   to the caller's stream: the McICA generator and the cloud optics beside taumol, and -- for passes of up to 393 216
  *   columns, where the overlap of the kernels' tails pays -- the sweep kernels beside each other; 0 = everything on the
- *   caller's stream; 2 / 3 = only the first / only the second half of that schedule (A/B runs).
+ *   caller's stream; 2 / 3 = only the first / only the second half of that schedule, 4 / 5 = the sweeps over two /
+ *   three streams (A/B runs; profiles/r02_stream_schedule_experiment.log).
  * "mcica_beside": n = 1..4: the KISS generator and the cloud optics run as ONE work-queue kernel with n CTAs per SM resident
  *   beside taumol (launched ahead of it on a high-priority stream), plus a full-grid launch after taumol for the items left;
  *   0 (default) = generator and cloud optics as their own kernels.  A measured and rejected scheduling variant (bit-identical
