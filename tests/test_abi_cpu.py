@@ -72,6 +72,32 @@ def test_kdata_put_validates_name_and_size():
     assert e.value.code == 7   # incomplete set
 
 
+def test_set_option_validates_names_and_ranges():
+    """rrtmg_lw_b200_set_option needs no device: every documented switch accepts its range and refuses the value next to
+    it with ERR_ARG (7); unknown names are refused; the header documents every name the library knows."""
+    from rrtmg_lw_b200 import api
+    ranges = {"concurrency": (0, 5), "mcica_beside": (0, 4), "tail_group": (0, 1), "kiss_sparse": (0, 1),
+              "sweep_groups": (0, 1)}
+    defaults = {"concurrency": 1, "mcica_beside": 0, "tail_group": 1, "kiss_sparse": 1, "sweep_groups": 0}
+    hdr = open(os.path.join(ROOT, "include", "rrtmg_lw_b200.h")).read()
+    for name, (lo, hi) in ranges.items():
+        assert '"%s"' % name in hdr, name
+        try:
+            for v in (lo, hi):
+                api.set_option(name, v)
+            for v in (lo - 1, hi + 1):
+                with pytest.raises(api.RrtmgLwError) as e:
+                    api.set_option(name, v)
+                assert e.value.code == 7, (name, v)
+        finally:
+            api.set_option(name, defaults[name])
+    with pytest.raises(api.RrtmgLwError) as e:
+        api.set_option("no_such_switch", 1)
+    assert e.value.code == 7
+    with pytest.raises(api.RrtmgLwError):
+        api.set_chunk(8)
+
+
 def test_fortran_shim_binds_only_exported_symbols():
     """Every bind(C, name=...) of fortran/rrtmg_lw_b200_shim.f90 is an export of the library and
     every k-array it hands over exists in the layout header."""
